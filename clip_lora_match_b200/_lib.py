@@ -1,0 +1,117 @@
+"""ctypes binding of libclm_b200.so — the C-ABI declared in include/clm_b200.h.
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, the
+caller gets an exception.  torch is used only to hold device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional
+
+LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libclm_b200.so"
+
+EPI_NONE = 0
+EPI_QUICKGELU = 1
+OUT_BF16 = 0
+OUT_F32 = 1
+
+
+class ClmError(RuntimeError):
+    pass
+
+
+class TowerConfig(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("width", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32),
+        ("mlp", C.c_int32), ("proj_dim", C.c_int32), ("tokens", C.c_int32), ("image", C.c_int32),
+        ("patch", C.c_int32), ("vocab", C.c_int32), ("eos_id", C.c_int32),
+        ("lora_cols_qkv", C.c_int32), ("lora_cols_out", C.c_int32), ("ln_eps", C.c_float),
+    ]
+
+
+_LAYER_FIELDS = [
+    "ln1_g", "ln1_b", "w_qkv", "b_qkv", "lora_a_qkv", "lora_b_qkv", "w_o", "b_o", "lora_a_o",
+    "lora_b_o", "ln2_g", "ln2_b", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
+]
+_TOWER_FIELDS = [
+    "patch_w", "class_emb", "pre_ln_g", "pre_ln_b", "tok_emb", "pos_emb", "final_ln_g",
+    "final_ln_b", "proj_w",
+]
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _LAYER_FIELDS]
+
+
+class TowerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _TOWER_FIELDS]
+
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+
+# name -> (restype, argtypes); mirrors include/clm_b200.h one to one
+SIGNATURES = {
+    "clm_last_error": (C.c_char_p, []),
+    "clm_version": (_I, []),
+    "clm_device_check": (_I, []),
+    "clm_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
+    "clm_l2norm": (_I, [_P, _P, _P, _I, _I, _P]),
+    "clm_embed_text": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "clm_patch_im2col": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "clm_vision_embed_ln": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "clm_pool_ln": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "clm_gemm_epi": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _P, _P, _I,
+                          _I, _P]),
+    "clm_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "clm_tower_create": (_I, [C.POINTER(TowerConfig), C.POINTER(TowerWeights),
+                              C.POINTER(LayerWeights), C.POINTER(_P)]),
+    "clm_tower_destroy": (None, [_P]),
+    "clm_tower_workspace_bytes": (C.c_size_t, [_P, _I]),
+    "clm_encode_image": (_I, [_P, _P, _I, _P, _I, _P, C.c_size_t, _P]),
+    "clm_encode_text": (_I, [_P, _P, _I, _P, _I, _P, C.c_size_t, _P]),
+    "clm_search_num_splits": (_I, [_I, _I]),
+    "clm_search_topk": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "clm_topk_merge": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, C.c_int64, _P, _P, _P]),
+    "clm_topk_merge_sorted": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises ClmError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ClmError(
+            f"{LIB_PATH} is missing: build it with `python -m clip_lora_match_b200.build` "
+            "(there is no CPU or PyTorch fallback for this path)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().clm_last_error().decode("utf-8", "replace")
+        raise ClmError(f"{what or 'clm call'} failed (rc={rc}): {msg}")
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def cur_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

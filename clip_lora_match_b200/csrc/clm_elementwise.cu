@@ -1,0 +1,312 @@
+// clm_elementwise.cu — the HBM-bound kernels of the encoder: LayerNorm, L2-normalise,
+// token/patch embedding, pooling.  One warp owns one row; rows are read and written with
+// 128-bit accesses that are contiguous across the warp; statistics are fp32 and use the
+// two-pass (mean, then centred variance) form so they track torch's nn.LayerNorm closely.
+#include "clm_common.cuh"
+
+namespace {
+
+using namespace clm;
+
+constexpr int kWarpsPerBlock = 8;
+
+// One row of `NV*128` floats held as NV float4 per lane (lane-interleaved: coalesced).
+template <int NV>
+struct Row {
+  float4 v[NV];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = p4[j * 32 + lane_id()];
+  }
+  __device__ __forceinline__ void add(const float* p) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 a = __ldg(p4 + j * 32 + lane_id());
+      v[j].x += a.x; v[j].y += a.y; v[j].z += a.z; v[j].w += a.w;
+    }
+  }
+  // (x - mean) * rstd * gamma + beta, in place
+  __device__ __forceinline__ void layernorm(const float* gamma, const float* beta, float eps) {
+    constexpr float inv_n = 1.0f / (NV * 128);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    const float mean = warp_sum(s) * inv_n;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 g = __ldg(g4 + j * 32 + lane_id());
+      const float4 b = __ldg(b4 + j * 32 + lane_id());
+      v[j].x = (v[j].x - mean) * rstd * g.x + b.x;
+      v[j].y = (v[j].y - mean) * rstd * g.y + b.y;
+      v[j].z = (v[j].z - mean) * rstd * g.z + b.z;
+      v[j].w = (v[j].w - mean) * rstd * g.w + b.w;
+    }
+  }
+  __device__ __forceinline__ void store_f32(float* p) const {
+    float4* p4 = reinterpret_cast<float4*>(p);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) p4[j * 32 + lane_id()] = v[j];
+  }
+  __device__ __forceinline__ void store_bf16(__nv_bfloat16* p) const {
+    uint2* p2 = reinterpret_cast<uint2*>(p);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      uint2 o;
+      o.x = pack_bf16x2(v[j].x, v[j].y);
+      o.y = pack_bf16x2(v[j].z, v[j].w);
+      p2[j * 32 + lane_id()] = o;
+    }
+  }
+};
+
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows, float eps) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  constexpr int D = NV * 128;
+  Row<NV> r;
+  r.load(x + static_cast<size_t>(row) * D);
+  r.layernorm(gamma, beta, eps);
+  r.store_bf16(y + static_cast<size_t>(row) * D);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+pool_ln_kernel(const float* __restrict__ h, const int32_t* __restrict__ row_idx,
+               const float* __restrict__ gamma, const float* __restrict__ beta,
+               __nv_bfloat16* __restrict__ y, int batch, int tokens, float eps) {
+  const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (b >= batch) return;
+  constexpr int D = NV * 128;
+  const int t = row_idx ? row_idx[b] : 0;
+  Row<NV> r;
+  r.load(h + (static_cast<size_t>(b) * tokens + t) * D);
+  r.layernorm(gamma, beta, eps);
+  r.store_bf16(y + static_cast<size_t>(b) * D);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+vision_embed_ln_kernel(const float* __restrict__ patch_out, const float* __restrict__ class_emb,
+                       const float* __restrict__ pos_emb, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float* __restrict__ h, int batch, int np,
+                       float eps) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int tokens = np + 1;
+  if (row >= batch * tokens) return;
+  constexpr int D = NV * 128;
+  const int b = row / tokens;
+  const int t = row - b * tokens;
+  Row<NV> r;
+  if (t == 0) r.load(class_emb);
+  else r.load(patch_out + (static_cast<size_t>(b) * np + (t - 1)) * D);
+  r.add(pos_emb + static_cast<size_t>(t) * D);
+  r.layernorm(gamma, beta, eps);
+  r.store_f32(h + static_cast<size_t>(row) * D);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+embed_text_kernel(const int32_t* __restrict__ ids, const float* __restrict__ tok_emb,
+                  const float* __restrict__ pos_emb, float* __restrict__ h, int rows, int tokens,
+                  int vocab) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  constexpr int D = NV * 128;
+  const int t = row % tokens;
+  int id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  Row<NV> r;
+  r.load(tok_emb + static_cast<size_t>(id) * D);
+  r.add(pos_emb + static_cast<size_t>(t) * D);
+  r.store_f32(h + static_cast<size_t>(row) * D);
+}
+
+// eos_pos[b] = first t with ids[b,t] == eos_id, else 0 (argmax of an all-zero mask)
+__global__ void eos_pos_kernel(const int32_t* __restrict__ ids, int32_t* __restrict__ eos_pos,
+                               int batch, int tokens, int eos_id) {
+  const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (b >= batch) return;
+  int first = 0x7fffffff;
+  for (int t = lane_id(); t < tokens; t += 32)
+    if (ids[static_cast<size_t>(b) * tokens + t] == eos_id) first = min(first, t);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+  if (lane_id() == 0) eos_pos[b] = (first == 0x7fffffff) ? 0 : first;
+}
+
+// generic-width L2 normalise (dim multiple of 4): warp per row, no epsilon (matches the reference)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+l2norm_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
+              int rows, int dim) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* x4 = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * dim);
+  const int n4 = dim >> 2;
+  float s = 0.f;
+  for (int i = lane_id(); i < n4; i += 32) {
+    const float4 a = x4[i];
+    s += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+  }
+  const float nrm = sqrtf(warp_sum(s));
+  float4* y4 = reinterpret_cast<float4*>(y + static_cast<size_t>(row) * dim);
+  uint2* yb2 = yb ? reinterpret_cast<uint2*>(yb + static_cast<size_t>(row) * dim) : nullptr;
+  for (int i = lane_id(); i < n4; i += 32) {
+    float4 a = x4[i];
+    a.x /= nrm; a.y /= nrm; a.z /= nrm; a.w /= nrm;
+    y4[i] = a;
+    if (yb2) {
+      uint2 o;
+      o.x = pack_bf16x2(a.x, a.y);
+      o.y = pack_bf16x2(a.z, a.w);
+      yb2[i] = o;
+    }
+  }
+}
+
+// im2col for a stride==kernel conv: out[(b*g*g + gy*g + gx), c*P*P + py*P + px] =
+// pix[b, c, gy*P+py, gx*P+px].  One thread produces 8 consecutive output columns (16 B).
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ pix, __nv_bfloat16* __restrict__ out, int batch, int image,
+              int patch, int kpad) {
+  const int grid_w = image / patch;
+  const int k = 3 * patch * patch;
+  const int chunks_per_row = kpad >> 3;
+  const long long total = static_cast<long long>(batch) * grid_w * grid_w * chunks_per_row;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int chunk = static_cast<int>(idx % chunks_per_row);
+  const long long prow = idx / chunks_per_row;
+  const int gx = static_cast<int>(prow % grid_w);
+  const int gy = static_cast<int>((prow / grid_w) % grid_w);
+  const int b = static_cast<int>(prow / (grid_w * grid_w));
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int col = chunk * 8 + i;
+    float val = 0.f;
+    if (col < k) {
+      const int c = col / (patch * patch);
+      const int rem = col - c * patch * patch;
+      const int py = rem / patch;
+      const int px = rem - py * patch;
+      val = pix[((static_cast<size_t>(b) * 3 + c) * image + (gy * patch + py)) * image +
+                (gx * patch + px)];
+    }
+    f[i] = val;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  reinterpret_cast<uint4*>(out)[idx] = o;
+}
+
+inline int blocks_for(int rows) { return (rows + kWarpsPerBlock - 1) / kWarpsPerBlock; }
+
+#define CLM_DISPATCH_DIM(dim, KERNEL_CALL)                                   \
+  switch (dim) {                                                             \
+    case 512: { constexpr int NV = 4; KERNEL_CALL; break; }                  \
+    case 768: { constexpr int NV = 6; KERNEL_CALL; break; }                  \
+    case 1024: { constexpr int NV = 8; KERNEL_CALL; break; }                 \
+    case 256: { constexpr int NV = 2; KERNEL_CALL; break; }                  \
+    case 128: { constexpr int NV = 1; KERNEL_CALL; break; }                  \
+    default:                                                                 \
+      clm_set_error("unsupported width %d (supported: 128,256,512,768,1024)", dim); \
+      return CLM_ERR_UNSUPPORTED;                                            \
+  }
+
+}  // namespace
+
+extern "C" int clm_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                             int rows, int dim, float eps, void* stream) {
+  CLM_REQUIRE(x && gamma && beta && y_bf16 && rows >= 0, "clm_layernorm: bad argument");
+  if (rows == 0) return CLM_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CLM_DISPATCH_DIM(dim, (layernorm_kernel<NV><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
+                            x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), rows, eps)));
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}
+
+extern "C" int clm_l2norm(const float* x, float* y, void* y_bf16_or_null, int rows, int dim,
+                          void* stream) {
+  CLM_REQUIRE(x && y && rows >= 0 && dim > 0 && dim % 4 == 0, "clm_l2norm: bad argument");
+  if (rows == 0) return CLM_OK;
+  l2norm_kernel<<<blocks_for(rows), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, y, static_cast<__nv_bfloat16*>(y_bf16_or_null), rows, dim);
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}
+
+extern "C" int clm_embed_text(const int32_t* ids, const float* tok_emb, const float* pos_emb,
+                              float* h, int32_t* eos_pos, int batch, int tokens, int dim, int vocab,
+                              int eos_id, void* stream) {
+  CLM_REQUIRE(ids && tok_emb && pos_emb && h && batch >= 0 && tokens > 0, "clm_embed_text: bad argument");
+  if (batch == 0) return CLM_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rows = batch * tokens;
+  CLM_DISPATCH_DIM(dim, (embed_text_kernel<NV><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
+                            ids, tok_emb, pos_emb, h, rows, tokens, vocab)));
+  if (eos_pos)
+    eos_pos_kernel<<<blocks_for(batch), kWarpsPerBlock * 32, 0, s>>>(ids, eos_pos, batch, tokens,
+                                                                     eos_id);
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}
+
+extern "C" int clm_patch_im2col(const float* pixel_values, void* patches_bf16, int batch, int image,
+                                int patch, int kpad, void* stream) {
+  CLM_REQUIRE(pixel_values && patches_bf16 && batch >= 0 && patch > 0 && image % patch == 0 &&
+                  kpad % 64 == 0 && kpad >= 3 * patch * patch,
+              "clm_patch_im2col: bad argument");
+  if (batch == 0) return CLM_OK;
+  const int g = image / patch;
+  const long long total = static_cast<long long>(batch) * g * g * (kpad / 8);
+  const int blocks = static_cast<int>((total + 255) / 256);
+  im2col_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pixel_values, static_cast<__nv_bfloat16*>(patches_bf16), batch, image, patch, kpad);
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}
+
+extern "C" int clm_vision_embed_ln(const float* patch_out, const float* class_emb,
+                                   const float* pos_emb, const float* gamma, const float* beta,
+                                   float* h, int batch, int np, int dim, float eps, void* stream) {
+  CLM_REQUIRE(patch_out && class_emb && pos_emb && gamma && beta && h && batch >= 0 && np > 0,
+              "clm_vision_embed_ln: bad argument");
+  if (batch == 0) return CLM_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rows = batch * (np + 1);
+  CLM_DISPATCH_DIM(dim, (vision_embed_ln_kernel<NV><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
+                            patch_out, class_emb, pos_emb, gamma, beta, h, batch, np, eps)));
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}
+
+extern "C" int clm_pool_ln(const float* h, const int32_t* row_idx_or_null, const float* gamma,
+                           const float* beta, void* y_bf16, int batch, int tokens, int dim, float eps,
+                           void* stream) {
+  CLM_REQUIRE(h && gamma && beta && y_bf16 && batch >= 0 && tokens > 0, "clm_pool_ln: bad argument");
+  if (batch == 0) return CLM_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CLM_DISPATCH_DIM(dim, (pool_ln_kernel<NV><<<blocks_for(batch), kWarpsPerBlock * 32, 0, s>>>(
+                            h, row_idx_or_null, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16),
+                            batch, tokens, eps)));
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}

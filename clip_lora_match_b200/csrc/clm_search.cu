@@ -1,0 +1,417 @@
+// clm_search.cu — brute-force cosine top-k over the embedding index.
+//
+// Pass 1 (search_kernel): scores = Q · E^T on tcgen05 from the bf16 shadow of the index.
+//   The mainloop is the same TMA -> smem ring -> tcgen05.mma -> TMEM pipeline as clm_gemm.cu
+//   (128 queries x 256 index rows per accumulator, double buffered).  The epilogue never
+//   writes a score: each epilogue thread owns one query row, streams its 256 scores per tile
+//   out of TMEM and keeps the kc best (score, row) pairs of its work unit in shared memory
+//   (replace-the-minimum list; a running threshold rejects ~all scores with one FMNMX tree
+//   and one compare per 32).  A work unit is (query tile, index split); units are ordered
+//   split-major so the CTAs that run together sweep the SAME index rows and share them in L2:
+//   the index crosses HBM about once per query batch (src/embedding/search.py:96,99 fused).
+//
+// Pass 2 (merge_kernel): per query, select the kc best of splits*kc candidates, re-score them
+//   exactly in fp32 against the fp32 master rows, order by (score desc, id asc), emit top k.
+//   bf16 scores only ever *nominate*; every returned score is an fp32 dot product, which is
+//   what makes the ids match the fp32 reference.
+#include <math.h>
+
+#include "clm_common.cuh"
+
+namespace {
+
+using namespace clm;
+
+constexpr int BM = 128;   // queries per tile
+constexpr int BN = 256;   // index rows per tile
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr int kAccStages = 2;
+constexpr int kABytes = BM * BK * 2;
+constexpr int kBBytes = BN * BK * 2;
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kMaxStages = 4;
+constexpr int kTmemCols = kAccStages * BN;
+
+struct SearchParams {
+  int nq, n, kblocks, q_tiles, splits, tiles_n, kc, stages;
+  float* cand_score;
+  int32_t* cand_id;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
+              SearchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  float* list_sc = reinterpret_cast<float*>(smem + p.stages * kStageBytes);
+  int32_t* list_id = reinterpret_cast<int32_t*>(list_sc + p.kc * BM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(list_id + p.kc * BM);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tmem_full = bars + 2 * kMaxStages;
+  uint64_t* tmem_empty = tmem_full + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_units = p.q_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_e);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int split = u / p.q_tiles;
+        const int q0 = (u % p.q_tiles) * BM;
+        const int t0 = static_cast<int>(static_cast<long long>(split) * p.tiles_n / p.splits);
+        const int t1 = static_cast<int>(static_cast<long long>(split + 1) * p.tiles_n / p.splits);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * kStageBytes;
+            mbar_arrive_expect_tx(&full[stage], kStageBytes);
+            tma_load_2d_hint(sa, &map_q, &full[stage], kb * BK, q0, kEvictLast);
+            tma_load_2d_hint(sa + kABytes, &map_e, &full[stage], kb * BK, t * BN, kEvictFirst);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int split = u / p.q_tiles;
+      const int t0 = static_cast<int>(static_cast<long long>(split) * p.tiles_n / p.splits);
+      const int t1 = static_cast<int>(static_cast<long long>(split + 1) * p.tiles_n / p.splits);
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+            const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16_ss(tmem_d, umma_desc_sw128(a_addr + k * 32, 1024),
+                           umma_desc_sw128(b_addr + k * 32, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);
+            if (kb == p.kblocks - 1) umma_commit(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue: streaming top-kc per query row =================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // query row inside the tile == TMEM lane
+    float* my_sc = list_sc + r;   // element j at my_sc[j * BM]  (lane-contiguous: no conflicts)
+    int32_t* my_id = list_id + r;
+    const int kc = p.kc;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int split = u / p.q_tiles;
+      const int q0 = (u % p.q_tiles) * BM;
+      const int t0 = static_cast<int>(static_cast<long long>(split) * p.tiles_n / p.splits);
+      const int t1 = static_cast<int>(static_cast<long long>(split + 1) * p.tiles_n / p.splits);
+      int cnt = 0;
+      int minpos = 0;
+      float thr = -INFINITY;
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(acc * BN);
+        const int row0 = t * BN;
+        const bool ragged = row0 + BN > p.n;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int base = row0 + c * 32;
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (base + i >= p.n) v[i] = 0xff800000u;  // -inf: rows past the end never win
+          }
+          float cmax = __uint_as_float(v[0]);
+#pragma unroll
+          for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, __uint_as_float(v[i]));
+          if (cmax > thr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float s = __uint_as_float(v[i]);
+              if (s > thr) {
+                int slot = minpos;
+                if (cnt < kc) slot = cnt++;
+                my_sc[slot * BM] = s;
+                my_id[slot * BM] = base + i;
+                if (cnt == kc) {
+                  float m = my_sc[0];
+                  int mp = 0;
+                  for (int j = 1; j < kc; ++j) {
+                    const float x = my_sc[j * BM];
+                    if (x < m) { m = x; mp = j; }
+                  }
+                  thr = m;
+                  minpos = mp;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+      // flush this unit's list: [query][split][kc], padded with (-inf, -1)
+      const int qrow = q0 + r;
+      if (qrow < p.nq) {
+        const size_t o = (static_cast<size_t>(qrow) * p.splits + split) * kc;
+        for (int j = 0; j < kc; ++j) {
+          const bool ok = j < cnt;
+          p.cand_score[o + j] = ok ? my_sc[j * BM] : -INFINITY;
+          p.cand_id[o + j] = ok ? my_id[j * BM] : -1;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// -----------------------------------------------------------------------------------------
+// merge / re-score
+// -----------------------------------------------------------------------------------------
+constexpr int kMergeThreads = 128;
+constexpr int kMaxKc = 64;
+
+// (score, id) ordering of torch.topk(largest=True) with a deterministic tie rule: lower id wins
+__device__ __forceinline__ bool better(float sa, long long ia, float sb, long long ib) {
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+// One block per query.  in: [lists*kc] candidates (id < 0 = empty).  Picks the `keep` best by
+// input score (block arg-max, repeated), optionally re-scores them in fp32, ranks, writes top k.
+template <typename IdT>
+__global__ void __launch_bounds__(kMergeThreads)
+merge_kernel(const float* __restrict__ in_score, const IdT* __restrict__ in_id, int total, int keep,
+             const float* __restrict__ q_f32, const float* __restrict__ index_f32, int dim, int k,
+             long long id_offset, float* __restrict__ out_score, long long* __restrict__ out_id) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  float* sc = reinterpret_cast<float*>(msm);                 // [total]
+  long long* sel_id = reinterpret_cast<long long*>(sc + ((total + 1) & ~1));  // [kMaxKc]
+  float* sel_sc = reinterpret_cast<float*>(sel_id + kMaxKc);  // [kMaxKc]
+  __shared__ float red_s[kMergeThreads / 32];
+  __shared__ int red_i[kMergeThreads / 32];
+  __shared__ int winner;
+
+  const int qi = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* qs = in_score + static_cast<size_t>(qi) * total;
+  const IdT* qid = in_id + static_cast<size_t>(qi) * total;
+  for (int i = tid; i < total; i += kMergeThreads) sc[i] = (qid[i] < 0) ? -INFINITY : qs[i];
+  __syncthreads();
+
+  int nsel = 0;
+  for (int round = 0; round < keep; ++round) {
+    float bs = -INFINITY;
+    int bi = -1;
+    for (int i = tid; i < total; i += kMergeThreads) {
+      const float s = sc[i];
+      if (s == -INFINITY) continue;  // empty slot or already selected
+      if (bi < 0 || s > bs || (s == bs && qid[i] < qid[bi])) { bs = s; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || os > bs || (os == bs && qid[oi] < qid[bi]))) { bs = os; bi = oi; }
+    }
+    if ((tid & 31) == 0) { red_s[tid >> 5] = bs; red_i[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      float ws = red_s[0];
+      int wi = red_i[0];
+      for (int w = 1; w < kMergeThreads / 32; ++w) {
+        const float os = red_s[w];
+        const int oi = red_i[w];
+        if (oi >= 0 && (wi < 0 || os > ws || (os == ws && qid[oi] < qid[wi]))) { ws = os; wi = oi; }
+      }
+      winner = wi;
+      if (wi >= 0) {
+        sel_id[round] = static_cast<long long>(qid[wi]);
+        sel_sc[round] = ws;
+        sc[wi] = -INFINITY;
+      }
+    }
+    __syncthreads();
+    if (winner < 0) break;
+    nsel = round + 1;
+  }
+  __syncthreads();
+
+  // exact fp32 re-score: one warp per candidate
+  if (index_f32 != nullptr) {
+    const float4* q4 = reinterpret_cast<const float4*>(q_f32 + static_cast<size_t>(qi) * dim);
+    const int n4 = dim >> 2;
+    for (int cnd = (tid >> 5); cnd < nsel; cnd += kMergeThreads / 32) {
+      const float4* e4 =
+          reinterpret_cast<const float4*>(index_f32 + static_cast<size_t>(sel_id[cnd]) * dim);
+      float s = 0.f;
+      for (int i = (tid & 31); i < n4; i += 32) {
+        const float4 a = q4[i];
+        const float4 e = __ldg(e4 + i);
+        s = fmaf(a.x, e.x, s); s = fmaf(a.y, e.y, s); s = fmaf(a.z, e.z, s); s = fmaf(a.w, e.w, s);
+      }
+      s = warp_sum(s);
+      if ((tid & 31) == 0) sel_sc[cnd] = s;
+    }
+    __syncthreads();
+  }
+
+  // rank by (score desc, id asc); nsel <= 64 so a counting rank is cheapest
+  if (tid < nsel) {
+    const float s = sel_sc[tid];
+    const long long id = sel_id[tid];
+    int rank = 0;
+    for (int j = 0; j < nsel; ++j)
+      if (j != tid && better(sel_sc[j], sel_id[j], s, id)) ++rank;
+    if (rank < k) {
+      out_score[static_cast<size_t>(qi) * k + rank] = s;
+      out_id[static_cast<size_t>(qi) * k + rank] = id + id_offset;
+    }
+  }
+  // fewer than k candidates (tiny index): pad
+  for (int j = nsel + tid; j < k; j += kMergeThreads) {
+    out_score[static_cast<size_t>(qi) * k + j] = -INFINITY;
+    out_id[static_cast<size_t>(qi) * k + j] = -1;
+  }
+}
+
+template <typename IdT>
+int launch_merge(const float* in_score, const IdT* in_id, int nq, int total, int keep,
+                 const float* q_f32, const float* index_f32, int dim, int k, long long id_offset,
+                 float* out_score, long long* out_id, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>((total + 1) & ~1) * 4 + kMaxKc * 8 + kMaxKc * 4;
+  CLM_REQUIRE(smem <= 200 * 1024, "topk merge: %d candidates per query exceed shared memory", total);
+  if (smem > 48 * 1024)
+    CLM_CUDA_CHECK(cudaFuncSetAttribute(merge_kernel<IdT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+  merge_kernel<IdT><<<nq, kMergeThreads, smem, s>>>(in_score, in_id, total, keep, q_f32, index_f32,
+                                                    dim, k, id_offset, out_score, out_id);
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}
+
+int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+
+}  // namespace
+
+extern "C" int clm_search_num_splits(int num_queries, int num_rows) {
+  if (num_queries <= 0 || num_rows <= 0) return 1;
+  const int q_tiles = (num_queries + BM - 1) / BM;
+  const int tiles_n = (num_rows + BN - 1) / BN;
+  const int sms = clm_num_sms();
+  int splits = sms / gcd_int(q_tiles, sms);  // q_tiles*splits is a multiple of the SM count
+  if (splits > tiles_n) splits = tiles_n;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int nq, int n, int dim,
+                               int kc, int splits, float* cand_score, int32_t* cand_id, void* stream) {
+  CLM_REQUIRE(q_bf16 && index_bf16 && cand_score && cand_id, "clm_search_topk: null argument");
+  CLM_REQUIRE(nq > 0 && n > 0 && dim > 0 && dim % 8 == 0, "clm_search_topk: bad shape nq=%d n=%d dim=%d",
+              nq, n, dim);
+  CLM_REQUIRE(kc >= 1 && kc <= kMaxKc, "clm_search_topk: kc=%d must be in [1,%d]", kc, kMaxKc);
+  const int q_tiles = (nq + BM - 1) / BM;
+  const int tiles_n = (n + BN - 1) / BN;
+  CLM_REQUIRE(splits >= 1 && splits <= tiles_n, "clm_search_topk: splits=%d must be in [1,%d]", splits,
+              tiles_n);
+  CUtensorMap mq, me;
+  int rc;
+  if ((rc = clm_make_tmap_bf16_2d(&mq, q_bf16, nq, dim, dim, BK, BM))) return rc;
+  if ((rc = clm_make_tmap_bf16_2d(&me, index_bf16, n, dim, dim, BK, BN))) return rc;
+  SearchParams p;
+  p.nq = nq;
+  p.n = n;
+  p.kblocks = (dim + BK - 1) / BK;
+  p.q_tiles = q_tiles;
+  p.splits = splits;
+  p.tiles_n = tiles_n;
+  p.kc = kc;
+  p.stages = kc <= 32 ? 4 : 3;
+  p.cand_score = cand_score;
+  p.cand_id = cand_id;
+  const int smem = p.stages * kStageBytes + kc * BM * 8 + 256 + 1024;
+  CLM_CUDA_CHECK(cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const long long units = static_cast<long long>(q_tiles) * splits;
+  const int grid = units < clm_num_sms() ? static_cast<int>(units) : clm_num_sms();
+  search_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(mq, me, p);
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}
+
+extern "C" int clm_topk_merge(const float* cand_score, const int32_t* cand_id, int nq, int lists, int kc,
+                              const float* q_f32, const float* index_f32, int dim, int k,
+                              int64_t id_offset, float* out_score, int64_t* out_id, void* stream) {
+  CLM_REQUIRE(cand_score && cand_id && out_score && out_id, "clm_topk_merge: null argument");
+  CLM_REQUIRE(nq > 0 && lists > 0 && kc >= 1 && kc <= kMaxKc && k >= 1 && k <= kc,
+              "clm_topk_merge: bad sizes nq=%d lists=%d kc=%d k=%d", nq, lists, kc, k);
+  CLM_REQUIRE(index_f32 == nullptr || (q_f32 != nullptr && dim % 4 == 0),
+              "clm_topk_merge: re-scoring needs fp32 queries and dim %% 4 == 0");
+  return launch_merge<int32_t>(cand_score, cand_id, nq, lists * kc, kc, q_f32, index_f32, dim, k,
+                               static_cast<long long>(id_offset), out_score,
+                               reinterpret_cast<long long*>(out_id), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int clm_topk_merge_sorted(const float* in_score, const int64_t* in_id, int nq, int lists,
+                                     int k, float* out_score, int64_t* out_id, void* stream) {
+  CLM_REQUIRE(in_score && in_id && out_score && out_id, "clm_topk_merge_sorted: null argument");
+  CLM_REQUIRE(nq > 0 && lists > 0 && k >= 1 && k <= kMaxKc, "clm_topk_merge_sorted: bad sizes");
+  return launch_merge<long long>(in_score, reinterpret_cast<const long long*>(in_id), nq, lists * k, k,
+                                 nullptr, nullptr, 0, k, 0, out_score,
+                                 reinterpret_cast<long long*>(out_id), static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,128 @@
+"""Thin torch-tensor front end over the C-ABI (one function per entry point).
+
+Every function checks dtypes/contiguity, allocates the output with torch (the caller owns it)
+and calls straight into libclm_b200.so on the current CUDA stream.  No arithmetic happens in
+Python; if the library is missing these raise (see _lib.load).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EPI_NONE, EPI_QUICKGELU, OUT_BF16, OUT_F32, check, cur_stream, ptr
+
+
+def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    _req(x, torch.float32, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    rows, dim = x.shape
+    y = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().clm_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(y), rows, dim, eps, cur_stream()),
+          "clm_layernorm")
+    return y
+
+
+def l2norm(x: torch.Tensor, want_bf16: bool = False):
+    _req(x, torch.float32, "x")
+    rows, dim = x.shape
+    y = torch.empty_like(x)
+    yb = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    check(_lib.load().clm_l2norm(ptr(x), ptr(y), ptr(yb), rows, dim, cur_stream()), "clm_l2norm")
+    return (y, yb) if want_bf16 else y
+
+
+def gemm_epi(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+             residual: Optional[torch.Tensor] = None, act: int = EPI_NONE,
+             out_dtype: torch.dtype = torch.bfloat16, a2: Optional[torch.Tensor] = None,
+             w2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act(a @ w.T (+ a2 @ w2.T) + bias) (+ residual);  a [M,K], w [N,K] bf16."""
+    _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N, K2w = w.shape
+    if K2w != K:
+        raise ValueError(f"a is [*, {K}] but w is [*, {K2w}]")
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+    if residual is not None:
+        _req(residual, torch.float32, "residual")
+    k2 = 0
+    if a2 is not None:
+        _req(a2, torch.bfloat16, "a2"); _req(w2, torch.bfloat16, "w2")
+        k2 = a2.shape[1]
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    od = OUT_F32 if out.dtype == torch.float32 else OUT_BF16
+    check(_lib.load().clm_gemm_epi(
+        ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K,
+        ptr(a2), a2.stride(0) if a2 is not None else 0, ptr(w2), w2.stride(0) if w2 is not None else 0, k2,
+        ptr(out), out.stride(0), od, ptr(bias), ptr(residual),
+        residual.stride(0) if residual is not None else 0, act, cur_stream()), "clm_gemm_epi")
+    return out
+
+
+def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, causal: bool) -> torch.Tensor:
+    _req(qkv, torch.bfloat16, "qkv")
+    dim = heads * 64
+    if tuple(qkv.shape) != (batch * tokens, 3 * dim):
+        raise ValueError(f"qkv must be [{batch * tokens}, {3 * dim}], got {tuple(qkv.shape)}")
+    out = torch.empty((batch * tokens, dim), dtype=torch.bfloat16, device=qkv.device)
+    check(_lib.load().clm_attention(ptr(qkv), ptr(out), batch, tokens, heads, int(causal), cur_stream()),
+          "clm_attention")
+    return out
+
+
+def search_topk(q_f32: torch.Tensor, q_bf16: torch.Tensor, index_bf16: torch.Tensor,
+                index_f32: Optional[torch.Tensor], k: int, id_offset: int = 0,
+                margin: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Top-k of q @ index.T: bf16 tensor-core scan + fused per-tile top-kc, then fp32 re-score.
+
+    Returns (scores fp32 [Q,k], ids int64 [Q,k]) sorted descending; ids are global
+    (id_offset added).  k must be <= rows of the index shard (the caller clamps, as the
+    reference does at src/embedding/search.py:98)."""
+    _req(q_f32, torch.float32, "q_f32"); _req(q_bf16, torch.bfloat16, "q_bf16")
+    _req(index_bf16, torch.bfloat16, "index_bf16")
+    if index_f32 is not None:
+        _req(index_f32, torch.float32, "index_f32")
+    nq, dim = q_bf16.shape
+    n = index_bf16.shape[0]
+    if not (1 <= k <= 64):
+        raise ValueError("k must be in [1, 64]")
+    if margin is None:
+        margin = 6 if index_f32 is not None else 0
+    kc = min(64, max(k + margin, min(16, n)))
+    kc = max(k, min(kc, 64))
+    lib = _lib.load()
+    splits = lib.clm_search_num_splits(nq, n)
+    cand_s = torch.empty((nq, splits, kc), dtype=torch.float32, device=q_bf16.device)
+    cand_i = torch.empty((nq, splits, kc), dtype=torch.int32, device=q_bf16.device)
+    check(lib.clm_search_topk(ptr(q_bf16), ptr(index_bf16), nq, n, dim, kc, splits, ptr(cand_s),
+                              ptr(cand_i), cur_stream()), "clm_search_topk")
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=q_bf16.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=q_bf16.device)
+    check(lib.clm_topk_merge(ptr(cand_s), ptr(cand_i), nq, splits, kc, ptr(q_f32), ptr(index_f32), dim,
+                             k, id_offset, ptr(out_s), ptr(out_i), cur_stream()), "clm_topk_merge")
+    return out_s, out_i
+
+
+def topk_merge_sorted(scores: torch.Tensor, ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge [Q, lists, k] sorted per-shard results into the global top-k."""
+    _req(scores, torch.float32, "scores"); _req(ids, torch.int64, "ids")
+    nq, lists, kk = scores.shape
+    if kk != k:
+        raise ValueError("last dim must equal k")
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=scores.device)
+    check(_lib.load().clm_topk_merge_sorted(ptr(scores), ptr(ids), nq, lists, k, ptr(out_s), ptr(out_i),
+                                            cur_stream()), "clm_topk_merge_sorted")
+    return out_s, out_i

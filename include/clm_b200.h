@@ -1,0 +1,210 @@
+/* clm_b200.h — C-ABI of the B200-native CLIP+LoRA retrieval hot path.
+ *
+ * This is the drop-in boundary.  The reference (youngalip/clip-lora-match) has no FFI
+ * of its own: its hot path is plain Python that calls transformers / peft / torch
+ * (SURVEY.md §8b).  Each entry point below therefore cites the reference *call site*
+ * whose arithmetic it replaces.  The Python wrappers in clip_lora_match_b200/ bind
+ * these with ctypes (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns every buffer; the library allocates nothing after *_create;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - bf16 buffers are raw uint16 storage (__nv_bfloat16);
+ *   - return value 0 = ok, non-zero = error (clm_last_error() gives the text);
+ *   - all functions are stream-ordered and re-entrant (no global mutable state except
+ *     the thread-local last-error string).
+ */
+#ifndef CLM_B200_H
+#define CLM_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLM_OK 0
+#define CLM_ERR_INVALID 1
+#define CLM_ERR_CUDA 2
+#define CLM_ERR_UNSUPPORTED 3
+
+/* epilogue selector for clm_gemm_epi (bit flags) */
+#define CLM_EPI_NONE 0
+#define CLM_EPI_QUICKGELU 1 /* x * sigmoid(1.702 x); transformers/activations.py QuickGELU */
+#define CLM_OUT_BF16 0
+#define CLM_OUT_F32 1
+
+const char* clm_last_error(void);
+int clm_version(void);
+/* 0 when a CUDA device of compute capability 10.x is usable, error otherwise. */
+int clm_device_check(void);
+
+/* ------------------------------------------------------------------------------------
+ * Elementwise / normalisation kernels (HBM-bound; warp-shuffle, 128-bit access)
+ * ---------------------------------------------------------------------------------- */
+
+/* nn.LayerNorm(eps) over the last dim: y = (x-mean)/sqrt(var+eps)*gamma+beta.
+ * Replaces transformers modeling_clip.py:359,361,562,677,686 as reached from
+ * models/clip_model.py:115,144.  x fp32 [rows, dim] (the fp32 residual stream),
+ * y bf16 [rows, dim] (the next GEMM's operand).  dim in {512, 768, 1024}. */
+int clm_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                  int rows, int dim, float eps, void* stream);
+
+/* Row L2 normalisation, no epsilon: x / ||x||  (models/clip_model.py:116,148;
+ * src/embedding/search.py:68,93).  fp32 in, fp32 out (may alias), optional bf16 copy. */
+int clm_l2norm(const float* x, float* y, void* y_bf16_or_null, int rows, int dim, void* stream);
+
+/* Text embeddings: h[b,t,:] = tok_emb[ids[b,t]] + pos_emb[t]  (modeling_clip.py:249-256).
+ * ids int32 [batch, tokens]; tables fp32; h fp32 [batch*tokens, dim].
+ * Also writes eos_pos[b] = first t with ids[b,t] == eos_id (0 if none), the pooling
+ * row of modeling_clip.py:577-584. */
+int clm_embed_text(const int32_t* ids, const float* tok_emb, const float* pos_emb, float* h,
+                   int32_t* eos_pos, int batch, int tokens, int dim, int vocab, int eos_id,
+                   void* stream);
+
+/* Patch extraction (the im2col view of nn.Conv2d(stride=patch, bias=False),
+ * modeling_clip.py:148-154,208-209).  pixel_values fp32 [batch,3,image,image] ->
+ * patches bf16 [batch*grid*grid, kpad] with column order (c, py, px), zero padded to
+ * kpad (multiple of 64). */
+int clm_patch_im2col(const float* pixel_values, void* patches_bf16, int batch, int image,
+                     int patch, int kpad, void* stream);
+
+/* Vision embeddings + pre_layrnorm (modeling_clip.py:202-219, 677):
+ * h[b,0,:] = LN(class_emb + pos[0]); h[b,1+p,:] = LN(patch_out[b*np+p,:] + pos[1+p]).
+ * patch_out fp32 [batch*np, dim]; h fp32 [batch*(np+1), dim]. */
+int clm_vision_embed_ln(const float* patch_out, const float* class_emb, const float* pos_emb,
+                        const float* gamma, const float* beta, float* h, int batch, int np,
+                        int dim, float eps, void* stream);
+
+/* Pooling: y[b,:] = LN(h[b*tokens + (row_idx ? row_idx[b] : 0), :])  -> bf16 [batch, dim]
+ * (modeling_clip.py:685-686 CLS + post_layernorm; :562,577-584 final_layer_norm + EOS row). */
+int clm_pool_ln(const float* h, const int32_t* row_idx_or_null, const float* gamma,
+                const float* beta, void* y_bf16, int batch, int tokens, int dim, float eps,
+                void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * tcgen05 / TMEM GEMM fed by TMA, with fused epilogue
+ * ---------------------------------------------------------------------------------- */
+
+/* out[M,N] = epi( A[M,K]·W[N,K]^T  (+ A2[M,K2]·W2[N,K2]^T)  + bias ) (+ residual)
+ * A, W, A2, W2 bf16 row-major with leading dims lda.. (elements; multiples of 8);
+ * K and K2 are padded by the hardware (TMA zero fill) to multiples of 64.
+ * nn.Linear of modeling_clip.py:295-298,310-312,334 (q/k/v/out), :344-350 (fc1+QuickGELU,
+ * fc2), :822-823,860-861 (projections).  The (A2,W2) pair is the unmerged PEFT LoRA
+ * update y += (x A^T) (s B)^T  (models/lora_adapter.py:35-42; Appendix B of SURVEY.md)
+ * folded in as a K-extension of the same accumulator.
+ * bias fp32 [N] or NULL; residual fp32 [M, ldr] or NULL (added after the activation);
+ * out is bf16 or fp32 per out_dtype; out may alias residual. */
+int clm_gemm_epi(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                 const void* A2, int lda2, const void* W2, int ldw2, int K2,
+                 void* out, int ldo, int out_dtype, const float* bias,
+                 const float* residual, int ldr, int epilogue, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fused attention (tcgen05: S=QK^T in TMEM, fp32 softmax in registers, O=PV)
+ * ---------------------------------------------------------------------------------- */
+
+/* qkv bf16 [batch*tokens, 3*dim] (q | k | v, head h at columns h*64..h*64+63 of each
+ * third); out bf16 [batch*tokens, dim].  softmax(q k^T / sqrt(64) + mask) v with the
+ * softmax in fp32 (modeling_clip.py:261-279); causal != 0 applies the text tower's
+ * causal mask (modeling_clip.py:546-557).  head_dim is 64 for every CLIP ViT. */
+int clm_attention(const void* qkv_bf16, void* out_bf16, int batch, int tokens, int heads,
+                  int causal, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Whole-tower convenience (what models/clip_model.py encode_image / encode_text run)
+ * ---------------------------------------------------------------------------------- */
+
+typedef struct clm_tower clm_tower; /* opaque */
+
+typedef struct {
+  int32_t kind;   /* 0 = vision, 1 = text */
+  int32_t width;  /* D */
+  int32_t layers;
+  int32_t heads;
+  int32_t mlp;      /* intermediate size */
+  int32_t proj_dim; /* P */
+  int32_t tokens;   /* vision: 1 + (image/patch)^2 ; text: context length (77) */
+  int32_t image;    /* vision only */
+  int32_t patch;    /* vision only */
+  int32_t vocab;    /* text only */
+  int32_t eos_id;   /* text only */
+  int32_t lora_cols_qkv; /* 0 or 64: padded total LoRA rank folded into the fused QKV GEMM */
+  int32_t lora_cols_out; /* 0 or 64: same for out_proj */
+  float ln_eps;
+} clm_tower_config;
+
+/* Per-layer device pointers.  Weights bf16 [out,in]; biases / LN params fp32. */
+typedef struct {
+  const float* ln1_g; const float* ln1_b;
+  const void* w_qkv; const float* b_qkv;       /* [3D, D], [3D] */
+  const void* lora_a_qkv; const void* lora_b_qkv; /* [64, D], [3D, 64] or NULL */
+  const void* w_o; const float* b_o;           /* [D, D], [D] */
+  const void* lora_a_o; const void* lora_b_o;  /* [64, D], [D, 64] or NULL */
+  const float* ln2_g; const float* ln2_b;
+  const void* w_fc1; const float* b_fc1;       /* [mlp, D] */
+  const void* w_fc2; const float* b_fc2;       /* [D, mlp] */
+} clm_layer_weights;
+
+typedef struct {
+  /* vision */
+  const void* patch_w;      /* bf16 [D, kpad] conv weight flattened (c,py,px), zero padded */
+  const float* class_emb;   /* [D] */
+  const float* pre_ln_g; const float* pre_ln_b;
+  /* text */
+  const float* tok_emb;     /* fp32 [vocab, D] */
+  /* both */
+  const float* pos_emb;     /* fp32 [tokens, D] */
+  const float* final_ln_g; const float* final_ln_b; /* post_layernorm / final_layer_norm */
+  const void* proj_w;       /* bf16 [P, D] visual_projection / text_projection (no bias) */
+} clm_tower_weights;
+
+int clm_tower_create(const clm_tower_config* cfg, const clm_tower_weights* w,
+                     const clm_layer_weights* layers, clm_tower** out);
+void clm_tower_destroy(clm_tower* t);
+/* bytes of caller-provided device workspace needed for a micro-batch of `batch` items */
+size_t clm_tower_workspace_bytes(const clm_tower* t, int batch);
+
+/* models/clip_model.py:89-118 without the PIL step: pixel_values fp32 [batch,3,H,W]
+ * -> embeddings fp32 [batch, P]; normalize != 0 applies x/||x|| (clip_model.py:116),
+ * normalize == 0 returns the raw projected features (embed_image.py:27 normalize=False). */
+int clm_encode_image(clm_tower* t, const float* pixel_values, int batch, float* out_emb,
+                     int normalize, void* workspace, size_t workspace_bytes, void* stream);
+/* models/clip_model.py:121-150 without the tokenizer: ids int32 [batch, tokens]
+ * (right padded with eos) -> L2-normalised embeddings fp32 [batch, P]. */
+int clm_encode_text(clm_tower* t, const int32_t* ids, int batch, float* out_emb,
+                    int normalize, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Search: similarity GEMM with fused per-tile top-k, merge, exact fp32 re-score
+ * ---------------------------------------------------------------------------------- */
+
+/* Number of index splits (partial candidate lists per query) the scan will use. */
+int clm_search_num_splits(int num_queries, int num_rows);
+
+/* First pass (src/embedding/search.py:96 + :99 fused): scores = Q·E^T on tensor cores
+ * from the bf16 shadow of the index; the score matrix stays in TMEM; every (query,
+ * split) keeps its kc best candidates.  q_bf16 [nq, dim], index_bf16 [n, dim],
+ * cand_score fp32 / cand_id int32 [nq, splits, kc].  dim multiple of 64, kc <= 64. */
+int clm_search_topk(const void* q_bf16, const void* index_bf16, int nq, int n, int dim, int kc,
+                    int splits, float* cand_score, int32_t* cand_id, void* stream);
+
+/* Second pass: per query merge splits*kc candidates to the kc best by first-pass score,
+ * re-score those exactly in fp32 against the fp32 master rows (q_f32·E_f32[id]), sort
+ * descending (ties: lower id first) and emit the top k with id_offset added (the shard's
+ * first global row).  Reproduces torch.topk(largest=True, sorted=True) of search.py:99. */
+int clm_topk_merge(const float* cand_score, const int32_t* cand_id, int nq, int lists, int kc,
+                   const float* q_f32, const float* index_f32, int dim, int k, int64_t id_offset,
+                   float* out_score, int64_t* out_id, void* stream);
+
+/* Cross-shard merge after the allgather: in [nq, lists, k] (score, global id) ->
+ * top k sorted.  No re-scoring (scores are already exact). */
+int clm_topk_merge_sorted(const float* in_score, const int64_t* in_id, int nq, int lists, int k,
+                          float* out_score, int64_t* out_id, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLM_B200_H */

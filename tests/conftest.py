@@ -1,0 +1,24 @@
+"""pytest configuration: registers the `gpu` marker and puts the repo root on sys.path."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def cuda_device():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("test is marked gpu but no CUDA device is visible")
+    from clip_lora_match_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.clm_device_check(), "clm_device_check")
+    return torch.device("cuda:0")

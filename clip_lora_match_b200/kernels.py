@@ -100,8 +100,7 @@ def search_topk(q_f32: torch.Tensor, q_bf16: torch.Tensor, index_bf16: torch.Ten
         raise ValueError("k must be in [1, 64]")
     if margin is None:
         margin = 6 if index_f32 is not None else 0
-    kc = min(64, max(k + margin, min(16, n)))
-    kc = max(k, min(kc, 64))
+    kc = max(k, min(64, max(k + margin, 16)))  # candidates kept per (query, split)
     lib = _lib.load()
     splits = lib.clm_search_num_splits(nq, n)
     cand_s = torch.empty((nq, splits, kc), dtype=torch.float32, device=q_bf16.device)

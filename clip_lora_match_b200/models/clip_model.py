@@ -1,0 +1,525 @@
+"""CLIP + LoRA encoder façade — the B200 mirror of the reference's models/clip_model.py.
+
+Reference surface kept (names, positional order, return types, exceptions):
+  load_clip_model(config_path, use_lora, lora_weights_path) -> (model, processor, device)
+                                                  reference models/clip_model.py:37-82
+  encode_image(image_path, model, processor, device) -> (d,) CPU fp32   reference :89-118
+  encode_text(text, model, processor, device)        -> (d,) CPU fp32   reference :121-150
+Batched extensions (the reference is batch-1 everywhere):
+  B200ClipModel.encode_images(pixel_values) / encode_texts(input_ids) -> [B, d] device fp32.
+
+`model` is a B200ClipModel: it owns bf16/fp32 device copies of the weights and two
+clm_tower handles (include/clm_b200.h); every FLOP of the forward runs in the sm_100a
+kernels of csrc/.  transformers is used only as a weight container (from_pretrained /
+random init of the named architecture) and for the host-side image processor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+import yaml
+
+from .. import _lib
+from .lora_adapter import LoraAdapter, linear_module_paths, load_lora_adapter
+
+LORA_COLS = 64  # padded total LoRA rank folded into one extra K block of the fused GEMMs
+BOS_ID, EOS_ID = 49406, 49407
+
+
+# ------------------------------------------------------------------------------------------
+# architectures
+# ------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class TowerArch:
+    width: int
+    layers: int
+    heads: int
+    mlp: int
+
+
+@dataclass(frozen=True)
+class ClipArch:
+    name: str
+    vision: TowerArch
+    text: TowerArch
+    patch: int
+    proj_dim: int
+    image: int = 224
+    context: int = 77
+    vocab: int = 49408
+    eos_id: int = EOS_ID
+    ln_eps: float = 1e-5
+
+    @property
+    def vision_tokens(self) -> int:
+        return 1 + (self.image // self.patch) ** 2
+
+
+ARCHS: Dict[str, ClipArch] = {
+    "openai/clip-vit-base-patch32": ClipArch(
+        "openai/clip-vit-base-patch32", TowerArch(768, 12, 12, 3072), TowerArch(512, 12, 8, 2048), 32, 512),
+    "openai/clip-vit-base-patch16": ClipArch(
+        "openai/clip-vit-base-patch16", TowerArch(768, 12, 12, 3072), TowerArch(512, 12, 8, 2048), 16, 512),
+    "openai/clip-vit-large-patch14": ClipArch(
+        "openai/clip-vit-large-patch14", TowerArch(1024, 24, 16, 4096), TowerArch(768, 12, 12, 3072), 14, 768),
+}
+
+
+def arch_from_name(name: str) -> ClipArch:
+    if name in ARCHS:
+        return ARCHS[name]
+    raise ValueError(f"unknown CLIP architecture {name!r}; known: {sorted(ARCHS)}")
+
+
+def arch_from_hf_config(cfg, name: str = "custom") -> ClipArch:
+    v, t = cfg.vision_config, cfg.text_config
+    return ClipArch(
+        name=name,
+        vision=TowerArch(v.hidden_size, v.num_hidden_layers, v.num_attention_heads, v.intermediate_size),
+        text=TowerArch(t.hidden_size, t.num_hidden_layers, t.num_attention_heads, t.intermediate_size),
+        patch=v.patch_size, proj_dim=cfg.projection_dim, image=v.image_size,
+        context=t.max_position_embeddings, vocab=t.vocab_size,
+        eos_id=t.eos_token_id if t.eos_token_id is not None else EOS_ID,
+        ln_eps=v.layer_norm_eps)
+
+
+def hf_config_for(arch: ClipArch):
+    """transformers CLIPConfig of the architecture (random-init container and oracle use it)."""
+    from transformers import CLIPConfig
+
+    return CLIPConfig(
+        text_config=dict(hidden_size=arch.text.width, num_hidden_layers=arch.text.layers,
+                         num_attention_heads=arch.text.heads, intermediate_size=arch.text.mlp,
+                         max_position_embeddings=arch.context, vocab_size=arch.vocab,
+                         projection_dim=arch.proj_dim, bos_token_id=BOS_ID, eos_token_id=arch.eos_id,
+                         hidden_act="quick_gelu", layer_norm_eps=arch.ln_eps),
+        vision_config=dict(hidden_size=arch.vision.width, num_hidden_layers=arch.vision.layers,
+                           num_attention_heads=arch.vision.heads, intermediate_size=arch.vision.mlp,
+                           patch_size=arch.patch, image_size=arch.image, projection_dim=arch.proj_dim,
+                           hidden_act="quick_gelu", layer_norm_eps=arch.ln_eps),
+        projection_dim=arch.proj_dim)
+
+
+# ------------------------------------------------------------------------------------------
+# the model object
+# ------------------------------------------------------------------------------------------
+class B200ClipModel:
+    """CLIP dual encoder whose forward is the C-ABI of include/clm_b200.h.
+
+    Quacks like the object the reference passes around (`.eval()`, `.to()`, `.parameters()`,
+    `.get_image_features`, `.get_text_features`) so reference-style callers keep working.
+    """
+
+    def __init__(self, arch: ClipArch, state_dict: Dict[str, torch.Tensor],
+                 lora: Optional[LoraAdapter] = None, device: Union[str, torch.device] = "cuda",
+                 max_workspace_bytes: int = 24 << 30):
+        self.arch = arch
+        self.name = arch.name
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("B200ClipModel needs a CUDA device: the sm_100a path has no CPU fallback")
+        self._lib = _lib.load()
+        _lib.check(self._lib.clm_device_check(), "clm_device_check")
+        self._sd = {k: v.detach().to("cpu", torch.float32) for k, v in state_dict.items()}
+        self.lora: Optional[LoraAdapter] = None
+        self.max_workspace_bytes = max_workspace_bytes
+        self._towers: Dict[str, int] = {}
+        self._keep: Dict[str, list] = {}
+        self._workspace: Optional[torch.Tensor] = None
+        self._dummy = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.set_lora(lora)
+
+    # ---- reference-compat surface ------------------------------------------------------
+    def eval(self):
+        return self
+
+    def to(self, *args, **kwargs):
+        return self
+
+    def parameters(self):
+        # the reference asks `next(model.parameters()).dtype` to cast pixel_values
+        # (models/clip_model.py:111-112); the C-ABI takes fp32 pixel_values.
+        yield self._dummy
+
+    def num_base_parameters(self) -> int:
+        return sum(v.numel() for v in self._sd.values())
+
+    def linear_dims(self) -> Dict[str, Tuple[int, int]]:
+        dims = {}
+        for p in linear_module_paths(self.arch.vision.layers, self.arch.text.layers):
+            w = self._sd.get(p + ".weight")
+            if w is not None:
+                dims[p] = (w.shape[0], w.shape[1])
+        return dims
+
+    # ---- weights -----------------------------------------------------------------------
+    def set_lora(self, lora: Optional[LoraAdapter]) -> None:
+        """(Re)build both towers with the given unmerged adapter (None = base model)."""
+        self._destroy_towers()
+        self.lora = lora
+        for kind in ("vision", "text"):
+            self._build_tower(kind)
+
+    def _dev(self, t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+        return t.to(device=self.device, dtype=dtype).contiguous()
+
+    def _lora_operands(self, prefix: str, width: int, group: List[str]):
+        """Pack the adapters of `group` (module leaves sharing one fused GEMM) into
+        A_cat [64, D] and (s·B)_cat [len(group)*D, 64]; None if no member has LoRA."""
+        if self.lora is None:
+            return None, None
+        present = [(i, m) for i, m in enumerate(group) if f"{prefix}.{m}" in self.lora.weights]
+        if not present:
+            return None, None
+        r = self.lora.config.r
+        if r * len(present) > LORA_COLS:
+            raise NotImplementedError(
+                f"total LoRA rank {r}x{len(present)} on {prefix} exceeds {LORA_COLS} columns")
+        a_cat = torch.zeros((LORA_COLS, width), dtype=torch.float32)
+        b_cat = torch.zeros((len(group) * width, LORA_COLS), dtype=torch.float32)
+        s = self.lora.scaling
+        for slot, (i, m) in enumerate(present):
+            a, b = self.lora.weights[f"{prefix}.{m}"]
+            if tuple(a.shape) != (r, width) or tuple(b.shape) != (width, r):
+                raise ValueError(f"LoRA shape mismatch on {prefix}.{m}: A {tuple(a.shape)} B {tuple(b.shape)}")
+            a_cat[slot * r:(slot + 1) * r] = a
+            b_cat[i * width:(i + 1) * width, slot * r:(slot + 1) * r] = b * s
+        return self._dev(a_cat, torch.bfloat16), self._dev(b_cat, torch.bfloat16)
+
+    def _build_tower(self, kind: str) -> None:
+        arch = self.arch
+        ta = arch.vision if kind == "vision" else arch.text
+        pre = "vision_model" if kind == "vision" else "text_model"
+        sd = self._sd
+        keep: list = []
+
+        def f32(name):
+            t = self._dev(sd[name], torch.float32)
+            keep.append(t)
+            return t.data_ptr()
+
+        def bf16(t):
+            t = self._dev(t, torch.bfloat16)
+            keep.append(t)
+            return t.data_ptr()
+
+        layers = (_lib.LayerWeights * ta.layers)()
+        any_qkv = any_out = False
+        for i in range(ta.layers):
+            lp = f"{pre}.encoder.layers.{i}"
+            ap = f"{lp}.self_attn"
+            L = layers[i]
+            L.ln1_g, L.ln1_b = f32(f"{lp}.layer_norm1.weight"), f32(f"{lp}.layer_norm1.bias")
+            L.ln2_g, L.ln2_b = f32(f"{lp}.layer_norm2.weight"), f32(f"{lp}.layer_norm2.bias")
+            L.w_qkv = bf16(torch.cat([sd[f"{ap}.q_proj.weight"], sd[f"{ap}.k_proj.weight"],
+                                      sd[f"{ap}.v_proj.weight"]], dim=0))
+            bq = self._dev(torch.cat([sd[f"{ap}.q_proj.bias"], sd[f"{ap}.k_proj.bias"],
+                                      sd[f"{ap}.v_proj.bias"]], dim=0), torch.float32)
+            keep.append(bq)
+            L.b_qkv = bq.data_ptr()
+            a_cat, b_cat = self._lora_operands(ap, ta.width, ["q_proj", "k_proj", "v_proj"])
+            if a_cat is not None:
+                keep += [a_cat, b_cat]
+                L.lora_a_qkv, L.lora_b_qkv = a_cat.data_ptr(), b_cat.data_ptr()
+                any_qkv = True
+            L.w_o, L.b_o = bf16(sd[f"{ap}.out_proj.weight"]), f32(f"{ap}.out_proj.bias")
+            a_o, b_o = self._lora_operands(ap, ta.width, ["out_proj"])
+            if a_o is not None:
+                keep += [a_o, b_o]
+                L.lora_a_o, L.lora_b_o = a_o.data_ptr(), b_o.data_ptr()
+                any_out = True
+            L.w_fc1, L.b_fc1 = bf16(sd[f"{lp}.mlp.fc1.weight"]), f32(f"{lp}.mlp.fc1.bias")
+            L.w_fc2, L.b_fc2 = bf16(sd[f"{lp}.mlp.fc2.weight"]), f32(f"{lp}.mlp.fc2.bias")
+
+        w = _lib.TowerWeights()
+        cfg = _lib.TowerConfig()
+        cfg.width, cfg.layers, cfg.heads, cfg.mlp = ta.width, ta.layers, ta.heads, ta.mlp
+        cfg.proj_dim, cfg.ln_eps = arch.proj_dim, arch.ln_eps
+        cfg.lora_cols_qkv = LORA_COLS if any_qkv else 0
+        cfg.lora_cols_out = LORA_COLS if any_out else 0
+        w.pos_emb = f32(f"{pre}.embeddings.position_embedding.weight")
+        if kind == "vision":
+            cfg.kind, cfg.tokens, cfg.image, cfg.patch = 0, arch.vision_tokens, arch.image, arch.patch
+            k = 3 * arch.patch * arch.patch
+            kpad = (k + 63) // 64 * 64
+            pw = torch.zeros((ta.width, kpad), dtype=torch.float32)
+            pw[:, :k] = sd[f"{pre}.embeddings.patch_embedding.weight"].reshape(ta.width, k)
+            w.patch_w = bf16(pw)
+            w.class_emb = f32(f"{pre}.embeddings.class_embedding")
+            w.pre_ln_g, w.pre_ln_b = f32(f"{pre}.pre_layrnorm.weight"), f32(f"{pre}.pre_layrnorm.bias")
+            w.final_ln_g, w.final_ln_b = f32(f"{pre}.post_layernorm.weight"), f32(f"{pre}.post_layernorm.bias")
+            w.proj_w = bf16(sd["visual_projection.weight"])
+        else:
+            cfg.kind, cfg.tokens, cfg.vocab, cfg.eos_id = 1, arch.context, arch.vocab, arch.eos_id
+            w.tok_emb = f32(f"{pre}.embeddings.token_embedding.weight")
+            w.final_ln_g, w.final_ln_b = f32(f"{pre}.final_layer_norm.weight"), f32(f"{pre}.final_layer_norm.bias")
+            w.proj_w = bf16(sd["text_projection.weight"])
+        handle = C.c_void_p()
+        _lib.check(self._lib.clm_tower_create(C.byref(cfg), C.byref(w), layers, C.byref(handle)),
+                   f"clm_tower_create({kind})")
+        self._towers[kind] = handle.value
+        self._keep[kind] = keep
+
+    def _destroy_towers(self) -> None:
+        for h in self._towers.values():
+            self._lib.clm_tower_destroy(h)
+        self._towers.clear()
+        self._keep.clear()
+
+    def __del__(self):
+        try:
+            self._destroy_towers()
+        except Exception:
+            pass
+
+    # ---- forward -----------------------------------------------------------------------
+    def _ensure_workspace(self, kind: str, batch: int) -> torch.Tensor:
+        need = self._lib.clm_tower_workspace_bytes(self._towers[kind], batch)
+        one = self._lib.clm_tower_workspace_bytes(self._towers[kind], 1)
+        want = max(one, min(need, self.max_workspace_bytes))
+        if self._workspace is None or self._workspace.numel() < want:
+            self._workspace = None
+            self._workspace = torch.empty(want, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def encode_images(self, pixel_values: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+        """[B,3,H,W] fp32 (any device) -> [B, proj_dim] fp32 on the GPU; the batched form of
+        reference encode_image (models/clip_model.py:107-116)."""
+        a = self.arch
+        if pixel_values.dim() != 4 or tuple(pixel_values.shape[1:]) != (3, a.image, a.image):
+            raise ValueError(f"pixel_values must be [B,3,{a.image},{a.image}], got {tuple(pixel_values.shape)}")
+        pv = pixel_values.to(device=self.device, dtype=torch.float32).contiguous()
+        b = pv.shape[0]
+        out = torch.empty((b, a.proj_dim), dtype=torch.float32, device=self.device)
+        if b == 0:
+            return out
+        ws = self._ensure_workspace("vision", b)
+        _lib.check(self._lib.clm_encode_image(self._towers["vision"], pv.data_ptr(), b, out.data_ptr(),
+                                              int(normalize), ws.data_ptr(), ws.numel(), _lib.cur_stream()),
+                   "clm_encode_image")
+        return out
+
+    def encode_texts(self, input_ids: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+        """[B, L<=77] int (right padded or not) -> [B, proj_dim] fp32 on the GPU.  Rows are padded
+        to the context length with EOS (the pooled EOS row of a causal tower does not see the
+        padding: SURVEY.md §8a, encode_text row)."""
+        a = self.arch
+        if input_ids.dim() != 2 or input_ids.shape[1] > a.context:
+            raise ValueError(f"input_ids must be [B, L<={a.context}], got {tuple(input_ids.shape)}")
+        ids = input_ids.to(device=self.device, dtype=torch.int32)
+        b, l = ids.shape
+        if l < a.context:
+            pad = torch.full((b, a.context - l), a.eos_id, dtype=torch.int32, device=self.device)
+            ids = torch.cat([ids, pad], dim=1)
+        ids = ids.contiguous()
+        out = torch.empty((b, a.proj_dim), dtype=torch.float32, device=self.device)
+        if b == 0:
+            return out
+        ws = self._ensure_workspace("text", b)
+        _lib.check(self._lib.clm_encode_text(self._towers["text"], ids.data_ptr(), b, out.data_ptr(),
+                                             int(normalize), ws.data_ptr(), ws.numel(), _lib.cur_stream()),
+                   "clm_encode_text")
+        return out
+
+    # transformers-4.x style accessors used by the reference (tensor in, tensor out)
+    def get_image_features(self, pixel_values: torch.Tensor, **_) -> torch.Tensor:
+        return self.encode_images(pixel_values, normalize=False)
+
+    def get_text_features(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                          **_) -> torch.Tensor:
+        if attention_mask is not None:
+            # positions masked out are padding: replace by EOS so the first-EOS pooling row is kept
+            input_ids = torch.where(attention_mask.to(input_ids.device).bool(), input_ids,
+                                    torch.full_like(input_ids, self.arch.eos_id))
+        return self.encode_texts(input_ids, normalize=False)
+
+
+# ------------------------------------------------------------------------------------------
+# processor (host side; out of the timed path)
+# ------------------------------------------------------------------------------------------
+class FallbackTokenizer:
+    """Deterministic stand-in used ONLY when no CLIP BPE vocabulary is on disk (this image has
+    none and no network): words are hashed into the BPE id range.  Shapes, BOS/EOS framing,
+    truncation and padding follow CLIPTokenizer; ids do not."""
+
+    model_max_length = 77
+
+    def __init__(self, vocab: int = 49408, bos: int = BOS_ID, eos: int = EOS_ID):
+        self.vocab, self.bos, self.eos = vocab, bos, eos
+
+    def _ids(self, text: str) -> List[int]:
+        import re
+        import zlib
+
+        words = re.findall(r"[a-z0-9]+|[^\sa-z0-9]", text.lower())
+        return [1 + zlib.crc32(w.encode("utf-8")) % (self.bos - 1) for w in words]
+
+    def __call__(self, texts, padding=True, truncation=True, max_length=None, return_tensors="pt", **_):
+        if isinstance(texts, str):
+            texts = [texts]
+        max_length = max_length or self.model_max_length
+        rows = []
+        for t in texts:
+            ids = [self.bos] + self._ids(t)
+            if truncation:
+                ids = ids[: max_length - 1]
+            rows.append(ids + [self.eos])
+        width = max_length if padding == "max_length" else max(len(r) for r in rows)
+        input_ids = torch.full((len(rows), width), self.eos, dtype=torch.long)
+        mask = torch.zeros((len(rows), width), dtype=torch.long)
+        for i, r in enumerate(rows):
+            input_ids[i, : len(r)] = torch.tensor(r, dtype=torch.long)
+            mask[i, : len(r)] = 1
+        return {"input_ids": input_ids, "attention_mask": mask}
+
+
+class ClmProcessor:
+    """Stand-in for transformers.CLIPProcessor with the calls the reference makes:
+    processor(images=..., return_tensors="pt") and processor(text=[...], padding=True,
+    truncation=True, return_tensors="pt"); `.tokenizer` as used by embed_text.py:35-41."""
+
+    def __init__(self, name: str):
+        from transformers import CLIPImageProcessor
+
+        self.image_processor = CLIPImageProcessor()  # CLIP defaults: 224 bicubic, centre crop, mean/std
+        self.tokenizer = None
+        try:
+            from transformers import CLIPTokenizerFast
+
+            self.tokenizer = CLIPTokenizerFast.from_pretrained(name, local_files_only=True)
+        except Exception:
+            self.tokenizer = FallbackTokenizer()
+            print(f"[clip_model] no CLIP BPE vocabulary on disk for '{name}': using the hashed "
+                  f"FallbackTokenizer (shapes only; see DESIGN.md)")
+
+    def __call__(self, text=None, images=None, return_tensors="pt", padding=True, truncation=True, **kw):
+        out = {}
+        if text is not None:
+            enc = self.tokenizer(text, padding=padding, truncation=truncation, return_tensors="pt",
+                                 **{k: v for k, v in kw.items() if k == "max_length"})
+            out["input_ids"], out["attention_mask"] = enc["input_ids"], enc["attention_mask"]
+        if images is not None:
+            out["pixel_values"] = self.image_processor(images=images, return_tensors="pt")["pixel_values"]
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# reference functions
+# ------------------------------------------------------------------------------------------
+def _load_clip_config(config_path: Union[str, Path]) -> dict:
+    path = Path(config_path)
+    if not path.exists():
+        raise FileNotFoundError(f"CLIP config file not found: {path}")
+    with open(path, "r", encoding="utf-8") as f:
+        return yaml.safe_load(f)
+
+
+def _get_device(device_str: Optional[str] = None) -> torch.device:
+    """Reference rule (models/clip_model.py:23-28): explicit string wins, else CUDA if present.
+    The B200 path additionally refuses CPU: there is no fallback implementation."""
+    if device_str is None:
+        if torch.cuda.is_available():
+            return torch.device("cuda")
+        raise RuntimeError("no CUDA device: the B200 path has no CPU fallback")
+    dev = torch.device(device_str)
+    if dev.type != "cuda":
+        raise ValueError(f"device '{device_str}' requested but the B200 path only runs on CUDA; "
+                         f"set model.device to 'cuda' (or remove it) in the CLIP config")
+    return dev
+
+
+def _get_dtype(dtype_str: str, device: torch.device) -> torch.dtype:
+    """The reference picks fp16 on CUDA else fp32 (:31-34).  Here the arithmetic type is fixed:
+    bf16 tensor-core operands, fp32 accumulation/residual/LN/softmax; the config key is
+    accepted for compatibility and reported."""
+    return torch.bfloat16
+
+
+def random_init_state_dict(arch: ClipArch, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Random-init weights of the named architecture with transformers' own init scheme
+    (there are no checkpoints on this box; BASELINE.json asks for exactly this)."""
+    from transformers import CLIPModel
+
+    torch.manual_seed(seed)
+    hf = CLIPModel(hf_config_for(arch))
+    hf.eval()
+    return {k: v.detach().clone() for k, v in hf.state_dict().items()}
+
+
+def load_clip_model(
+    config_path: Union[str, Path] = "config/clip_config.yaml",
+    use_lora: bool = False,
+    lora_weights_path: Optional[Union[str, Path]] = None,
+) -> Tuple[B200ClipModel, ClmProcessor, torch.device]:
+    """Load CLIP (+ optional LoRA adapter) per the YAML config; same contract as the reference,
+    including its soft fallbacks: a missing/unset LoRA dir prints a notice and continues without
+    LoRA (reference :65-75)."""
+    config = _load_clip_config(config_path)
+    model_cfg = config.get("model", {}) or {}
+    model_name = model_cfg.get("name", "openai/clip-vit-base-patch32")
+    device = _get_device(model_cfg.get("device"))
+    dtype = _get_dtype(model_cfg.get("dtype", "bfloat16"), device)
+    seed = int(model_cfg.get("seed", 0))
+    print(f"[clip_model] Loading CLIP model '{model_name}' on device: {device} (dtype={dtype})")
+
+    state_dict = None
+    arch = None
+    try:
+        from transformers import CLIPModel
+
+        hf = CLIPModel.from_pretrained(model_name, local_files_only=True)
+        arch = arch_from_hf_config(hf.config, model_name)
+        state_dict = hf.state_dict()
+    except Exception:
+        arch = arch_from_name(model_name)
+        print(f"[clip_model] no local checkpoint for '{model_name}': random-init weights of that "
+              f"architecture (seed={seed})")
+        state_dict = random_init_state_dict(arch, seed)
+
+    lora = None
+    if use_lora:
+        paths_cfg = config.get("paths", {}) or {}
+        if lora_weights_path is None:
+            lora_weights_path = paths_cfg.get("lora_weights_dir")
+        if lora_weights_path is None:
+            print("[clip_model] use_lora=True but lora_weights_path is not set, continuing without LoRA.")
+        else:
+            lora_path = Path(lora_weights_path)
+            if not lora_path.exists():
+                print(f"[clip_model] LoRA weights not found at: {lora_path}, continuing without LoRA.")
+            else:
+                print(f"[clip_model] Loading LoRA weights from: {lora_path}")
+                lora = load_lora_adapter(lora_path)
+
+    model = B200ClipModel(arch, state_dict, lora=lora, device=device)
+    processor = ClmProcessor(model_name)
+    model.eval()
+    return model, processor, device
+
+
+def encode_image(image_path: Union[str, Path], model: B200ClipModel, processor, device: torch.device) -> torch.Tensor:
+    """One image file -> L2-normalised embedding (d,) on CPU fp32 (reference :89-118)."""
+    from PIL import Image
+
+    image_path = Path(image_path)
+    if not image_path.exists():
+        raise FileNotFoundError(f"Image not found: {image_path}")
+    image = Image.open(image_path).convert("RGB")
+    inputs = processor(images=image, return_tensors="pt")
+    pixel_values = inputs["pixel_values"].to(device)
+    with torch.no_grad():
+        feats = model.encode_images(pixel_values, normalize=True)  # x / ||x|| fused (clm_l2norm)
+    return feats.squeeze(0).to("cpu", torch.float32)
+
+
+def encode_text(text: str, model: B200ClipModel, processor, device: torch.device) -> torch.Tensor:
+    """One caption -> L2-normalised embedding (d,) on CPU fp32 (reference :121-150)."""
+    inputs = processor(text=[text], return_tensors="pt", padding=True, truncation=True)
+    input_ids = inputs["input_ids"].to(device)
+    with torch.no_grad():
+        feats = model.encode_texts(input_ids, normalize=True)
+    return feats.squeeze(0).to("cpu", torch.float32)

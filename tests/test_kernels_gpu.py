@@ -1,0 +1,261 @@
+"""GPU unit tests: every sm_100a kernel, called through the C-ABI, against a plain torch fp32
+restatement of the same op on the same seeded inputs.  Tolerances are stated per test.
+
+On failure the test dumps the offending tensors to gpurun_out/debug/ so one GPU round-trip
+gives enough evidence to fix descriptor / layout mistakes.
+"""
+import os
+
+import pytest
+import torch
+
+from clip_lora_match_b200 import kernels as K
+
+pytestmark = pytest.mark.gpu
+
+DUMP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "debug")
+
+
+def _dump(name, **tensors):
+    os.makedirs(DUMP, exist_ok=True)
+    torch.save({k: v.detach().cpu() for k, v in tensors.items()}, os.path.join(DUMP, name + ".pt"))
+
+
+def _gen(seed):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+def _randn(shape, seed, scale=1.0):
+    return (torch.randn(shape, generator=_gen(seed)) * scale)
+
+
+def _close(name, got, ref, atol, rtol, **extra):
+    got = got.float().cpu()
+    ref = ref.float().cpu()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    if bad.any() or not torch.isfinite(got).all():
+        _dump(name, got=got, ref=ref, **extra)
+        idx = bad.nonzero()[:5].tolist()
+        raise AssertionError(
+            f"{name}: {int(bad.sum())}/{bad.numel()} elements off; max err {float(err.max()):.4g}; "
+            f"first bad {idx}; got {[float(got[tuple(i)]) for i in idx]} ref {[float(ref[tuple(i)]) for i in idx]}")
+
+
+# ------------------------------------------------------------------------------------------
+# elementwise
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [512, 768, 1024])
+@pytest.mark.parametrize("rows", [1, 37, 1000])
+def test_layernorm(cuda_device, dim, rows):
+    x = _randn((rows, dim), 1, 3.0) + 0.5
+    g = _randn((dim,), 2) * 0.2 + 1.0
+    b = _randn((dim,), 3) * 0.1
+    y = K.layernorm(x.to(cuda_device), g.to(cuda_device), b.to(cuda_device), 1e-5)
+    ref = torch.nn.functional.layer_norm(x, (dim,), g, b, 1e-5)
+    # output is bf16: half an ulp of bf16 (2^-9 relative) plus fp32 noise
+    _close(f"layernorm_{rows}x{dim}", y, ref, atol=2e-3, rtol=4e-3)
+
+
+@pytest.mark.parametrize("dim", [512, 768])
+def test_l2norm(cuda_device, dim):
+    x = _randn((33, dim), 4, 2.0)
+    y, yb = K.l2norm(x.to(cuda_device), want_bf16=True)
+    ref = x / x.norm(dim=-1, keepdim=True)
+    _close(f"l2norm_{dim}", y, ref, atol=1e-6, rtol=1e-5)
+    _close(f"l2norm_bf16_{dim}", yb, ref, atol=1e-4, rtol=4e-3)
+
+
+# ------------------------------------------------------------------------------------------
+# tcgen05 GEMM
+# ------------------------------------------------------------------------------------------
+def _gemm_ref(a, w, bias=None, residual=None, act=0, a2=None, w2=None):
+    acc = a.float() @ w.float().T
+    if a2 is not None:
+        acc = acc + a2.float() @ w2.float().T
+    if bias is not None:
+        acc = acc + bias
+    if act == K.EPI_QUICKGELU:
+        acc = acc * torch.sigmoid(1.702 * acc)
+    if residual is not None:
+        acc = acc + residual
+    return acc
+
+
+GEMM_SHAPES = [
+    # M, N, K           (what it covers)
+    (128, 256, 64),      # one tile, one k-block
+    (128, 256, 768),     # k loop across the 4-stage ring (phase flips)
+    (256, 512, 128),     # 2x2 tiles
+    (197 * 3, 2304, 768),  # ragged M (TMA zero fill + row guard), many tiles, QKV shape
+    (1000, 768, 3072),   # fc2 shape, long K
+    (300, 64, 768),      # BN=64 path (LoRA down-projection)
+    (130, 128, 512),     # BN=128 path
+    (77 * 5, 1536, 512),  # text tower QKV
+    (50 * 4, 768, 588 + 52),  # patch-embed style K = 640 (588 padded)
+]
+
+
+@pytest.mark.parametrize("M,N,Kd", GEMM_SHAPES)
+def test_gemm_plain(cuda_device, M, N, Kd):
+    a = _randn((M, Kd), 10).bfloat16()
+    w = _randn((N, Kd), 11, Kd ** -0.5).bfloat16()
+    out = K.gemm_epi(a.to(cuda_device), w.to(cuda_device), out_dtype=torch.float32)
+    ref = _gemm_ref(a, w)
+    # bf16 products are exact in fp32; only the accumulation order differs
+    _close(f"gemm_plain_{M}x{N}x{Kd}", out, ref, atol=2e-3, rtol=1e-3, a=a, w=w)
+
+
+def test_gemm_identity_layout(cuda_device):
+    """A = I (128x64 one-hot rows) makes the output a copy of W^T: pinpoints descriptor/swizzle errors."""
+    M, N, Kd = 128, 256, 64
+    a = torch.zeros((M, Kd))
+    a[torch.arange(M), torch.arange(M) % Kd] = 1.0
+    w = (torch.arange(N * Kd, dtype=torch.float32).reshape(N, Kd) % 251) / 16.0
+    out = K.gemm_epi(a.bfloat16().to(cuda_device), w.bfloat16().to(cuda_device), out_dtype=torch.float32)
+    ref = _gemm_ref(a.bfloat16(), w.bfloat16())
+    _close("gemm_identity", out, ref, atol=1e-3, rtol=0, a=a, w=w)
+
+
+@pytest.mark.parametrize("M,N,Kd", [(197 * 2, 768, 768), (300, 3072, 768)])
+def test_gemm_epilogues(cuda_device, M, N, Kd):
+    a = _randn((M, Kd), 20).bfloat16()
+    w = _randn((N, Kd), 21, Kd ** -0.5).bfloat16()
+    bias = _randn((N,), 22)
+    res = _randn((M, N), 23)
+    d = cuda_device
+    # bias, bf16 out
+    out = K.gemm_epi(a.to(d), w.to(d), bias=bias.to(d))
+    _close(f"gemm_bias_bf16_{N}", out, _gemm_ref(a, w, bias), atol=2e-2, rtol=8e-3)
+    # bias + quickgelu, bf16 out
+    out = K.gemm_epi(a.to(d), w.to(d), bias=bias.to(d), act=K.EPI_QUICKGELU)
+    _close(f"gemm_gelu_{N}", out, _gemm_ref(a, w, bias, act=K.EPI_QUICKGELU), atol=2e-2, rtol=8e-3)
+    # bias + residual, fp32 out, in place on the residual buffer
+    res_d = res.to(d).clone()
+    out = K.gemm_epi(a.to(d), w.to(d), bias=bias.to(d), residual=res_d, out=res_d)
+    _close(f"gemm_residual_{N}", out, _gemm_ref(a, w, bias, res), atol=2e-3, rtol=1e-3)
+
+
+def test_gemm_lora_extension(cuda_device):
+    """y = x W^T + (x A^T)(s B)^T with the second product folded in as extra K blocks."""
+    M, D, r = 197 * 2, 768, 16
+    x = _randn((M, D), 30).bfloat16()
+    w = _randn((3 * D, D), 31, D ** -0.5).bfloat16()
+    bias = _randn((3 * D,), 32)
+    a_cat = torch.zeros((64, D))
+    a_cat[:r] = _randn((r, D), 33, D ** -0.5)       # q
+    a_cat[r:2 * r] = _randn((r, D), 34, D ** -0.5)  # v
+    b_cat = torch.zeros((3 * D, 64))
+    b_cat[:D, :r] = _randn((D, r), 35, 0.05) * 2.0
+    b_cat[2 * D:, r:2 * r] = _randn((D, r), 36, 0.05) * 2.0
+    d = cuda_device
+    a_cat_b, b_cat_b = a_cat.bfloat16(), b_cat.bfloat16()
+    t = K.gemm_epi(x.to(d), a_cat_b.to(d))  # bf16 [M,64]
+    _close("lora_down", t, _gemm_ref(x, a_cat_b), atol=2e-2, rtol=8e-3)
+    out = K.gemm_epi(x.to(d), w.to(d), bias=bias.to(d), a2=t, w2=b_cat_b.to(d), out_dtype=torch.float32)
+    ref = _gemm_ref(x, w, bias, a2=t.cpu(), w2=b_cat_b)
+    _close("gemm_lora_ext", out, ref, atol=3e-3, rtol=1e-3)
+    # and it must differ from the base GEMM where LoRA applies (q, v) but not on k
+    base = _gemm_ref(x, w, bias)
+    assert (ref[:, :D] - base[:, :D]).abs().max() > 1e-2
+    assert (ref[:, D:2 * D] - base[:, D:2 * D]).abs().max() == 0
+
+
+# ------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------
+def _attn_ref(qkv, batch, tokens, heads, causal):
+    D = heads * 64
+    q, k, v = qkv.float().reshape(batch, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        mask = torch.full((tokens, tokens), float("-inf")).triu(1)
+        s = s + mask
+    p = torch.softmax(s, dim=-1)
+    o = p @ v
+    return o.permute(0, 2, 1, 3).reshape(batch * tokens, D)
+
+
+@pytest.mark.parametrize("batch,tokens,heads,causal", [
+    (2, 64, 1, False),    # exactly one box, one head
+    (3, 50, 12, False),   # ViT-B/32
+    (2, 197, 12, False),  # ViT-B/16: two query tiles, ragged keys
+    (2, 257, 16, False),  # ViT-L/14: S wider than one UMMA N (256 + 16)
+    (5, 77, 8, True),     # text tower, causal
+    (2, 77, 12, True),
+])
+def test_attention(cuda_device, batch, tokens, heads, causal):
+    D = heads * 64
+    qkv = _randn((batch * tokens, 3 * D), 40, 1.5).bfloat16()
+    out = K.attention(qkv.to(cuda_device), batch, tokens, heads, causal)
+    ref = _attn_ref(qkv, batch, tokens, heads, causal)
+    # P is rounded to bf16 before PV and the output is bf16
+    _close(f"attention_{batch}x{tokens}x{heads}_{int(causal)}", out, ref, atol=1.5e-2, rtol=1e-2, qkv=qkv)
+
+
+# ------------------------------------------------------------------------------------------
+# search
+# ------------------------------------------------------------------------------------------
+def _unit_rows(n, d, seed):
+    x = _randn((n, d), seed)
+    return x / x.norm(dim=-1, keepdim=True)
+
+
+def _check_topk(name, got_s, got_i, q, e, k):
+    """ids must match the fp32 oracle except for ties within 1e-4 in oracle score (north_star)."""
+    sims = q @ e.T
+    ref_s, ref_i = torch.topk(sims, k, dim=-1, largest=True, sorted=True)
+    got_s, got_i = got_s.cpu(), got_i.cpu()
+    assert got_i.shape == ref_i.shape
+    assert (got_i >= 0).all() and (got_i < e.shape[0]).all(), f"{name}: ids out of range"
+    if not torch.allclose(got_s, ref_s, atol=2e-6, rtol=1e-5):
+        _dump(name, got_s=got_s, got_i=got_i, ref_s=ref_s, ref_i=ref_i)
+        raise AssertionError(f"{name}: scores differ, max {float((got_s - ref_s).abs().max()):.3g}")
+    mism = got_i != ref_i
+    if mism.any():
+        s_at_got = torch.gather(sims, 1, got_i)
+        gap = (s_at_got - ref_s).abs()[mism]
+        if not (gap <= 1e-4).all():
+            _dump(name, got_s=got_s, got_i=got_i, ref_s=ref_s, ref_i=ref_i)
+            raise AssertionError(f"{name}: {int(mism.sum())} id mismatches beyond the 1e-4 tie window")
+    # no duplicates per query
+    for row in got_i.tolist():
+        assert len(set(row)) == len(row), f"{name}: duplicate ids"
+
+
+@pytest.mark.parametrize("nq,n,d,k", [
+    (1, 6, 512, 3),          # the shipped fixture's size: index smaller than a tile, k < n
+    (1, 300, 512, 5),        # reference-style single query
+    (16, 10000, 512, 10),    # config 1
+    (1000, 10000, 512, 10),  # config 1, full query set
+    (130, 70000, 768, 10),   # two query tiles, many splits, ragged last tile
+    (64, 40000, 768, 50),    # k = 50 (config 5): kc = 56, 3-stage ring
+])
+def test_search_topk(cuda_device, nq, n, d, k):
+    e = _unit_rows(n, d, 50)
+    q = _unit_rows(nq, d, 51)
+    dv = cuda_device
+    kk = min(k, n)
+    s, i = K.search_topk(q.to(dv), q.bfloat16().to(dv), e.bfloat16().to(dv), e.to(dv), kk)
+    _check_topk(f"search_{nq}x{n}x{d}_k{k}", s, i, q, e, kk)
+
+
+def test_search_id_offset_and_merge(cuda_device):
+    """Row-sharded search: two shards searched separately then merged == unsharded search."""
+    n, d, k, nq = 20000, 512, 10, 40
+    e = _unit_rows(n, d, 60)
+    q = _unit_rows(nq, d, 61)
+    dv = cuda_device
+    half = n // 2
+    parts = []
+    for lo, hi in ((0, half), (half, n)):
+        es = e[lo:hi].contiguous()
+        parts.append(K.search_topk(q.to(dv), q.bfloat16().to(dv), es.bfloat16().to(dv), es.to(dv), k,
+                                   id_offset=lo))
+    scores = torch.stack([p[0] for p in parts], dim=1).contiguous()
+    ids = torch.stack([p[1] for p in parts], dim=1).contiguous()
+    s, i = K.topk_merge_sorted(scores, ids, k)
+    _check_topk("search_sharded_merge", s, i, q, e, k)

@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py — the retrieval hot path on N B200s of one node (contract: see DESIGN.md §Measurement).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle) on the host cores
+
+Workload (BASELINE.json configs[1]): CLIP ViT-B/16 + LoRA r=16 (q,v), one step = 1024 synthetic
+224px images + 1024 synthetic 77-token captions through both towers, random-init weights.
+`value` is image-caption pairs per second (each image is encoded together with its caption; the
+image-tower-only and text-tower-only rates are in `detail`).  The search half of the metric
+(top-10 over a 10M x 768 index, 4096-query batches, row-sharded over the N GPUs) is reported
+under `search` in the same JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ARCH = "openai/clip-vit-base-patch16"
+LORA_R, LORA_ALPHA, LORA_TARGETS = 16, 32, ["q_proj", "v_proj"]
+BATCH = 1024
+INDEX_ROWS, INDEX_DIM, QUERY_BATCH, TOP_K = 10_000_000, 768, 4096, 10
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"],
+                "tf_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+def flops_per_item(T, D, L, M, P, r, n_lora, patch_k=0, np_=0):
+    """L(8TD^2 + 4TDM + 4T^2D + n_lora 4TDr) + 2 Np 3P^2 D + 2DP."""
+    return L * (8 * T * D * D + 4 * T * D * M + 4 * T * T * D + n_lora * 4 * T * D * r) + \
+        2 * np_ * patch_k * D + 2 * D * P
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        clocks, maxc, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                clocks.append(float(r[1])); maxc.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not clocks:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples drawing more than half of the highest power seen
+        hot = [c for c, p in zip(clocks, power) if p >= 0.5 * max(power)] or clocks
+        return {"sm_mhz": statistics.median(hot), "sm_max_mhz": max(maxc), "power_w_max": max(power),
+                "samples": len(clocks), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's own path (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_encode_rate(target_seconds=12.0, per_step=8):
+    """Oracle (transformers fp32 CLIPModel + PEFT-semantics LoRA + reference post-processing) on
+    all host threads: image+caption pairs per second on a bounded sample of the same workload."""
+    import torch
+
+    from oracle import clip_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = O.build_model(ARCH, seed=0)
+    O.synthetic_lora(model, LORA_R, LORA_ALPHA, LORA_TARGETS, seed=1)
+    pv = O.synth_images(per_step, seed=2)
+    ids, mask = O.synth_captions(per_step, seed=3)
+    O.encode_images(model, pv[:2]); O.encode_texts(model, ids[:2], mask[:2])  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        O.encode_images(model, pv, batch_size=16)
+        O.encode_texts(model, ids, mask, batch_size=16)
+        n += per_step
+        dt = time.perf_counter() - t0
+        if dt >= target_seconds:
+            break
+    return n / dt, cores, f"{n} image+caption pairs of configs[1] (ViT-B/16+LoRA r=16, fp32, batch {per_step}) in {dt:.1f}s"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import clip_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = O.build_model(ARCH, seed=0)
+    O.synthetic_lora(model, LORA_R, LORA_ALPHA, LORA_TARGETS, seed=1)
+    per_step = 8
+    pv = O.synth_images(per_step, seed=2)
+    ids, mask = O.synth_captions(per_step, seed=3)
+
+    def step():
+        O.encode_images(model, pv, batch_size=16)
+        O.encode_texts(model, ids, mask, batch_size=16)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = f"each step = {per_step} image+caption pairs of configs[1] (bounded sample of the 1024-pair step)"
+    line = {
+        "impl": "reference", "metric": "CLIP+LoRA images/sec", "value": value, "unit": "image-caption pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "image-caption pairs/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "image-caption pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: CLIP ViT-B/16 + LoRA r=16 (q,v) image+text encoding, 1024 images + "
+                        "1024 captions per step per GPU, random-init weights",
+            "arch": ARCH, "lora": {"r": LORA_R, "alpha": LORA_ALPHA, "targets": LORA_TARGETS, "merged": False},
+            "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "tokens": {"image": 197, "text": 77},
+            "parallelism": f"dp{n_gpus}", "l2": "inputs larger than L2 (616 MB pixel_values per step)"}
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-search", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--index-rows", type=int, default=INDEX_ROWS)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from clip_lora_match_b200 import _lib
+    from clip_lora_match_b200.models import clip_model as CM
+    from clip_lora_match_b200.models.lora_adapter import LoraConfig, init_lora_adapter
+    from clip_lora_match_b200.src.embedding.search import TextSearchIndex, shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    peaks = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier+synchronize, CUDA events on the launching stream, max over ranks."""
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b))
+
+    # ---- model + inputs (resident in HBM before the timed region) ------------------------
+    arch = CM.arch_from_name(ARCH)
+    sd = CM.random_init_state_dict(arch, seed=0)
+    model = CM.B200ClipModel(arch, sd, device=dev)
+    lora = init_lora_adapter(model.linear_dims(), LoraConfig(r=LORA_R, lora_alpha=LORA_ALPHA,
+                                                             target_modules=LORA_TARGETS),
+                             seed=1, init_b_std=0.02, base_model_name=ARCH)
+    model.set_lora(lora)
+    g = torch.Generator(device=dev).manual_seed(2 + rank)
+    pv = torch.randn((BATCH, 3, 224, 224), generator=g, device=dev)
+    from oracle import clip_oracle as O  # synthetic caption generator only (§8d), not timed
+
+    ids = O.synth_captions(BATCH, seed=3 + rank)[0].to(dev, torch.int32)
+
+    out = {}
+
+    def step():
+        out["img"] = model.encode_images(pv)
+        out["txt"] = model.encode_texts(ids)
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.clm_launch_count()
+    ms = timed(step, args.steps)
+    launches = lib.clm_launch_count() - l0
+    ms_img = timed(lambda: model.encode_images(pv), args.steps)
+    ms_txt = timed(lambda: model.encode_texts(ids), args.steps)
+    clocks = sampler.stop()
+    assert torch.isfinite(out["img"]).all() and torch.isfinite(out["txt"]).all()
+    value = BATCH * world * args.steps / (ms / 1e3)
+
+    # ---- per-kernel durations, measured live with events around every launch -----------
+    lib.clm_prof_enable(1)
+    step()
+    prof = {k: _lib.prof_summary(k) for k in ("gemm", "attention", "elementwise")}
+    lib.clm_prof_enable(0)
+    gemm = prof["gemm"]
+    achieved_tf = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
+    step_kernel_ms = sum(p["ms"] for p in prof.values())
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN> (tcgen05 GEMM, all launches of one step)",
+                "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved_tf / peaks["tf_sustained"], "frac_of_burst": achieved_tf / peaks["tf_burst"],
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(1, gemm["launches"]),
+                "share_of_step_kernel_time": gemm["ms"] / step_kernel_ms, "traffic": None}
+    va, ta = arch.vision, arch.text
+    fl_img = flops_per_item(197, va.width, va.layers, va.mlp, arch.proj_dim, LORA_R, 2, 3 * 16 * 16, 196)
+    fl_txt = flops_per_item(77, ta.width, ta.layers, ta.mlp, arch.proj_dim, LORA_R, 2)
+    step_tf = (fl_img + fl_txt) * BATCH / (ms / args.steps * 1e-3) / 1e12
+    detail = {
+        "images_per_s_image_tower_only": BATCH * world * args.steps / (ms_img / 1e3),
+        "texts_per_s_text_tower_only": BATCH * world * args.steps / (ms_txt / 1e3),
+        "algorithmic_gflop_per_image": fl_img / 1e9, "algorithmic_gflop_per_caption": fl_txt / 1e9,
+        "whole_step_tflops_per_gpu": step_tf, "whole_step_frac_of_sustained_peak": step_tf / peaks["tf_sustained"],
+        "whole_step_frac_of_burst_peak": step_tf / peaks["tf_burst"],
+        "kernel_ms_per_step": {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in prof.items()},
+    }
+
+    # ---- end to end: host (pinned) inputs -> embeddings back on the host, every step ----
+    pv_host = pv.cpu().pin_memory()
+    ids_host = ids.cpu().pin_memory()
+    emb_host = torch.empty((2, BATCH, arch.proj_dim), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        img = model.encode_images(pv_host.to(dev, non_blocking=True))
+        txt = model.encode_texts(ids_host.to(dev, non_blocking=True))
+        emb_host[0].copy_(img, non_blocking=True)
+        emb_host[1].copy_(txt, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e = {"value": BATCH * world * args.steps / (ms_e2e / 1e3), "unit": "image-caption pairs/s",
+           "h2d_bytes_per_step": pv_host.numel() * 4 + ids_host.numel() * 4,
+           "d2h_bytes_per_step": emb_host.numel() * 4, "ms_per_step": ms_e2e / args.steps}
+    del pv_host, model, pv
+    torch.cuda.empty_cache()
+
+    # ---- search: top-10 over the row-sharded 10M x 768 index ----------------------------
+    search = None
+    if not args.no_search:
+        n_total = args.index_rows
+        lo, hi = shard_bounds(n_total, rank, world)
+        gi = torch.Generator(device=dev).manual_seed(4 + rank)
+        shard = torch.empty((hi - lo, INDEX_DIM), dtype=torch.float32, device=dev)
+        for s0 in range(0, hi - lo, 1_000_000):
+            blk = torch.randn((min(1_000_000, hi - lo - s0), INDEX_DIM), generator=gi, device=dev)
+            shard[s0:s0 + blk.shape[0]] = blk
+        idx = TextSearchIndex(embeddings=shard, device=dev, distributed=world > 1, row_offset=lo,
+                              total_rows=n_total, verbose=False)
+        del shard
+        gq = torch.Generator(device=dev).manual_seed(5)
+        q = torch.randn((QUERY_BATCH, INDEX_DIM), generator=gq, device=dev)
+        res = {}
+
+        def sstep():
+            res["s"], res["i"] = idx.search_batch(q, top_k=TOP_K)
+
+        for _ in range(args.warmup):
+            sstep()
+        ms_s = timed(sstep, args.steps)
+        lib.clm_prof_enable(1)
+        sstep()
+        ps, pm = _lib.prof_summary("search"), _lib.prof_summary("merge")
+        lib.clm_prof_enable(0)
+        s_tf = ps["flops"] / (ps["ms"] * 1e-3) / 1e12
+        # streaming regime (HBM-bound): one 64-query tile scans the shard
+        q64 = q[:64].contiguous()
+        for _ in range(2):
+            idx.search_batch(q64, top_k=TOP_K)
+        lib.clm_prof_enable(1)
+        for _ in range(3):
+            idx.search_batch(q64, top_k=TOP_K)
+        p64 = _lib.prof_summary("search")
+        lib.clm_prof_enable(0)
+        gbs = p64["bytes"] / (p64["ms"] * 1e-3) / 1e9
+        # host-buffer end to end: pinned queries in, (score,id) out
+        q_host = q.cpu().pin_memory()
+
+        def s_e2e():
+            s_, i_ = idx.search_batch(q_host.to(dev, non_blocking=True), top_k=TOP_K)
+            s_.cpu(); i_.cpu()
+
+        s_e2e()
+        ms_se = timed(s_e2e, args.steps)
+        search = {
+            "metric": "top-10 queries/sec over 10M-row index", "value": QUERY_BATCH * args.steps / (ms_s / 1e3),
+            "unit": "queries/s", "index": [n_total, INDEX_DIM], "rows_per_gpu": hi - lo, "query_batch": QUERY_BATCH,
+            "k": TOP_K, "scaling": "strong (index rows fixed, sharded over GPUs)", "ms_per_batch": ms_s / args.steps,
+            "exact": "bf16 tensor-core scan nominates k+6 per (query, split); fp32 re-score of the candidates",
+            "e2e": {"value": QUERY_BATCH * args.steps / (ms_se / 1e3), "unit": "queries/s",
+                    "h2d_bytes_per_step": q_host.numel() * 4, "d2h_bytes_per_step": QUERY_BATCH * TOP_K * 12},
+            "roofline_q4096": {"bound": "tensor", "kernel": "search_kernel", "achieved": s_tf,
+                               "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": s_tf / peaks["tf_burst"],
+                               "scan_ms": ps["ms"], "merge_ms": pm["ms"]},
+            "roofline_q64": {"bound": "hbm", "kernel": "search_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                             "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "scan_ms": p64["ms"] / 3,
+                             "bytes_per_scan": p64["bytes"] / 3},
+        }
+        del idx
+        torch.cuda.empty_cache()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_encode_rate()
+        cpu = {"value": v, "unit": "image-caption pairs/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        line = {
+            "metric": "CLIP+LoRA images/sec", "value": value, "unit": "image-caption pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "detail": detail, "search": search,
+        }
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -76,6 +76,12 @@ SIGNATURES = {
     "clm_search_topk": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "clm_topk_merge": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, C.c_int64, _P, _P, _P]),
     "clm_topk_merge_sorted": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "clm_cosine_gemv": (_I, [_P, _P, _I, _I, _P, _P]),
+    "clm_launch_count": (C.c_ulonglong, []),
+    "clm_prof_enable": (_I, [_I]),
+    "clm_prof_records": (_I, [C.POINTER(C.c_double), _I]),
+    "clm_prof_summary": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                              C.POINTER(C.c_int)]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -115,3 +121,26 @@ def ptr(t) -> Optional[int]:
 def cur_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+KERNEL_KINDS = {"gemm": 0, "attention": 1, "elementwise": 2, "search": 3, "merge": 4}
+
+
+def prof_summary(kind: str) -> dict:
+    """{ms, flops, bytes, launches} of the launches of one kind recorded since prof_enable(1)."""
+    ms, fl, by, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+    check(load().clm_prof_summary(KERNEL_KINDS[kind], C.byref(ms), C.byref(fl), C.byref(by), C.byref(n)),
+          "clm_prof_summary")
+    return {"ms": ms.value, "flops": fl.value, "bytes": by.value, "launches": n.value}
+
+
+def prof_records() -> list:
+    """[(kind_name, flops, bytes, ms)] for every launch recorded since prof_enable(1), in order."""
+    lib = load()
+    n = lib.clm_prof_records(None, 0)
+    if n <= 0:
+        return []
+    buf = (C.c_double * (4 * n))()
+    lib.clm_prof_records(buf, n)
+    names = {v: k for k, v in KERNEL_KINDS.items()}
+    return [(names[int(buf[4 * i])], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]) for i in range(n)]

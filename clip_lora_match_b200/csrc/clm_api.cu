@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "clm_common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -92,4 +96,91 @@ int clm_make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uin
     return CLM_ERR_CUDA;
   }
   return CLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// launch accounting / event profiler
+// ---------------------------------------------------------------------------------------
+namespace {
+struct ProfRec {
+  int kind;
+  double flops, bytes;
+  cudaEvent_t a, b;
+};
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<bool> g_prof_on{false};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_recs;
+thread_local ProfRec* g_open = nullptr;
+thread_local ProfRec g_cur;
+}  // namespace
+
+void clm_prof_begin(int kind, double flops, double bytes, cudaStream_t s) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_open = nullptr;
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  g_cur.kind = kind;
+  g_cur.flops = flops;
+  g_cur.bytes = bytes;
+  if (cudaEventCreate(&g_cur.a) != cudaSuccess || cudaEventCreate(&g_cur.b) != cudaSuccess) return;
+  cudaEventRecord(g_cur.a, s);
+  g_open = &g_cur;
+}
+
+void clm_prof_end(cudaStream_t s) {
+  if (!g_open) return;
+  cudaEventRecord(g_cur.b, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_recs.push_back(g_cur);
+  g_open = nullptr;
+}
+
+extern "C" unsigned long long clm_launch_count(void) { return g_launches.load(); }
+
+extern "C" int clm_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_recs.clear();
+  g_prof_on.store(on != 0);
+  return CLM_OK;
+}
+
+extern "C" int clm_prof_summary(int kind, double* ms, double* flops, double* bytes, int* launches) {
+  CLM_REQUIRE(kind >= 0 && kind < CLM_K_COUNT && ms && flops && bytes && launches,
+              "clm_prof_summary: bad argument");
+  CLM_CUDA_CHECK(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double t = 0, f = 0, b = 0;
+  int n = 0;
+  for (auto& r : g_recs) {
+    if (r.kind != kind) continue;
+    float e = 0.f;
+    CLM_CUDA_CHECK(cudaEventElapsedTime(&e, r.a, r.b));
+    t += e;
+    f += r.flops;
+    b += r.bytes;
+    ++n;
+  }
+  *ms = t; *flops = f; *bytes = b; *launches = n;
+  return CLM_OK;
+}
+
+// Per-launch records (the launch list): out[4*i .. 4*i+3] = {kind, flops, bytes, ms}.
+// Returns the number of records available (may exceed max_records; only max_records are written).
+extern "C" int clm_prof_records(double* out, int max_records) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int i = 0;
+  for (auto& r : g_recs) {
+    if (out && i < max_records) {
+      float e = 0.f;
+      cudaEventElapsedTime(&e, r.a, r.b);
+      out[4 * i + 0] = r.kind; out[4 * i + 1] = r.flops; out[4 * i + 2] = r.bytes; out[4 * i + 3] = e;
+    }
+    ++i;
+  }
+  return i;
 }

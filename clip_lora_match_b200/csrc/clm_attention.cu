@@ -36,16 +36,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
 
 template <bool kCausal>
 __global__ void __launch_bounds__(kThreads)
-attention_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out,
-                 int T, int H, int Tp, int Tk, int mtiles, uint32_t tmem_cols, int region_a_bytes) {
+attention_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_tail,
+                 __nv_bfloat16* __restrict__ out, int T, int H, int Tp, int Tk, int mtiles,
+                 uint32_t tmem_cols, int region_a_bytes) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                       // 128 x 64 bf16
-  uint8_t* sK = smem + 2 * kBoxBytes;       // Tk x 64 bf16
+  uint8_t* sK = smem + 2 * kBoxBytes;       // Tp x 64 bf16
   uint8_t* sP = smem;                       // aliases Q,K once S is complete: 128 x Tk bf16
-  uint8_t* sV = smem + region_a_bytes;      // Tk x 64 bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Tk * 128);
+  uint8_t* sV = smem + region_a_bytes;      // Tp x 64 bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Tp * 128);
   uint64_t* bar_load = bars;
   uint64_t* bar_mma = bars + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
@@ -58,10 +59,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __r
   const int b = bh / H;
   const int D = H * kHeadDim;
   const int row_base = b * T;
-  const int kboxes = Tk / kBoxRows;
+  const int n64 = Tp / kBoxRows;          // full 64-row boxes of K / V
+  const int n16 = (Tp % kBoxRows) / 16;   // 16-row boxes covering the ragged tail
 
   if (tid == 0) {
     tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_tail);
     mbar_init(bar_load, 1);
     mbar_init(bar_mma, 1);
     fence_barrier_init();
@@ -76,15 +79,20 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __r
   const uint32_t tmem = *tmem_slot;
 
   if (tid == 0) {
-    mbar_arrive_expect_tx(bar_load, static_cast<uint32_t>((2 + 2 * kboxes) * kBoxBytes));
+    mbar_arrive_expect_tx(bar_load, static_cast<uint32_t>(2 * kBoxBytes + 2 * Tp * 128));
     for (int i = 0; i < 2; ++i)
       tma_load_2d(sQ + i * kBoxBytes, &map_qkv, bar_load, h * kHeadDim,
                   row_base + mt * 128 + i * kBoxRows);
-    for (int i = 0; i < kboxes; ++i) {
+    for (int i = 0; i < n64; ++i)
       tma_load_2d(sK + i * kBoxBytes, &map_qkv, bar_load, D + h * kHeadDim, row_base + i * kBoxRows);
-      tma_load_2d(sV + i * kBoxBytes, &map_qkv, bar_load, 2 * D + h * kHeadDim,
-                  row_base + i * kBoxRows);
-    }
+    for (int i = 0; i < n16; ++i)
+      tma_load_2d(sK + n64 * kBoxBytes + i * 2048, &map_tail, bar_load, D + h * kHeadDim,
+                  row_base + n64 * kBoxRows + i * 16);
+    for (int i = 0; i < n64; ++i)
+      tma_load_2d(sV + i * kBoxBytes, &map_qkv, bar_load, 2 * D + h * kHeadDim, row_base + i * kBoxRows);
+    for (int i = 0; i < n16; ++i)
+      tma_load_2d(sV + n64 * kBoxBytes + i * 2048, &map_tail, bar_load, 2 * D + h * kHeadDim,
+                  row_base + n64 * kBoxRows + i * 16);
   }
   mbar_wait(bar_load, 0);
 
@@ -117,15 +125,23 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __r
   const int nchunks = (Tp + 31) / 32;
   constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
 
+  // pass 1: row maximum.  Only chunks that cross `valid` need per-element masking.
   float mx = -INFINITY;
   for (int c = 0; c < nchunks; ++c) {
     uint32_t v[32];
     tmem_ld_32x32b_x32(trow + c * 32, v);
     tmem_ld_wait();
+    if (c * 32 + 32 <= valid) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+    }
   }
+  // pass 2: p = 2^(s*c - mx*c) (one FFMA + one MUFU), row sum, P -> shared memory as bf16
+  const float neg_mx = -mx * kScaleLog2e;
   float sum = 0.f;
   uint8_t* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
   for (int c = 0; c < nchunks; ++c) {
@@ -133,11 +149,19 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __r
     tmem_ld_32x32b_x32(trow + c * 32, v);
     tmem_ld_wait();
     float p[32];
+    if (c * 32 + 32 <= valid) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float e = exp2f((__uint_as_float(v[i]) - mx) * kScaleLog2e);
-      p[i] = (c * 32 + i < valid) ? e : 0.f;
-      sum += p[i];
+      for (int i = 0; i < 32; ++i) {
+        p[i] = fast_exp2(fmaf(__uint_as_float(v[i]), kScaleLog2e, neg_mx));
+        sum += p[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e = fast_exp2(fmaf(__uint_as_float(v[i]), kScaleLog2e, neg_mx));
+        p[i] = (c * 32 + i < valid) ? e : 0.f;
+        sum += p[i];
+      }
     }
     uint8_t* pblk = prow + (c >> 1) * 16384;  // 64-column k-block
     const int j0 = (c & 1) * 4;               // first 16-byte chunk inside the 128-byte row
@@ -213,27 +237,34 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   const int tp32 = (Tp + 31) / 32 * 32;
   uint32_t tmem_cols = 64;
   while (static_cast<int>(tmem_cols) < tp32) tmem_cols <<= 1;
-  const int qk_bytes = 2 * kBoxBytes + Tk * 128;
+  const int qk_bytes = 2 * kBoxBytes + Tp * 128;
   const int p_bytes = (Tk / 64) * 16384;
-  const int region_a = qk_bytes > p_bytes ? qk_bytes : p_bytes;
-  const int smem_bytes = region_a + Tk * 128 + 64 + 1024;
+  const int region_a = ((qk_bytes > p_bytes ? qk_bytes : p_bytes) + 1023) / 1024 * 1024;
+  const int smem_bytes = region_a + Tp * 128 + 64 + 1024;
 
   CUtensorMap map;
   int rc = clm_make_tmap_bf16_2d(&map, qkv, static_cast<uint64_t>(batch) * T, 3ull * D, 3ull * D,
                                  kHeadDim, kBoxRows);
   if (rc) return rc;
+  CUtensorMap map_tail;
+  rc = clm_make_tmap_bf16_2d(&map_tail, qkv, static_cast<uint64_t>(batch) * T, 3ull * D, 3ull * D,
+                             kHeadDim, 16);
+  if (rc) return rc;
   const long long grid = static_cast<long long>(batch) * heads * mtiles;
   CLM_REQUIRE(grid < 2147483647LL, "clm_attention: grid too large");
+  // algorithmic work: QK^T and PV at the true T (causal not discounted)
+  ProfScope prof(CLM_K_ATTENTION, 4.0 * batch * heads * static_cast<double>(T) * T * kHeadDim,
+                 2.0 * batch * T * 4.0 * D, stream);
   if (causal) {
     CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attention_kernel<true><<<static_cast<int>(grid), kThreads, smem_bytes, stream>>>(
-        map, static_cast<__nv_bfloat16*>(out), T, heads, Tp, Tk, mtiles, tmem_cols, region_a);
+        map, map_tail, static_cast<__nv_bfloat16*>(out), T, heads, Tp, Tk, mtiles, tmem_cols, region_a);
   } else {
     CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attention_kernel<false><<<static_cast<int>(grid), kThreads, smem_bytes, stream>>>(
-        map, static_cast<__nv_bfloat16*>(out), T, heads, Tp, Tk, mtiles, tmem_cols, region_a);
+        map, map_tail, static_cast<__nv_bfloat16*>(out), T, heads, Tp, Tk, mtiles, tmem_cols, region_a);
   }
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;

@@ -45,6 +45,20 @@ int clm_make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uin
 
 int clm_num_sms();
 
+// Launch accounting + optional per-launch CUDA-event timing (bench.py's roofline numbers).
+// Every kernel launch in the library goes through a ProfScope: it always counts the launch and,
+// when profiling is enabled, brackets it with two events on the launching stream.
+#define CLM_K_COUNT 5  // kinds are CLM_K_* in include/clm_b200.h
+void clm_prof_begin(int kind, double flops, double bytes, cudaStream_t s);
+void clm_prof_end(cudaStream_t s);
+struct ProfScope {
+  cudaStream_t s;
+  ProfScope(int kind, double flops, double bytes, cudaStream_t stream) : s(stream) {
+    clm_prof_begin(kind, flops, bytes, stream);
+  }
+  ~ProfScope() { clm_prof_end(s); }
+};
+
 // ---------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------
@@ -229,6 +243,28 @@ __device__ __forceinline__ void tmem_ld_wait() {
 }
 
 // ---- misc -----------------------------------------------------------------------------
+// single-MUFU approximations (rel. error ~2^-22): plenty for values that are rounded to bf16
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_tanh(float x) {  // MUFU.TANH, max rel. error 2^-11
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// QuickGELU x*sigmoid(1.702x) = 0.5x (1 + tanh(0.851x)): ONE MUFU op per element instead of
+// ex2 + rcp.  |abs error| <= 0.5|x| * 2^-11, below the bf16 rounding of the stored activation.
+__device__ __forceinline__ float quick_gelu(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, fast_tanh(0.851f * x), h);
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

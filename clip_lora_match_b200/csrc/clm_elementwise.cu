@@ -237,6 +237,7 @@ extern "C" int clm_layernorm(const float* x, const float* gamma, const float* be
   CLM_REQUIRE(x && gamma && beta && y_bf16 && rows >= 0, "clm_layernorm: bad argument");
   if (rows == 0) return CLM_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 6.0 * rows * dim, s);
   CLM_DISPATCH_DIM(dim, (layernorm_kernel<NV><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
                             x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), rows, eps)));
   CLM_CUDA_CHECK(cudaGetLastError());
@@ -247,6 +248,7 @@ extern "C" int clm_l2norm(const float* x, float* y, void* y_bf16_or_null, int ro
                           void* stream) {
   CLM_REQUIRE(x && y && rows >= 0 && dim > 0 && dim % 4 == 0, "clm_l2norm: bad argument");
   if (rows == 0) return CLM_OK;
+  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 8.0 * rows * dim, static_cast<cudaStream_t>(stream));
   l2norm_kernel<<<blocks_for(rows), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       x, y, static_cast<__nv_bfloat16*>(y_bf16_or_null), rows, dim);
   CLM_CUDA_CHECK(cudaGetLastError());
@@ -260,6 +262,7 @@ extern "C" int clm_embed_text(const int32_t* ids, const float* tok_emb, const fl
   if (batch == 0) return CLM_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int rows = batch * tokens;
+  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 8.0 * rows * dim, s);
   CLM_DISPATCH_DIM(dim, (embed_text_kernel<NV><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
                             ids, tok_emb, pos_emb, h, rows, tokens, vocab)));
   if (eos_pos)
@@ -278,6 +281,8 @@ extern "C" int clm_patch_im2col(const float* pixel_values, void* patches_bf16, i
   const int g = image / patch;
   const long long total = static_cast<long long>(batch) * g * g * (kpad / 8);
   const int blocks = static_cast<int>((total + 255) / 256);
+  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 12.0 * batch * image * image + 16.0 * total,
+                 static_cast<cudaStream_t>(stream));
   im2col_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       pixel_values, static_cast<__nv_bfloat16*>(patches_bf16), batch, image, patch, kpad);
   CLM_CUDA_CHECK(cudaGetLastError());
@@ -292,6 +297,7 @@ extern "C" int clm_vision_embed_ln(const float* patch_out, const float* class_em
   if (batch == 0) return CLM_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int rows = batch * (np + 1);
+  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 8.0 * rows * dim, s);
   CLM_DISPATCH_DIM(dim, (vision_embed_ln_kernel<NV><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
                             patch_out, class_emb, pos_emb, gamma, beta, h, batch, np, eps)));
   CLM_CUDA_CHECK(cudaGetLastError());
@@ -304,6 +310,7 @@ extern "C" int clm_pool_ln(const float* h, const int32_t* row_idx_or_null, const
   CLM_REQUIRE(h && gamma && beta && y_bf16 && batch >= 0 && tokens > 0, "clm_pool_ln: bad argument");
   if (batch == 0) return CLM_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 6.0 * batch * dim, s);
   CLM_DISPATCH_DIM(dim, (pool_ln_kernel<NV><<<blocks_for(batch), kWarpsPerBlock * 32, 0, s>>>(
                             h, row_idx_or_null, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16),
                             batch, tokens, eps)));

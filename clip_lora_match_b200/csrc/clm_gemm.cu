@@ -6,10 +6,12 @@
 // neither needs a transpose: TMA drops 64-column (128-byte) swizzled boxes into shared
 // memory and tcgen05.mma reads them through K-major SWIZZLE_128B descriptors.
 //
-// CTA = 192 threads:
+// CTA = 320 threads:
 //   warp 0      TMA producer (one elected lane)          smem ring: full[]/empty[] mbarriers
 //   warp 1      TMEM allocator + MMA issuer (one lane)   accumulator ring: tmem_full[]/tmem_empty[]
-//   warps 2..5  epilogue: tcgen05.ld -> bias/QuickGELU/residual -> global stores
+//   warps 2..9  epilogue: tcgen05.ld -> bias/QuickGELU/residual -> global stores.  Warp w reads
+//               TMEM lane quarter (w % 4) and column half ((w - 2) / 4); the fp32 residual of the
+//               next 32-column chunk is prefetched while the current chunk is converted/stored.
 // The accumulator is double buffered in TMEM (2 x BN fp32 columns) so the epilogue of tile i
 // overlaps the MMAs of tile i+1.  The grid is persistent: min(tiles, #SM) CTAs stride over
 // the tile list (n fastest, so CTAs that run together share A rows through L2).
@@ -23,8 +25,9 @@ namespace {
 using namespace clm;
 
 constexpr int BM = 128;
+constexpr int kEpiWarps = 8;
 constexpr int BK = 64;
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;
 constexpr int kAccStages = 2;
 
 template <int BN>
@@ -34,7 +37,8 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = kAccStages * BN;  // 512 / 256 / 128: powers of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiWarps * 4096 /*epilogue staging*/;
 };
 
 struct EpiParams {
@@ -83,7 +87,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -154,77 +158,83 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
   } else {
     // ================= epilogue warps =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // TMEM gives each lane one accumulator ROW (32 fp32 columns per tcgen05.ld).  Storing that
+    // directly would touch 32 different cache lines per warp instruction, so each warp transposes
+    // its 32x32 chunk through a private 4 KiB shared-memory buffer (16-byte pieces XOR-swizzled by
+    // row: conflict-free both ways) and does bias / activation / residual / stores in the
+    // COALESCED domain: lane l owns columns 4*(l%8)..+3 of rows (l/8) + 4*i, i = 0..7, so every
+    // global instruction covers 4 full 128-byte row segments.
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
+    constexpr int kChunks = BN / 64;    // 32-column chunks per warp
+    uint8_t* stage = smem + C::kStages * C::kStageBytes + 256 + (warp - 2) * 4096;
+    const int piece = lane & 7;         // 16-byte piece (4 fp32 columns) inside the 128-byte chunk row
+    const int rsub = lane >> 3;         // row offset inside each group of 4 rows
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * BM;
-      const int n0 = (tile % n_tiles) * BN;
+      const int m0 = (tile / n_tiles) * BM + q * 32;
+      const int n0 = (tile % n_tiles) * BN + half * (BN / 2);
+      float4 rcur[8], rnxt[8];  // residual of the current / next chunk (coalesced layout)
+      auto load_residual = [&](float4 (&dst)[8], int col0) {
+        const int col = col0 + piece * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = m0 + i * 4 + rsub;
+          dst[i] = (row < M && col < N)
+                       ? *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(row) * ep.ldr + col)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      if (ep.residual) load_residual(rcur, n0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                             static_cast<uint32_t>(acc * BN);
+                             static_cast<uint32_t>(acc * BN + half * (BN / 2));
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < kChunks; ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c * 32, v);
-        tmem_ld_wait();
         const int col0 = n0 + c * 32;
-        if (row_ok && col0 < N) {
-          float f[32];
+        if (c + 1 < kChunks && ep.residual) load_residual(rnxt, col0 + 32);
+        tmem_ld_wait();
+        // row-per-lane -> shared (piece j of row `lane` lands in slot j ^ (lane & 7))
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (ep.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int col = col0 + piece * 4;
+        const bool col_ok = col < N;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias && col_ok) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (col0 + i * 4 < N) {
-                const float4 b = __ldg(b4 + i);
-                f[4 * i + 0] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
-              }
-            }
-          }
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + rsub;
+          float4 f = *reinterpret_cast<const float4*>(stage + rl * 128 + ((piece ^ (rl & 7)) << 4));
+          f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
           if (ep.act == CLM_EPI_QUICKGELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = f[i] * __frcp_rn(1.0f + __expf(-1.702f * f[i]));
+            f.x = quick_gelu(f.x); f.y = quick_gelu(f.y); f.z = quick_gelu(f.z); f.w = quick_gelu(f.w);
           }
           if (ep.residual) {
-            const float4* r4 = reinterpret_cast<const float4*>(
-                ep.residual + static_cast<size_t>(row) * ep.ldr + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (col0 + i * 4 < N) {
-                const float4 r = r4[i];
-                f[4 * i + 0] += r.x; f[4 * i + 1] += r.y; f[4 * i + 2] += r.z; f[4 * i + 3] += r.w;
-              }
-            }
+            const float4 r = rcur[i];
+            f.x += r.x; f.y += r.y; f.z += r.z; f.w += r.w;
           }
-          if (ep.out_f32) {
-            float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(ep.out) +
-                                                   static_cast<size_t>(row) * ep.ldo + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (col0 + i * 4 < N)
-                o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-            }
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) +
-                                                 static_cast<size_t>(row) * ep.ldo + col0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (col0 + i * 8 < N) {
-                uint4 o;
-                o.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
-                o.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
-                o.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
-                o.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
-                o4[i] = o;
-              }
+          const int row = m0 + rl;
+          if (row < M && col_ok) {
+            if (ep.out_f32) {
+              *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ldo + col) = f;
+            } else {
+              *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(row) * ep.ldo + col) =
+                  make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
             }
           }
         }
+        if (ep.residual) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rcur[i] = rnxt[i];
+        }
+        __syncwarp();  // the staging buffer is rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();
@@ -302,6 +312,11 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
   ep.act = epilogue;
   const int kb_main = (K + BK - 1) / BK;
   const int kb_ext = has_ext ? (K2 + BK - 1) / BK : 0;
+  const double flops = 2.0 * M * N * (static_cast<double>(K) + (has_ext ? K2 : 0));
+  const double bytes = 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) +
+                       static_cast<double>(M) * N * (ep.out_f32 ? 4 : 2) +
+                       (residual ? 4.0 * M * N : 0.0);
+  ProfScope prof(CLM_K_GEMM, flops, bytes, stream);
   switch (BN) {
     case 256: return launch_gemm<256>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);
     case 128: return launch_gemm<128>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);

@@ -339,10 +339,30 @@ int launch_merge(const float* in_score, const IdT* in_id, int nq, int total, int
   if (smem > 48 * 1024)
     CLM_CUDA_CHECK(cudaFuncSetAttribute(merge_kernel<IdT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
+  ProfScope prof(CLM_K_MERGE, 0.0, 8.0 * nq * total + (index_f32 ? 4.0 * nq * keep * dim : 0.0), s);
   merge_kernel<IdT><<<nq, kMergeThreads, smem, s>>>(in_score, in_id, total, keep, q_f32, index_f32,
                                                     dim, k, id_offset, out_score, out_id);
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
+}
+
+// exact fp32 scores of ONE query against every row (the reference's batch-1 matmul,
+// src/embedding/search.py:96 / similarity.py:32): one warp per row, 128-bit loads, pure streaming.
+__global__ void __launch_bounds__(256)
+gemv_kernel(const float* __restrict__ q, const float* __restrict__ e, int n, int dim,
+            float* __restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float4* q4 = reinterpret_cast<const float4*>(q);
+  const float4* e4 = reinterpret_cast<const float4*>(e + static_cast<size_t>(row) * dim);
+  float s = 0.f;
+  for (int i = (threadIdx.x & 31); i < (dim >> 2); i += 32) {
+    const float4 a = __ldg(q4 + i);
+    const float4 b = e4[i];
+    s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) out[row] = s;
 }
 
 int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
@@ -389,6 +409,10 @@ extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int n
   CLM_CUDA_CHECK(cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const long long units = static_cast<long long>(q_tiles) * splits;
   const int grid = units < clm_num_sms() ? static_cast<int>(units) : clm_num_sms();
+  // algorithmic bytes: index once + queries once + candidate lists
+  ProfScope prof(CLM_K_SEARCH, 2.0 * nq * static_cast<double>(n) * dim,
+                 2.0 * dim * (static_cast<double>(n) + nq) + 8.0 * nq * splits * kc,
+                 static_cast<cudaStream_t>(stream));
   search_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(mq, me, p);
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
@@ -414,4 +438,16 @@ extern "C" int clm_topk_merge_sorted(const float* in_score, const int64_t* in_id
   return launch_merge<long long>(in_score, reinterpret_cast<const long long*>(in_id), nq, lists * k, k,
                                  nullptr, nullptr, 0, k, 0, out_score,
                                  reinterpret_cast<long long*>(out_id), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int clm_cosine_gemv(const float* q_f32, const float* index_f32, int n, int dim, float* out,
+                               void* stream) {
+  CLM_REQUIRE(q_f32 && index_f32 && out && n >= 0 && dim > 0 && dim % 4 == 0,
+              "clm_cosine_gemv: bad argument");
+  if (n == 0) return CLM_OK;
+  ProfScope prof(CLM_K_SEARCH, 2.0 * n * dim, 4.0 * dim * (static_cast<double>(n) + 1) + 4.0 * n,
+                 static_cast<cudaStream_t>(stream));
+  gemv_kernel<<<(n + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(q_f32, index_f32, n, dim, out);
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
 }

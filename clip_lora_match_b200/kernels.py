@@ -125,3 +125,29 @@ def topk_merge_sorted(scores: torch.Tensor, ids: torch.Tensor, k: int) -> Tuple[
     check(_lib.load().clm_topk_merge_sorted(ptr(scores), ptr(ids), nq, lists, k, ptr(out_s), ptr(out_i),
                                             cur_stream()), "clm_topk_merge_sorted")
     return out_s, out_i
+
+
+def rescore(cand_score: torch.Tensor, cand_id: torch.Tensor, q_f32: torch.Tensor,
+            index_f32: torch.Tensor, k: int, id_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact fp32 scores of nominated rows: cand_* [Q, lists, kc] -> top-k (score desc, id asc)."""
+    _req(cand_score, torch.float32, "cand_score"); _req(cand_id, torch.int32, "cand_id")
+    _req(q_f32, torch.float32, "q_f32"); _req(index_f32, torch.float32, "index_f32")
+    nq, lists, kc = cand_score.shape
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=q_f32.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=q_f32.device)
+    check(_lib.load().clm_topk_merge(ptr(cand_score), ptr(cand_id), nq, lists, kc, ptr(q_f32),
+                                     ptr(index_f32), q_f32.shape[1], k, id_offset, ptr(out_s), ptr(out_i),
+                                     cur_stream()), "clm_topk_merge")
+    return out_s, out_i
+
+
+def cosine_gemv(q_f32: torch.Tensor, index_f32: torch.Tensor) -> torch.Tensor:
+    """Exact fp32 scores of one (already normalised) query against every index row -> (N,)."""
+    _req(q_f32, torch.float32, "q_f32"); _req(index_f32, torch.float32, "index_f32")
+    n, dim = index_f32.shape
+    if q_f32.numel() != dim:
+        raise ValueError("query must have exactly `dim` elements")
+    out = torch.empty(n, dtype=torch.float32, device=index_f32.device)
+    check(_lib.load().clm_cosine_gemv(ptr(q_f32), ptr(index_f32), n, dim, ptr(out), cur_stream()),
+          "clm_cosine_gemv")
+    return out

@@ -390,7 +390,11 @@ class ClmProcessor:
         try:
             from transformers import CLIPTokenizerFast
 
-            self.tokenizer = CLIPTokenizerFast.from_pretrained(name, local_files_only=True)
+            tok = CLIPTokenizerFast.from_pretrained(name, local_files_only=True)
+            # transformers 5 can hand back an EMPTY tokenizer when no vocabulary files exist
+            if tok.eos_token_id != EOS_ID or tok.bos_token_id != BOS_ID or len(tok) < 49408:
+                raise RuntimeError("CLIP BPE vocabulary not available")
+            self.tokenizer = tok
         except Exception:
             self.tokenizer = FallbackTokenizer()
             print(f"[clip_model] no CLIP BPE vocabulary on disk for '{name}': using the hashed "

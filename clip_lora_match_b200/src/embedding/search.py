@@ -1,0 +1,195 @@
+"""Embedding index + brute-force cosine top-k — B200 mirror of the reference's
+src/embedding/search.py.
+
+Reference surface kept (names, argument order, exceptions, result type):
+  SearchResult                                      reference :14-20
+  TextSearchIndex(index_path)                       reference :24-68
+    .search_with_embedding(query_emb, top_k=5)      reference :70-115  ((d,) / (1,d) only)
+    .search_by_text / .search_by_image              reference :117-151
+Extensions:
+  .search_batch(queries [Q,d], top_k) -> (scores [Q,k], ids [Q,k]) device tensors
+  row sharding over torch.distributed ranks (each GPU holds a contiguous block of rows, local
+  fused top-k, ONE all_gather of Q*k (score,id) pairs, merge) — SURVEY.md §8(e).
+
+The index lives on the GPU as an fp32 master (exact re-scoring) plus a bf16 shadow (the copy
+the tensor-core scan streams).  Loading accepts both metadata key spellings of the
+reference's writers (`image_path`/`text` and `image_paths`/`texts`, reference :41-56).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from pathlib import Path
+from typing import List, Optional, Tuple, Union
+
+import torch
+
+from ... import kernels as K
+from ...models.clip_model import encode_image, encode_text
+
+
+@dataclass
+class SearchResult:
+    """One search hit (reference :14-20)."""
+    index: int
+    score: float
+    image_path: str
+    text: str
+
+
+def _dist_info(distributed: bool) -> Tuple[int, int]:
+    if not distributed:
+        return 0, 1
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("distributed=True needs an initialised torch.distributed process group")
+    return dist.get_rank(), dist.get_world_size()
+
+
+def shard_bounds(num_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block of rows owned by `rank` (balanced to within one row)."""
+    return (num_rows * rank) // world, (num_rows * (rank + 1)) // world
+
+
+def gather_shard_topk(scores: Optional[torch.Tensor], ids: Optional[torch.Tensor], nq: int, k: int,
+                      device: torch.device, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The one exchange step of the sharded search: every rank contributes its local top-k
+    (padded to k with (-inf, -1)); returns [Q, world, k] scores / global ids on every rank.
+    Payload per rank is Q*k*12 bytes (328 KB..2.4 MB at Q=4096), i.e. latency-bound on NVLink."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    pad_s = torch.full((nq, k), float("-inf"), dtype=torch.float32, device=device)
+    pad_i = torch.full((nq, k), -1, dtype=torch.int64, device=device)
+    if scores is not None and scores.shape[1] > 0:
+        kl = scores.shape[1]
+        pad_s[:, :kl], pad_i[:, :kl] = scores, ids
+    all_s = [torch.empty_like(pad_s) for _ in range(world)]
+    all_i = [torch.empty_like(pad_i) for _ in range(world)]
+    dist.all_gather(all_s, pad_s, group=group)
+    dist.all_gather(all_i, pad_i, group=group)
+    return torch.stack(all_s, dim=1).contiguous(), torch.stack(all_i, dim=1).contiguous()
+
+
+class TextSearchIndex:
+    def __init__(self, index_path: Optional[Union[str, Path]] = None, *,
+                 embeddings: Optional[torch.Tensor] = None, image_paths: Optional[list] = None,
+                 texts: Optional[list] = None, device: Union[str, torch.device] = "cuda",
+                 distributed: bool = False, row_offset: Optional[int] = None,
+                 total_rows: Optional[int] = None, verbose: bool = True):
+        """Load a `.pt` index written by scripts/build_*_index.py (or take tensors directly).
+
+        With distributed=True every rank keeps rows shard_bounds(N, rank, world) of a full index
+        file; passing `embeddings` that are already the rank's shard requires row_offset (first
+        global row) and total_rows."""
+        if index_path is not None:
+            index_path = Path(index_path)
+            if not index_path.exists():
+                raise FileNotFoundError(f"Index file not found: {index_path}")
+            obj = torch.load(index_path, map_location="cpu")
+            embs = obj.get("embeddings")
+            if embs is None:
+                raise ValueError("Index file does not contain 'embeddings'")
+            images = obj.get("image_paths")
+            if images is None:
+                images = obj.get("image_path")
+            txts = obj.get("texts")
+            if txts is None:
+                txts = obj.get("text")
+            image_paths = list(images) if images is not None else []
+            texts = list(txts) if txts is not None else []
+        else:
+            if embeddings is None:
+                raise ValueError("either index_path or embeddings is required")
+            embs = embeddings
+            image_paths = list(image_paths) if image_paths is not None else []
+            texts = list(texts) if texts is not None else []
+        if embs.dim() == 1:
+            embs = embs.unsqueeze(0)
+
+        self.device = torch.device(device)
+        self.rank, self.world = _dist_info(distributed)
+        self.distributed = distributed
+        self.image_paths: List[str] = image_paths
+        self.texts: List[str] = texts
+
+        if distributed and row_offset is None:
+            n_total = embs.shape[0]
+            lo, hi = shard_bounds(n_total, self.rank, self.world)
+            embs = embs[lo:hi]
+            self.row_offset, self.num_items = lo, n_total
+        else:
+            self.row_offset = int(row_offset or 0)
+            self.num_items = int(total_rows) if total_rows is not None else embs.shape[0]
+        self.dim = embs.shape[1]
+
+        if index_path is not None and self.num_items != len(self.image_paths) and verbose:
+            print(f"[TextSearchIndex] WARNING: embeddings rows ({self.num_items}) "
+                  f"!= len(image_paths) ({len(self.image_paths)})")
+        if verbose:
+            print(f"[TextSearchIndex] Loaded {self.num_items} items with dim={self.dim}"
+                  + (f" (rank {self.rank}/{self.world}: rows {self.row_offset}.."
+                     f"{self.row_offset + embs.shape[0]})" if distributed else ""))
+
+        # row-normalise once, on the GPU, in fp32 (reference :68); keep fp32 master + bf16 shadow
+        local = embs.to(device=self.device, dtype=torch.float32).contiguous()
+        if local.shape[0] > 0:
+            self.embeddings, self.embeddings_bf16 = K.l2norm(local, want_bf16=True)
+        else:
+            self.embeddings, self.embeddings_bf16 = local, local.to(torch.bfloat16)
+        self.local_rows = self.embeddings.shape[0]
+
+    # ---- batched search (extension) ------------------------------------------------------
+    def search_batch(self, queries: torch.Tensor, top_k: int = 5) -> Tuple[torch.Tensor, torch.Tensor]:
+        """queries [Q, d] (any device) -> (scores fp32 [Q,k], global ids int64 [Q,k]) on the GPU,
+        sorted descending, k = min(top_k, N).  On a sharded index every rank passes the same
+        queries and gets the same merged result."""
+        if queries.dim() != 2:
+            raise ValueError(f"queries must be [Q, d], got {tuple(queries.shape)}")
+        if queries.shape[-1] != self.dim:
+            raise ValueError(f"query_emb dim {queries.shape[-1]} != index dim {self.dim}")
+        k = min(top_k, self.num_items)
+        if k < 1:
+            raise ValueError("top_k must be >= 1 and the index non-empty")
+        if k > 64:
+            raise ValueError("top_k > 64 is not supported by the fused top-k kernel")
+        q = queries.to(device=self.device, dtype=torch.float32).contiguous()
+        qn, qb = K.l2norm(q, want_bf16=True)  # reference :93
+        nq = qn.shape[0]
+        k_local = min(k, self.local_rows)
+        if k_local > 0:
+            s, i = K.search_topk(qn, qb, self.embeddings_bf16, self.embeddings, k_local,
+                                 id_offset=self.row_offset)
+        if not self.distributed or self.world == 1:
+            return s, i
+        if k_local > 0:
+            gs, gi = gather_shard_topk(s, i, nq, k, self.device)
+        else:
+            gs, gi = gather_shard_topk(None, None, nq, k, self.device)
+        return K.topk_merge_sorted(gs, gi, k)
+
+    # ---- reference API -------------------------------------------------------------------
+    def search_with_embedding(self, query_emb: torch.Tensor, top_k: int = 5) -> List[SearchResult]:
+        """Single-query search; shape rules and errors as the reference (:80-90)."""
+        if query_emb.ndim == 1:
+            query_emb = query_emb.unsqueeze(0)
+        elif query_emb.ndim != 2 or query_emb.shape[0] != 1:
+            raise ValueError(f"query_emb must be shape (d,) or (1, d), got {tuple(query_emb.shape)}")
+        if query_emb.shape[-1] != self.dim:
+            raise ValueError(f"query_emb dim {query_emb.shape[-1]} != index dim {self.dim}")
+        scores, indices = self.search_batch(query_emb, top_k=top_k)
+        results: List[SearchResult] = []
+        for idx, score in zip(indices[0].tolist(), scores[0].tolist()):
+            img = self.image_paths[idx] if idx < len(self.image_paths) else ""
+            txt = self.texts[idx] if idx < len(self.texts) else ""
+            results.append(SearchResult(index=idx, score=float(score), image_path=img, text=txt))
+        return results
+
+    def search_by_text(self, query: str, model, processor, device: torch.device, top_k: int = 5) -> List[SearchResult]:
+        query_emb = encode_text(query, model, processor, device)
+        return self.search_with_embedding(query_emb, top_k=top_k)
+
+    def search_by_image(self, image_path: Union[str, Path], model, processor, device: torch.device,
+                        top_k: int = 5) -> List[SearchResult]:
+        query_emb = encode_image(image_path, model, processor, device)
+        return self.search_with_embedding(query_emb, top_k=top_k)

@@ -204,6 +204,31 @@ int clm_topk_merge(const float* cand_score, const int32_t* cand_id, int nq, int 
 int clm_topk_merge_sorted(const float* in_score, const int64_t* in_id, int nq, int lists, int k,
                           float* out_score, int64_t* out_id, void* stream);
 
+/* out[i] = q · E[i] in exact fp32 for ONE query: the reference's batch-1 scoring
+ * (src/embedding/search.py:96, src/embedding/similarity.py:32).  Rows are expected to be
+ * L2-normalised already (clm_l2norm).  HBM-streaming kernel, one warp per row. */
+int clm_cosine_gemv(const float* q_f32, const float* index_f32, int n, int dim, float* out,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Launch accounting and per-launch timing (measurement support for bench.py)
+ * ---------------------------------------------------------------------------------- */
+#define CLM_K_GEMM 0
+#define CLM_K_ATTENTION 1
+#define CLM_K_ELEMENTWISE 2
+#define CLM_K_SEARCH 3
+#define CLM_K_MERGE 4
+/* total number of kernels this library has launched in this process */
+unsigned long long clm_launch_count(void);
+/* on != 0: bracket every subsequent launch with CUDA events on its stream (clears old records) */
+int clm_prof_enable(int on);
+/* device-synchronises, then sums the recorded launches of one kind: total ms, the algorithmic
+ * FLOPs and bytes the launches were issued for, and their count */
+int clm_prof_summary(int kind, double* ms, double* flops, double* bytes, int* launches);
+/* the launch list: out[4i..4i+3] = {kind, flops, bytes, ms} in launch order; returns the number of
+ * records available (only max_records are written), -1 on a CUDA error */
+int clm_prof_records(double* out, int max_records);
+
 #ifdef __cplusplus
 }
 #endif

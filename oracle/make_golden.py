@@ -1,0 +1,210 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own code in the build container.
+
+TEST INFRASTRUCTURE.  Needs /root/reference (read-only) — it exists only in the build
+container, so the fixtures are committed and this script documents how they were made:
+
+    python -m oracle.make_golden
+
+What is executed from the reference, unmodified, imported from /root/reference:
+  * src/embedding/search.py  TextSearchIndex.__init__ / .search_with_embedding
+  * src/embedding/similarity.py  cosine_similarity / top_k_similar
+  * models/lora_adapter.py  create_lora_config / attach_lora_to_clip
+  * models/clip_model.py  encode_image / encode_text
+with `peft` replaced by oracle/peft_stub.py (the package is not installable here) and the
+transformers-5.x CLIPModel wrapped so that get_*_features return the pooled tensor as the
+4.x API the reference was written against did.
+"""
+from __future__ import annotations
+
+import io
+import sys
+import tempfile
+from contextlib import redirect_stdout
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = Path(__file__).resolve().parents[1]
+REF = Path("/root/reference")
+GOLD = ROOT / "tests" / "golden"
+
+sys.path.insert(0, str(ROOT))
+from oracle import clip_oracle as O  # noqa: E402
+from oracle import peft_stub  # noqa: E402
+
+
+def import_reference():
+    if not REF.exists():
+        raise SystemExit("/root/reference is not present: golden vectors can only be regenerated "
+                         "in the build container")
+    sys.modules["peft"] = peft_stub
+    sys.path.insert(0, str(REF))
+    import models.clip_model as ref_cm
+    import models.lora_adapter as ref_la
+    import src.embedding.search as ref_search
+    import src.embedding.similarity as ref_sim
+    return ref_cm, ref_la, ref_search, ref_sim
+
+
+class Tf4Compat(nn.Module):
+    """transformers-4.x behaviour of get_image_features/get_text_features over 5.x."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+    def get_image_features(self, pixel_values=None, **kw):
+        return O._pooled(self.model.get_image_features(pixel_values=pixel_values, **kw))
+
+    def get_text_features(self, input_ids=None, attention_mask=None, **kw):
+        return O._pooled(self.model.get_text_features(input_ids=input_ids, attention_mask=attention_mask, **kw))
+
+
+def synth_png(seed: int, path: Path) -> None:
+    """Seeded 224x224 RGB noise image (tests regenerate the same array)."""
+    from PIL import Image
+
+    rng = np.random.RandomState(seed)
+    arr = rng.randint(0, 256, size=(224, 224, 3), dtype=np.uint8)
+    Image.fromarray(arr, "RGB").save(path)
+
+
+class ShimProcessor:
+    """processor(images=...) -> the real offline CLIPImageProcessor(); processor(text=[...]) ->
+    pre-chosen input_ids (no BPE vocabulary exists on this box)."""
+
+    def __init__(self, ids_by_text):
+        from transformers import CLIPImageProcessor
+
+        self.ip = CLIPImageProcessor()
+        self.ids_by_text = ids_by_text
+
+    def __call__(self, text=None, images=None, return_tensors="pt", **kw):
+        if images is not None:
+            return self.ip(images=images, return_tensors="pt")
+        ids = torch.stack([self.ids_by_text[t] for t in text])
+        return {"input_ids": ids, "attention_mask": torch.ones_like(ids)}
+
+
+def search_golden(ref_search, ref_sim):
+    out = {}
+    buf = io.StringIO()
+    # (1) the one fixture the reference ships
+    with redirect_stdout(buf):
+        idx = ref_search.TextSearchIndex(REF / "data" / "index" / "custom_items_index.pt")
+    raw = torch.load(REF / "data" / "index" / "custom_items_index.pt", map_location="cpu")
+    out["fixture_embeddings"] = raw["embeddings"].float().numpy()
+    g = torch.Generator().manual_seed(100)
+    queries = torch.cat([raw["embeddings"].float()[:3] * 2.5, torch.randn((5, idx.dim), generator=g)], 0)
+    out["fixture_queries"] = queries.numpy()
+    for k in (1, 3, 5, 10):
+        ids, scores = [], []
+        for q in queries:
+            res = idx.search_with_embedding(q, top_k=k)
+            ids.append([r.index for r in res])
+            scores.append([r.score for r in res])
+        out[f"fixture_ids_k{k}"] = np.asarray(ids, dtype=np.int64)
+        out[f"fixture_scores_k{k}"] = np.asarray(scores, dtype=np.float32)
+    # (2) synthetic index through the same class (writer format of build_text_index.py:69-73)
+    n, d, nq = 3000, 512, 24
+    emb = O.synth_unit_rows(n, d, 4) * 1.7  # un-normalised on purpose: __init__ renormalises (:68)
+    qs = torch.randn((nq, d), generator=torch.Generator().manual_seed(5))
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "idx.pt"
+        torch.save({"embeddings": emb, "image_path": [f"img{i}.jpg" for i in range(n)],
+                    "text": [f"t{i}" for i in range(n)]}, p)
+        with redirect_stdout(buf):
+            idx2 = ref_search.TextSearchIndex(p)
+        ids, scores = [], []
+        for q in qs:
+            res = idx2.search_with_embedding(q, top_k=10)
+            ids.append([r.index for r in res])
+            scores.append([r.score for r in res])
+    out["synth_n"], out["synth_d"], out["synth_nq"] = n, d, nq
+    out["synth_ids_k10"] = np.asarray(ids, dtype=np.int64)
+    out["synth_scores_k10"] = np.asarray(scores, dtype=np.float32)
+    # (3) similarity.py
+    tv, ti = [], []
+    for q in qs[:8]:
+        v, i = ref_sim.top_k_similar(q, emb, k=5)
+        tv.append(v.numpy())
+        ti.append(i.numpy())
+    out["sim_values_k5"] = np.stack(tv)
+    out["sim_indices_k5"] = np.stack(ti)
+    out["sim_cosine_q0"] = ref_sim.cosine_similarity(qs[0], emb).numpy()[:64]
+    np.savez_compressed(GOLD / "search_golden.npz", **out)
+    print("search_golden.npz:", {k: getattr(v, "shape", v) for k, v in out.items()})
+
+
+def encoder_golden(ref_cm, ref_la):
+    out = {}
+    buf = io.StringIO()
+    cases = [("tiny-test", 4, 4, 8, 16, ["q_proj", "v_proj"]),
+             ("tiny-test", 2, 2, 8, 16, ["q_proj", "k_proj", "v_proj", "out_proj"]),
+             ("openai/clip-vit-base-patch32", 2, 2, 8, 16, ["q_proj", "v_proj"])]
+    for ci, (arch, n_img, n_txt, r, alpha, targets) in enumerate(cases):
+        model = O.build_model(arch, seed=0)
+        shim = Tf4Compat(model)
+        with tempfile.TemporaryDirectory() as td:
+            y = Path(td) / "lora.yaml"
+            y.write_text("model:\n  target_modules:\n" + "".join(f"    - \"{t}\"\n" for t in targets) +
+                         f"lora:\n  r: {r}\n  alpha: {alpha}\n  dropout: 0.1\n  bias: \"none\"\n")
+            cfg = ref_la.create_lora_config(y)                      # reference code
+            with redirect_stdout(buf):
+                peft_model = ref_la.attach_lora_to_clip(shim, cfg)  # reference code
+            trainable, total = peft_model.trainable_parameter_count()
+            peft_model.eval()
+            # non-zero B (PEFT's B=0 would make LoRA a no-op): same seeded weights the tests rebuild
+            g = torch.Generator().manual_seed(1)
+            weights = {}
+            for path in O.get_lora_weights(shim).keys():
+                mod = shim.get_submodule(path)
+                a = torch.empty_like(mod.lora_A.weight)
+                bound = 1.0 / (a.shape[1] ** 0.5)
+                a.uniform_(-bound, bound, generator=g)
+                b = torch.randn(mod.lora_B.weight.shape, generator=g) * 0.02
+                weights[path] = (a, b)
+            O.set_lora_weights(shim, weights)
+            ids, _ = O.synth_captions(n_txt, seed=3)
+            # reference encode_text tokenises with padding=True on ONE text => no padding: cut at first EOS
+            texts, ids_by_text = [], {}
+            for i in range(n_txt):
+                row = ids[i]
+                end = int((row == O.EOS_ID).nonzero()[0]) + 1
+                texts.append(f"caption-{i}")
+                ids_by_text[f"caption-{i}"] = row[:end]
+            proc = ShimProcessor(ids_by_text)
+            dev = torch.device("cpu")
+            img_emb = []
+            for i in range(n_img):
+                p = Path(td) / f"img{i}.png"
+                synth_png(1000 + i, p)
+                img_emb.append(ref_cm.encode_image(p, peft_model, proc, dev).numpy())   # reference code
+            txt_emb = [ref_cm.encode_text(t, peft_model, proc, dev).numpy() for t in texts]  # reference code
+        pre = f"case{ci}_"
+        out[pre + "arch"] = arch
+        out[pre + "targets"] = ",".join(targets)
+        out[pre + "r"], out[pre + "alpha"] = r, alpha
+        out[pre + "n_wrapped"] = len(weights)
+        out[pre + "trainable"], out[pre + "total"] = trainable, total
+        out[pre + "image_seeds"] = np.arange(1000, 1000 + n_img)
+        out[pre + "input_ids"] = ids.numpy()
+        out[pre + "image_emb"] = np.stack(img_emb)
+        out[pre + "text_emb"] = np.stack(txt_emb)
+        print(f"case {ci}: {arch} wrapped={len(weights)} trainable={trainable}")
+    out["n_cases"] = len(cases)
+    np.savez_compressed(GOLD / "encoder_golden.npz", **out)
+
+
+def main():
+    GOLD.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(8)
+    ref_cm, ref_la, ref_search, ref_sim = import_reference()
+    search_golden(ref_search, ref_sim)
+    encoder_golden(ref_cm, ref_la)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,205 @@
+"""CPU tests of the host-side mirror: C-ABI library loads and exports every symbol that
+include/clm_b200.h declares, LoRA config / matching / PEFT on-disk layout, architecture
+tables, tokenizer stand-in, index-file handling.  No compute call is made (no GPU here).
+"""
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from clip_lora_match_b200 import _lib
+from clip_lora_match_b200.models import clip_model as CM
+from clip_lora_match_b200.models import lora_adapter as LA
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "clm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(clm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/clm_b200.h but not exported"
+    # and the ctypes table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.clm_version() >= 100
+
+
+def test_invalid_arguments_return_error_codes_not_crashes():
+    lib = _lib.load()
+    rc = lib.clm_layernorm(None, None, None, None, 4, 768, 1e-5, None)
+    assert rc != 0 and b"clm_layernorm" in lib.clm_last_error()
+    rc = lib.clm_search_topk(None, None, 1, 1, 512, 10, 1, None, None, None)
+    assert rc != 0
+    with pytest.raises(_lib.ClmError):
+        _lib.check(rc, "clm_search_topk")
+    assert lib.clm_search_num_splits(4096, 1250000) >= 1
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from clip_lora_match_b200 import kernels as K
+
+    with pytest.raises(ValueError, match="CUDA"):
+        K.layernorm(torch.zeros(2, 512), torch.ones(512), torch.zeros(512))
+    with pytest.raises(ValueError):
+        CM.B200ClipModel(CM.ARCHS["openai/clip-vit-base-patch32"], {}, device="cpu")
+
+
+def test_struct_layout_matches_header():
+    import ctypes as C
+
+    assert C.sizeof(_lib.TowerConfig) == 14 * 4
+    assert C.sizeof(_lib.LayerWeights) == 16 * 8
+    assert C.sizeof(_lib.TowerWeights) == 9 * 8
+
+
+# ---- LoRA -----------------------------------------------------------------------------------
+def test_create_lora_config_defaults_and_yaml(tmp_path):
+    y = tmp_path / "lora.yaml"
+    y.write_text("lora: {}\nmodel: {}\n")
+    c = LA.create_lora_config(y)
+    assert (c.r, c.lora_alpha, c.lora_dropout, c.bias) == (8, 16, 0.1, "none")
+    assert c.target_modules == ["q_proj", "v_proj"] and c.task_type == "FEATURE_EXTRACTION"
+    shipped = LA.create_lora_config(os.path.join(ROOT, "clip_lora_match_b200", "config", "lora_config.yaml"))
+    assert shipped.target_modules == ["q_proj", "k_proj", "v_proj", "out_proj"]
+    assert shipped.scaling == 2.0
+    with pytest.raises(FileNotFoundError):
+        LA.create_lora_config(tmp_path / "missing.yaml")
+
+
+def test_target_matching_hits_both_towers():
+    names = LA.linear_module_paths(vision_layers=12, text_layers=12)
+    qv = LA.match_target_modules(names, ["q_proj", "v_proj"])
+    assert len(qv) == 48  # 24 attention blocks x 2 (golden: case2 n_wrapped)
+    assert any(n.startswith("text_model.") for n in qv) and any(n.startswith("vision_model.") for n in qv)
+    assert len(LA.match_target_modules(names, ["q_proj", "k_proj", "v_proj", "out_proj"])) == 96
+    assert LA.match_target_modules(names, ["proj"]) == []  # suffix must follow a dot
+    assert LA.match_target_modules(names, ["visual_projection"]) == ["visual_projection"]
+
+
+def _dims(width_v=768, width_t=512, layers=2):
+    d = {}
+    for tower, w in (("text_model", width_t), ("vision_model", width_v)):
+        for i in range(layers):
+            for m in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                d[f"{tower}.encoder.layers.{i}.self_attn.{m}"] = (w, w)
+            d[f"{tower}.encoder.layers.{i}.mlp.fc1"] = (4 * w, w)
+    return d
+
+
+def test_adapter_init_export_roundtrip(tmp_path):
+    cfg = LA.LoraConfig(r=8, lora_alpha=16, target_modules=["q_proj", "v_proj"])
+    ad = LA.init_lora_adapter(_dims(), cfg, seed=1, init_b_std=0.02, base_model_name="openai/clip-vit-base-patch32")
+    assert len(ad.weights) == 8
+    a, b = ad.weights["vision_model.encoder.layers.0.self_attn.q_proj"]
+    assert a.shape == (8, 768) and b.shape == (768, 8)
+    assert a.abs().max() <= 1 / 768 ** 0.5 + 1e-7
+    zero_b = LA.init_lora_adapter(_dims(), cfg, seed=1)
+    assert all(bb.abs().max() == 0 for _, bb in zero_b.weights.values())  # PEFT default
+    out = LA.save_lora_adapter(ad, tmp_path / "epoch_1")
+    assert (out / "adapter_config.json").exists() and (out / "adapter_model.safetensors").exists()
+    raw = json.loads((out / "adapter_config.json").read_text())
+    assert raw["peft_type"] == "LORA" and raw["r"] == 8 and raw["lora_alpha"] == 16
+    from safetensors.torch import load_file
+
+    keys = set(load_file(str(out / "adapter_model.safetensors")).keys())
+    assert "base_model.model.text_model.encoder.layers.1.self_attn.v_proj.lora_B.weight" in keys
+    back = LA.load_lora_adapter(out)
+    assert back.config.r == 8 and back.scaling == 2.0 and set(back.weights) == set(ad.weights)
+    for k in ad.weights:
+        assert torch.equal(back.weights[k][0], ad.weights[k][0])
+        assert torch.equal(back.weights[k][1], ad.weights[k][1])
+
+
+def test_adapter_layout_interoperates_with_peft_semantics(tmp_path):
+    """An adapter saved by the oracle's peft stand-in (the layout the reference's
+    train_lora.py:243-247 writes) loads here, and vice versa."""
+    from oracle import clip_oracle as O
+    from oracle import peft_stub
+
+    model = O.build_model("tiny-test", seed=0)
+    pm = peft_stub.get_peft_model(model, peft_stub.LoraConfig(r=8, lora_alpha=16,
+                                                              target_modules=["q_proj", "v_proj"]))
+    pm.save_pretrained(tmp_path / "a")
+    ad = LA.load_lora_adapter(tmp_path / "a")
+    assert len(ad.weights) == 8 and ad.config.target_modules == ["q_proj", "v_proj"]
+    LA.save_lora_adapter(ad, tmp_path / "b")
+    model2 = O.build_model("tiny-test", seed=0)
+    pm2 = peft_stub.PeftModel.from_pretrained(model2, str(tmp_path / "b"))
+    w1, w2 = O.get_lora_weights(model), O.get_lora_weights(model2)
+    assert set(w1) == set(w2)
+    for k in w1:
+        assert torch.equal(w1[k][0], w2[k][0])
+    assert pm2.peft_config.r == 8
+
+
+def test_unsupported_lora_targets_fail_loudly():
+    cfg = LA.LoraConfig(target_modules=["fc1"])
+    with pytest.raises(NotImplementedError):
+        LA.init_lora_adapter(_dims(), cfg)
+    with pytest.raises(FileNotFoundError):
+        LA.load_lora_adapter("/nonexistent/adapter")
+
+
+# ---- architectures / processor ---------------------------------------------------------------
+def test_arch_tables_agree_with_transformers_configs():
+    from oracle import clip_oracle as O
+
+    for name in ("openai/clip-vit-base-patch32", "openai/clip-vit-base-patch16", "openai/clip-vit-large-patch14"):
+        arch = CM.arch_from_name(name)
+        back = CM.arch_from_hf_config(CM.hf_config_for(arch), name)
+        assert back == arch
+        vw, vl, vh, vm, p, tw, tl, th, tm, proj = O.ARCH_TABLE[name]
+        assert (arch.vision.width, arch.vision.layers, arch.vision.heads, arch.vision.mlp, arch.patch) == (vw, vl, vh, vm, p)
+        assert (arch.text.width, arch.text.layers, arch.text.heads, arch.text.mlp, arch.proj_dim) == (tw, tl, th, tm, proj)
+    assert CM.ARCHS["openai/clip-vit-base-patch32"].vision_tokens == 50
+    assert CM.ARCHS["openai/clip-vit-base-patch16"].vision_tokens == 197
+    assert CM.ARCHS["openai/clip-vit-large-patch14"].vision_tokens == 257
+    with pytest.raises(ValueError):
+        CM.arch_from_name("openai/clip-vit-huge")
+
+
+def test_fallback_tokenizer_framing():
+    tok = CM.FallbackTokenizer()
+    enc = tok(["tas pink kanken, ditemukan di lab iot", "kaca mata"], padding=True, truncation=True)
+    ids, mask = enc["input_ids"], enc["attention_mask"]
+    assert ids.shape == mask.shape and ids.shape[0] == 2
+    assert (ids[:, 0] == CM.BOS_ID).all()
+    for row, m in zip(ids, mask):
+        n = int(m.sum())
+        assert row[n - 1] == CM.EOS_ID and (row[n:] == CM.EOS_ID).all()
+        assert (row[1:n - 1] < CM.BOS_ID).all()
+    long = tok(["x " * 200], padding=True, truncation=True)["input_ids"]
+    assert long.shape[1] == 77 and long[0, -1] == CM.EOS_ID
+    assert tok(["a"], padding="max_length")["input_ids"].shape[1] == 77
+    # deterministic
+    assert torch.equal(tok(["same text"])["input_ids"], tok(["same text"])["input_ids"])
+
+
+def test_config_errors_match_reference_behaviour(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        CM.load_clip_model(tmp_path / "missing.yaml")
+    y = tmp_path / "clip.yaml"
+    y.write_text("model:\n  name: openai/clip-vit-base-patch32\n  device: cpu\n")
+    with pytest.raises(ValueError, match="CUDA"):
+        CM.load_clip_model(y)
+
+
+def test_shard_bounds_partition_rows():
+    from clip_lora_match_b200.src.embedding.search import shard_bounds
+
+    for n, w in ((10_000_000, 8), (6, 4), (7, 8), (1, 1)):
+        spans = [shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard_bounds(10_000_000, 3, 8) == (3_750_000, 5_000_000)

@@ -1,0 +1,268 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI, via the reference-shaped Python
+surface) against the CPU oracle on the same seeded inputs, against the committed golden
+fixtures, and — at BASELINE sizes — through size-independent properties.
+
+Tolerances (BASELINE.json north_star): per-vector cosine >= 0.999 vs the fp32 oracle; top-k
+ids identical except for ties within 1e-4 in oracle score.  Stricter diagnostics (mean-centred
+cosine, relative L2) are asserted too because plain cosine is weak on random-init weights
+(SURVEY.md §7 H1).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+COS_MIN = 0.999          # north_star
+CENTERED_COS_MIN = 0.98  # diagnostic bar (bf16 operands vs fp32 oracle)
+REL_L2_MAX = 0.03
+
+
+def _b200_model(arch_name, oracle_model, lora_weights, r, alpha, targets, device):
+    from clip_lora_match_b200.models import clip_model as CM
+    from clip_lora_match_b200.models.lora_adapter import LoraAdapter, LoraConfig
+
+    if arch_name == "tiny-test":
+        arch = CM.arch_from_hf_config(O.hf_config(arch_name), arch_name)
+    else:
+        arch = CM.arch_from_name(arch_name)
+    lora = None
+    if lora_weights:
+        lora = LoraAdapter(LoraConfig(r=r, lora_alpha=alpha, target_modules=list(targets)), lora_weights)
+    return CM.B200ClipModel(arch, O.base_state_dict(oracle_model), lora=lora, device=device)
+
+
+def _assert_parity(name, got, ref):
+    m = O.parity_metrics(got, ref)
+    print(f"[parity] {name}: {m}")
+    assert torch.isfinite(got).all(), f"{name}: non-finite output"
+    assert m["cos_min"] >= COS_MIN, f"{name}: {m}"
+    assert m["centered_cos_min"] >= CENTERED_COS_MIN, f"{name}: {m}"
+    assert m["rel_l2_max"] <= REL_L2_MAX, f"{name}: {m}"
+    n = got.float().norm(dim=-1)
+    assert torch.allclose(n, torch.ones_like(n), atol=1e-5), f"{name}: rows not unit norm"
+
+
+CASES = [
+    # arch, n_img, n_txt, r, alpha, targets
+    ("tiny-test", 5, 7, 8, 16, ("q_proj", "v_proj")),
+    ("tiny-test", 3, 3, 8, 16, ("q_proj", "k_proj", "v_proj", "out_proj")),   # shipped YAML's targets
+    ("tiny-test", 3, 3, 8, 16, ()),                                           # no LoRA
+    ("openai/clip-vit-base-patch32", 6, 6, 8, 16, ("q_proj", "v_proj")),      # config 1
+    ("openai/clip-vit-base-patch16", 3, 3, 16, 32, ("q_proj", "v_proj")),     # config 2
+    ("openai/clip-vit-large-patch14", 2, 2, 16, 32, ("q_proj", "v_proj")),    # config 3
+]
+
+
+@pytest.mark.parametrize("arch,n_img,n_txt,r,alpha,targets", CASES)
+def test_encoder_parity_vs_oracle(cuda_device, arch, n_img, n_txt, r, alpha, targets):
+    torch.set_num_threads(os.cpu_count() or 8)
+    model = O.build_model(arch, seed=0)
+    weights = O.synthetic_lora(model, r, alpha, targets, seed=1) if targets else {}
+    gpu = _b200_model(arch, model, weights, r, alpha, targets, cuda_device)
+    pv = O.synth_images(n_img, seed=2)
+    ids, mask = O.synth_captions(n_txt, seed=3)
+    ref_img = O.encode_images(model, pv)
+    ref_txt = O.encode_texts(model, ids, mask)
+    got_img = gpu.encode_images(pv).cpu()
+    got_txt = gpu.encode_texts(ids).cpu()
+    tag = f"{arch.split('/')[-1]}_r{r}_{len(targets)}t"
+    _assert_parity(tag + "_image", got_img, ref_img)
+    _assert_parity(tag + "_text", got_txt, ref_txt)
+    # un-normalised features (embed_image(normalize=False) surface)
+    raw = gpu.encode_images(pv, normalize=False).cpu()
+    ref_raw = O.encode_images(model, pv, normalize=False)
+    assert O.parity_metrics(raw, ref_raw)["rel_l2_max"] <= REL_L2_MAX
+    # LoRA must actually change the output (a fused no-op would also "pass" parity vs itself)
+    if targets:
+        gpu.set_lora(None)
+        base = gpu.encode_images(pv).cpu()
+        assert (base - got_img).abs().max() > 1e-4
+
+
+def test_encoder_matches_reference_golden_vectors(cuda_device):
+    """B/32 + LoRA r=8 q/v embeddings produced by the reference's own encode_image/encode_text
+    (tests/golden/encoder_golden.npz, case 2) through the reference-shaped surface."""
+    eg = np.load(os.path.join(GOLD, "encoder_golden.npz"))
+    for ci in range(int(eg["n_cases"])):
+        pre = f"case{ci}_"
+        arch = str(eg[pre + "arch"])
+        targets = tuple(str(eg[pre + "targets"]).split(","))
+        r, alpha = int(eg[pre + "r"]), int(eg[pre + "alpha"])
+        model = O.build_model(arch, seed=0)
+        weights = O.synthetic_lora(model, r, alpha, targets, seed=1)
+        gpu = _b200_model(arch, model, weights, r, alpha, targets, cuda_device)
+        from transformers import CLIPImageProcessor
+
+        imgs = [np.random.RandomState(int(s)).randint(0, 256, size=(224, 224, 3), dtype=np.uint8)
+                for s in eg[pre + "image_seeds"]]
+        pv = CLIPImageProcessor()(images=imgs, return_tensors="pt")["pixel_values"]
+        _assert_parity(f"golden_case{ci}_image", gpu.encode_images(pv).cpu(),
+                       torch.from_numpy(eg[pre + "image_emb"]))
+        n_txt = eg[pre + "text_emb"].shape[0]
+        ids = torch.from_numpy(eg[pre + "input_ids"])[:n_txt]
+        _assert_parity(f"golden_case{ci}_text", gpu.encode_texts(ids).cpu(),
+                       torch.from_numpy(eg[pre + "text_emb"]))
+
+
+def test_reference_style_single_item_api(cuda_device, tmp_path):
+    """encode_image(path, model, processor, device) / encode_text(text, ...) return (d,) CPU fp32
+    and agree with the batched path; errors are the reference's."""
+    from PIL import Image
+
+    from clip_lora_match_b200.models import clip_model as CM
+
+    model = O.build_model("tiny-test", seed=0)
+    gpu = _b200_model("tiny-test", model, {}, 8, 16, (), cuda_device)
+    proc = CM.ClmProcessor("openai/clip-vit-base-patch32")
+    arr = np.random.RandomState(7).randint(0, 256, size=(300, 260, 3), dtype=np.uint8)
+    p = tmp_path / "q.png"
+    Image.fromarray(arr, "RGB").save(p)
+    e = CM.encode_image(p, gpu, proc, cuda_device)
+    assert e.shape == (64,) and e.dtype == torch.float32 and e.device.type == "cpu"
+    pv = proc(images=Image.open(p).convert("RGB"), return_tensors="pt")["pixel_values"]
+    ref = O.encode_images(model, pv)[0]
+    assert torch.nn.functional.cosine_similarity(e, ref, dim=0) >= COS_MIN
+    t = CM.encode_text("tas pink kanken, ditemukan di lab iot", gpu, proc, cuda_device)
+    ids = proc(text=["tas pink kanken, ditemukan di lab iot"])["input_ids"]
+    reft = O.encode_texts(model, ids, None)[0]
+    assert t.shape == (64,) and torch.nn.functional.cosine_similarity(t, reft, dim=0) >= COS_MIN
+    with pytest.raises(FileNotFoundError):
+        CM.encode_image(tmp_path / "nope.png", gpu, proc, cuda_device)
+    # empty and ragged batches
+    assert gpu.encode_images(torch.empty((0, 3, 224, 224))).shape == (0, 64)
+    short = gpu.encode_texts(ids).cpu()  # [1, L<77]: padded with EOS inside
+    assert torch.allclose(short[0], t, atol=1e-6)
+
+
+def test_micro_batching_is_invisible(cuda_device):
+    """A workspace too small for the batch splits it into micro-batches; results are identical."""
+    model = O.build_model("tiny-test", seed=0)
+    gpu = _b200_model("tiny-test", model, {}, 8, 16, (), cuda_device)
+    pv = O.synth_images(37, seed=2)
+    full = gpu.encode_images(pv).cpu()
+    one = gpu._lib.clm_tower_workspace_bytes(gpu._towers["vision"], 1)
+    gpu.max_workspace_bytes = one * 5
+    gpu._workspace = None
+    split = gpu.encode_images(pv).cpu()
+    assert torch.equal(full, split)
+
+
+# ------------------------------------------------------------------------------------------
+# search
+# ------------------------------------------------------------------------------------------
+def _check_ids(name, s, i, sims, k):
+    ref_s, ref_i = torch.topk(sims, k, dim=-1, largest=True, sorted=True)
+    s, i = s.cpu(), i.cpu()
+    assert torch.allclose(s, ref_s, atol=2e-6, rtol=1e-5), f"{name}: scores differ"
+    assert O.ids_match_with_ties(ref_s, ref_i, i, sims), f"{name}: ids differ beyond the 1e-4 tie window"
+
+
+def test_search_index_on_shipped_fixture_matches_reference(cuda_device, tmp_path):
+    """TextSearchIndex over the reference's own 6x512 index (both metadata key spellings),
+    ids and scores exactly as the reference's search_with_embedding returned them."""
+    from clip_lora_match_b200.src.embedding.search import SearchResult, TextSearchIndex
+
+    sg = np.load(os.path.join(GOLD, "search_golden.npz"))
+    emb = torch.from_numpy(sg["fixture_embeddings"])
+    qs = torch.from_numpy(sg["fixture_queries"])
+    for keys in (("image_paths", "texts"), ("image_path", "text")):
+        p = tmp_path / f"idx_{keys[0]}.pt"
+        torch.save({"embeddings": emb, keys[0]: [f"i{j}.jpg" for j in range(6)],
+                    keys[1]: [f"t{j}" for j in range(6)]}, p)
+        idx = TextSearchIndex(p)
+        assert (idx.num_items, idx.dim) == (6, 512)
+        for k in (1, 3, 5, 10):
+            for qi, q in enumerate(qs):
+                res = idx.search_with_embedding(q, top_k=k)
+                assert all(isinstance(r, SearchResult) for r in res)
+                assert [r.index for r in res] == sg[f"fixture_ids_k{k}"][qi].tolist()
+                assert np.allclose([r.score for r in res], sg[f"fixture_scores_k{k}"][qi], atol=2e-6)
+                assert res[0].image_path == f"i{res[0].index}.jpg" and res[0].text == f"t{res[0].index}"
+    # reference error behaviour
+    with pytest.raises(ValueError):
+        idx.search_with_embedding(torch.zeros(2, 512))
+    with pytest.raises(ValueError):
+        idx.search_with_embedding(torch.zeros(256))
+    with pytest.raises(FileNotFoundError):
+        TextSearchIndex(tmp_path / "missing.pt")
+    torch.save({"foo": 1}, tmp_path / "bad.pt")
+    with pytest.raises(ValueError):
+        TextSearchIndex(tmp_path / "bad.pt")
+
+
+def test_search_matches_reference_synthetic_golden(cuda_device):
+    from clip_lora_match_b200.src.embedding.search import TextSearchIndex
+    from clip_lora_match_b200.src.embedding.similarity import cosine_similarity, top_k_similar
+
+    sg = np.load(os.path.join(GOLD, "search_golden.npz"))
+    n, d, nq = int(sg["synth_n"]), int(sg["synth_d"]), int(sg["synth_nq"])
+    emb = O.synth_unit_rows(n, d, 4) * 1.7
+    qs = torch.randn((nq, d), generator=torch.Generator().manual_seed(5))
+    idx = TextSearchIndex(embeddings=emb, verbose=False)
+    s, i = idx.search_batch(qs, top_k=10)
+    sims = O.normalize_rows(qs) @ O.normalize_rows(emb).T
+    assert np.allclose(s.cpu().numpy(), sg["synth_scores_k10"], atol=2e-6)
+    assert O.ids_match_with_ties(torch.from_numpy(sg["synth_scores_k10"]),
+                                 torch.from_numpy(sg["synth_ids_k10"]), i.cpu(), sims)
+    v, ix = top_k_similar(qs[0], emb, k=5)
+    assert v.shape == (5,) and ix.dtype == torch.int64
+    assert np.allclose(v.numpy(), sg["sim_values_k5"][0], atol=2e-6)
+    assert ix.tolist() == sg["sim_indices_k5"][0].tolist()
+    cos = cosine_similarity(qs[0], emb)
+    assert cos.shape == (n,) and np.allclose(cos[:64].numpy(), sg["sim_cosine_q0"], atol=2e-6)
+
+
+def test_search_config1_full(cuda_device):
+    """BASELINE config 1: 1000 queries, top-10 over 10k x 512."""
+    from clip_lora_match_b200.src.embedding.search import TextSearchIndex
+
+    e = O.synth_unit_rows(10_000, 512, 4)
+    q = O.synth_unit_rows(1000, 512, 5)
+    idx = TextSearchIndex(embeddings=e, verbose=False)
+    s, i = idx.search_batch(q, top_k=10)
+    _check_ids("cfg1", s, i, q @ e.T, 10)
+
+
+@pytest.mark.parametrize("n,nq,k", [(2_000_000, 512, 10), (10_000_000, 4096, 10), (10_000_000, 256, 50)])
+def test_search_at_scale_properties(cuda_device, n, nq, k):
+    """BASELINE configs 4/5 sizes (10M x 768 on one GPU): size-independent properties.
+    (a) planted near-duplicates of each query must come back as top-1 with the planted id;
+    (b) scores are sorted descending, ids unique and in range;
+    (c) every returned score equals the exact fp32 dot product of its row;
+    (d) for a sample of queries the result equals an exact fp32 torch scan."""
+    d = 768
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(4)
+    e = torch.empty((n, d), dtype=torch.float32, device=dev)
+    step = 1_000_000
+    for lo in range(0, n, step):
+        blk = torch.randn((min(step, n - lo), d), generator=g, device=dev)
+        e[lo:lo + blk.shape[0]] = blk / blk.norm(dim=-1, keepdim=True)
+    q = torch.randn((nq, d), generator=g, device=dev)
+    q = q / q.norm(dim=-1, keepdim=True)
+    planted = torch.randperm(n, generator=g, device=dev)[:nq]
+    noise = torch.randn((nq, d), generator=g, device=dev) * 0.01
+    rows = q + noise
+    e[planted] = rows / rows.norm(dim=-1, keepdim=True)
+    from clip_lora_match_b200 import kernels as K
+
+    eb = e.to(torch.bfloat16)
+    s, i = K.search_topk(q, q.to(torch.bfloat16), eb, e, k)
+    torch.cuda.synchronize()
+    assert torch.equal(i[:, 0], planted), "(a) planted rows not returned as top-1"
+    assert (s[:, :-1] >= s[:, 1:]).all(), "(b) scores not sorted"
+    assert (i >= 0).all() and (i < n).all()
+    assert (torch.sort(i, dim=1).values.diff(dim=1) != 0).all(), "(b) duplicate ids"
+    exact = torch.einsum("qkd,qd->qk", e[i.reshape(-1)].reshape(nq, k, d), q)
+    assert torch.allclose(s, exact, atol=2e-6, rtol=1e-5), "(c) scores are not exact fp32 dots"
+    sample = torch.arange(0, nq, max(1, nq // 16), device=dev)[:16]
+    sims = q[sample] @ e.T
+    ref_s, ref_i = torch.topk(sims, k, dim=-1)
+    assert torch.allclose(s[sample], ref_s, atol=2e-6, rtol=1e-5)
+    assert O.ids_match_with_ties(ref_s.cpu(), ref_i.cpu(), i[sample].cpu(), sims.cpu()), "(d) ids differ"

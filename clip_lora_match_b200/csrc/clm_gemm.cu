@@ -6,36 +6,46 @@
 // neither needs a transpose: TMA drops 64-column (128-byte) swizzled boxes into shared
 // memory and tcgen05.mma reads them through K-major SWIZZLE_128B descriptors.
 //
+// Two variants of one kernel (template kCtas):
+//   kCtas = 2  CTA pair (cluster of 2, tcgen05 cta_group::2): a 256 x 256 tile per pair; each CTA
+//              TMA-loads its own 128 rows of A and HALF of the B tile, the leader CTA's MMA thread
+//              issues UMMA M=256 that reads both CTAs' shared memory and writes both CTAs' TMEM.
+//              Per-SM operand traffic drops by a third (32 KiB instead of 48 KiB per k-block) and
+//              the freed shared memory gives a 6-deep ring.  Used when N % 256 == 0.
+//   kCtas = 1  single CTA, 128 x BN tile (BN = 256 / 128 / 64): everything else (LoRA
+//              down-projection N = 64, tiny shapes).
+//
 // CTA = 320 threads:
 //   warp 0      TMA producer (one elected lane)          smem ring: full[]/empty[] mbarriers
 //   warp 1      TMEM allocator + MMA issuer (one lane)   accumulator ring: tmem_full[]/tmem_empty[]
-//   warps 2..9  epilogue: tcgen05.ld -> bias/QuickGELU/residual -> global stores.  Warp w reads
-//               TMEM lane quarter (w % 4) and column half ((w - 2) / 4); the fp32 residual of the
-//               next 32-column chunk is prefetched while the current chunk is converted/stored.
+//   warps 2..9  epilogue: tcgen05.ld -> smem transpose -> bias/QuickGELU/residual -> coalesced
+//               global stores.  Warp w reads TMEM lane quarter (w % 4), column half ((w - 2) / 4).
 // The accumulator is double buffered in TMEM (2 x BN fp32 columns) so the epilogue of tile i
-// overlaps the MMAs of tile i+1.  The grid is persistent: min(tiles, #SM) CTAs stride over
-// the tile list (n fastest, so CTAs that run together share A rows through L2).
+// overlaps the MMAs of tile i+1.  The grid is persistent and strides over the tile list (n
+// fastest, so CTAs that run together share A rows through L2).
 //
 // The optional (A2, W2) pair is the unmerged LoRA update folded in as extra K blocks of the
 // SAME accumulator: y = x W^T + (x A^T)(s B)^T  (K4/K6 in §2b).
+#include <stdlib.h>
+
 #include "clm_common.cuh"
 
 namespace {
 
 using namespace clm;
 
-constexpr int BM = 128;
+constexpr int BM = 128;  // rows per CTA
 constexpr int kEpiWarps = 8;
 constexpr int BK = 64;
 constexpr int kNumThreads = 320;
 constexpr int kAccStages = 2;
 
-template <int BN>
+template <int BN, int kCtas>
 struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / kCtas) * BK * 2;  // this CTA's share of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (kStageBytes == 49152) ? 4 : (kStageBytes == 32768 ? 6 : 8);
   static constexpr int kTmemCols = kAccStages * BN;  // 512 / 256 / 128: powers of two
   static constexpr int kSmemBytes =
       kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiWarps * 4096 /*epilogue staging*/;
@@ -51,12 +61,74 @@ struct EpiParams {
   int act;
 };
 
-template <int BN>
+// ---- cta_group::2 helpers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      :
+      : "r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32  remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64  _, [remAddr32];\n\t"
+      "}"
+      :
+      : "r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int BN, int kCtas>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
             int M, int N, int kb_main, int kb_ext, EpiParams ep) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, kCtas>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -69,8 +141,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (kCtas == 2) ? cluster_ctarank() : 0u;  // position inside the CTA pair
+  const int worker = (kCtas == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int num_workers = (kCtas == 2) ? (gridDim.x >> 1) : gridDim.x;
+  constexpr int TM = BM * kCtas;  // tile rows per worker
   const int n_tiles = (N + BN - 1) / BN;
-  const int m_tiles = (M + BM - 1) / BM;
+  const int m_tiles = (M + TM - 1) / TM;
   const int num_tiles = m_tiles * n_tiles;
   const int kb_total = kb_main + kb_ext;
 
@@ -87,74 +163,92 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], kEpiWarps * kCtas);  // one arrive per epilogue warp of the pair
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_base_slot, C::kTmemCols);
-    tmem_relinquish();
+    if (kCtas == 2) {
+      tmem_alloc_2sm(tmem_base_slot, C::kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_base_slot, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer (every CTA loads its own A rows and its share of B) ======
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BM;
-        const int n0 = (tile % n_tiles) * BN;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        const int m0 = (tile / n_tiles) * TM + static_cast<int>(rank) * BM;
+        const int n0 = (tile % n_tiles) * BN + static_cast<int>(rank) * (BN / kCtas);
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
-          mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
-          if (kb < kb_main) {
-            tma_load_2d(sa, &map_a, &full[stage], kb * BK, m0);
-            tma_load_2d(sb, &map_b, &full[stage], kb * BK, n0);
+          const CUtensorMap* ma = kb < kb_main ? &map_a : &map_a2;
+          const CUtensorMap* mb = kb < kb_main ? &map_b : &map_b2;
+          const int kc = (kb < kb_main ? kb : kb - kb_main) * BK;
+          if (kCtas == 2) {
+            // the leader's barrier collects the bytes of BOTH CTAs
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::kStageBytes);
+            tma_load_2d_2sm(sa, ma, &full[stage], kc, m0);
+            tma_load_2d_2sm(sb, mb, &full[stage], kc, n0);
           } else {
-            tma_load_2d(sa, &map_a2, &full[stage], (kb - kb_main) * BK, m0);
-            tma_load_2d(sb, &map_b2, &full[stage], (kb - kb_main) * BK, n0);
+            mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
+            tma_load_2d(sa, ma, &full[stage], kc, m0);
+            tma_load_2d(sb, mb, &full[stage], kc, n0);
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
-      for (int kb = 0; kb < kb_total; ++kb) {
-        mbar_wait(&full[stage], phase);
+    // ================= MMA issuer (leader CTA only) =================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t b_addr = a_addr + C::kABytes;
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(smem + stage * C::kStageBytes);
+            const uint32_t b_addr = a_addr + C::kABytes;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advancing 16 bf16 (32 B) along K inside the 128-B swizzle atom
-            const uint64_t da = umma_desc_sw128(a_addr + k * 32, 1024);
-            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 1024);
-            umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advancing 16 bf16 (32 B) along K inside the 128-B swizzle atom
+              const uint64_t da = umma_desc_sw128(a_addr + k * 32, 1024);
+              const uint64_t db = umma_desc_sw128(b_addr + k * 32, 1024);
+              if (kCtas == 2) umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if (kCtas == 2) {
+              umma_commit_2sm(&empty[stage]);                           // frees the slot in both CTAs
+              if (kb == kb_total - 1) umma_commit_2sm(&tmem_full[acc]);  // accumulators ready (both)
+            } else {
+              umma_commit(&empty[stage]);
+              if (kb == kb_total - 1) umma_commit(&tmem_full[acc]);
+            }
           }
-          umma_commit(&empty[stage]);                          // smem slot free when MMAs done
-          if (kb == kb_total - 1) umma_commit(&tmem_full[acc]);  // accumulator ready
+          __syncwarp();
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ================= epilogue warps =================
@@ -172,8 +266,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int rsub = lane >> 3;         // row offset inside each group of 4 rows
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * BM + q * 32;
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      const int m0 = (tile / n_tiles) * TM + static_cast<int>(rank) * BM + q * 32;
       const int n0 = (tile % n_tiles) * BN + half * (BN / 2);
       float4 rcur[8], rnxt[8];  // residual of the current / next chunk (coalesced layout)
       auto load_residual = [&](float4 (&dst)[8], int col0) {
@@ -238,32 +332,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (kCtas == 2) mbar_arrive_cta(&tmem_empty[acc], 0);  // the leader's MMA thread waits on it
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if (kCtas == 2) tmem_dealloc_2sm(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
+  }
 }
 
-template <int BN>
+template <int BN, int kCtas>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2,
                 const CUtensorMap& mb2, int M, int N, int kb_main, int kb_ext, const EpiParams& ep,
                 cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, kCtas>;
   static bool attr_set = false;
   if (!attr_set) {
-    CLM_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CLM_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < clm_num_sms() ? tiles : clm_num_sms();
-  gemm_kernel<BN><<<grid, kNumThreads, C::kSmemBytes, stream>>>(ma, mb, ma2, mb2, M, N, kb_main,
-                                                                kb_ext, ep);
-  CLM_CUDA_CHECK(cudaGetLastError());
+  const int tiles = ((M + BM * kCtas - 1) / (BM * kCtas)) * ((N + BN - 1) / BN);
+  const int max_workers = clm_num_sms() / kCtas;
+  const int workers = tiles < max_workers ? tiles : max_workers;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(workers * kCtas);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, kCtas>, ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep));
   return CLM_OK;
 }
 
@@ -290,14 +401,24 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
     CLM_REQUIRE(lda2 % 8 == 0 && ldw2 % 8 == 0 && lda2 >= K2 && ldw2 >= K2,
                 "clm_gemm_epi: bad extension leading dims");
   }
-  const int BN = (N >= 256 && N % 256 == 0) ? 256 : ((N >= 128 && N % 128 == 0) ? 128 : (N > 128 ? 256 : (N > 64 ? 128 : 64)));
+  static int force_1cta = -1;  // CLM_GEMM_1CTA=1 forces the single-CTA kernel (A/B measurements)
+  if (force_1cta < 0) {
+    const char* e = getenv("CLM_GEMM_1CTA");
+    force_1cta = (e && e[0] == '1') ? 1 : 0;
+  }
+  // CTA-pair kernel for the big GEMMs; single-CTA kernel for narrow / ragged N and tiny M
+  const bool pair = !force_1cta && (N % 256 == 0) && (M > 128);
+  const int BN = pair ? 256
+                      : ((N >= 256 && N % 256 == 0) ? 256
+                         : ((N >= 128 && N % 128 == 0) ? 128 : (N > 128 ? 256 : (N > 64 ? 128 : 64))));
+  const int b_box_rows = pair ? BN / 2 : BN;
   CUtensorMap ma, mb, ma2, mb2;
   int rc;
   if ((rc = clm_make_tmap_bf16_2d(&ma, A, M, K, lda, BK, BM))) return rc;
-  if ((rc = clm_make_tmap_bf16_2d(&mb, W, N, K, ldw, BK, BN))) return rc;
+  if ((rc = clm_make_tmap_bf16_2d(&mb, W, N, K, ldw, BK, b_box_rows))) return rc;
   if (has_ext) {
     if ((rc = clm_make_tmap_bf16_2d(&ma2, A2, M, K2, lda2, BK, BM))) return rc;
-    if ((rc = clm_make_tmap_bf16_2d(&mb2, W2, N, K2, ldw2, BK, BN))) return rc;
+    if ((rc = clm_make_tmap_bf16_2d(&mb2, W2, N, K2, ldw2, BK, b_box_rows))) return rc;
   } else {
     ma2 = ma;
     mb2 = mb;
@@ -317,10 +438,11 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
                        static_cast<double>(M) * N * (ep.out_f32 ? 4 : 2) +
                        (residual ? 4.0 * M * N : 0.0);
   ProfScope prof(CLM_K_GEMM, flops, bytes, stream);
+  if (pair) return launch_gemm<256, 2>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);
   switch (BN) {
-    case 256: return launch_gemm<256>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);
-    case 128: return launch_gemm<128>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);
-    default: return launch_gemm<64>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);
+    case 256: return launch_gemm<256, 1>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);
+    case 128: return launch_gemm<128, 1>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);
+    default: return launch_gemm<64, 1>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);
   }
 }
 

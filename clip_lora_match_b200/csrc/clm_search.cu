@@ -35,6 +35,7 @@ constexpr int kTmemCols = kAccStages * BN;
 
 struct SearchParams {
   int nq, n, kblocks, q_tiles, splits, tiles_n, kc, stages;
+  float* thr_io;  // per-query running lower bound of the kc-th best score, shared by all units (or null)
   float* cand_score;
   int32_t* cand_id;
 };
@@ -153,8 +154,19 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const int t1 = static_cast<int>(static_cast<long long>(split + 1) * p.tiles_n / p.splits);
       int cnt = 0;
       int minpos = 0;
+      // thr is a lower bound of this query's kc-th best score over the WHOLE index: the k-th best of
+      // any subset of rows qualifies, so every unit publishes its own list minimum (atomic max in
+      // global memory) and re-reads the shared bound once per tile.  Units that start after the
+      // first wave inherit a nearly final bound and almost never enter the insert path.
+      float* gthr = (p.thr_io != nullptr && q0 + r < p.nq) ? p.thr_io + q0 + r : nullptr;
       float thr = -INFINITY;
+      float published = -INFINITY;
       for (int t = t0; t < t1; ++t) {
+        if (gthr) {
+          const float g = __ldcg(gthr);
+          published = fmaxf(published, g);
+          thr = fmaxf(thr, g);
+        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -191,8 +203,13 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     const float x = my_sc[j * BM];
                     if (x < m) { m = x; mp = j; }
                   }
-                  thr = m;
+                  thr = fmaxf(thr, m);
                   minpos = mp;
+                  if (gthr && m > published) {  // publish: float max through the integer atomics
+                    published = m;
+                    if (m >= 0.f) atomicMax(reinterpret_cast<int*>(gthr), __float_as_int(m));
+                    else atomicMin(reinterpret_cast<unsigned int*>(gthr), __float_as_uint(m));
+                  }
                 }
               }
             }
@@ -365,6 +382,54 @@ gemv_kernel(const float* __restrict__ q, const float* __restrict__ e, int n, int
   if ((threadIdx.x & 31) == 0) out[row] = s;
 }
 
+// kth largest value of each row of a [rows, n] fp32 matrix (n <= 16384): one block per row, the row
+// is staged in shared memory and the block arg-max is removed kth-1 times.  Used to seed the scan's
+// per-query threshold from the scores of a small sample of index rows.
+constexpr int kSelThreads = 256;
+__global__ void __launch_bounds__(kSelThreads)
+kth_largest_kernel(const float* __restrict__ x, int n, int kth, float guard, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t ksm[];
+  float* v = reinterpret_cast<float*>(ksm);
+  __shared__ float red_v[kSelThreads / 32];
+  __shared__ int red_i[kSelThreads / 32];
+  __shared__ int win;
+  const int tid = threadIdx.x;
+  const float* row = x + static_cast<size_t>(blockIdx.x) * n;
+  for (int i = tid; i < n; i += kSelThreads) v[i] = row[i];
+  __syncthreads();
+  float best = -INFINITY;
+  for (int round = 0; round < kth; ++round) {
+    float bv = -INFINITY;
+    int bi = -1;
+    for (int i = tid; i < n; i += kSelThreads) {
+      const float a = v[i];
+      if (a > bv) { bv = a; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      float wv = red_v[0];
+      int wi = red_i[0];
+      for (int w = 1; w < kSelThreads / 32; ++w)
+        if (red_v[w] > wv) { wv = red_v[w]; wi = red_i[w]; }
+      win = wi;
+      if (wi >= 0) v[wi] = -INFINITY;
+      red_v[0] = wv;
+    }
+    __syncthreads();
+    best = red_v[0];
+    if (win < 0) { best = -INFINITY; break; }
+    __syncthreads();
+  }
+  if (tid == 0) out[blockIdx.x] = best - guard;
+}
+
 int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
 
 }  // namespace
@@ -381,7 +446,8 @@ extern "C" int clm_search_num_splits(int num_queries, int num_rows) {
 }
 
 extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int nq, int n, int dim,
-                               int kc, int splits, float* cand_score, int32_t* cand_id, void* stream) {
+                               int kc, int splits, float* thr_io, float* cand_score,
+                               int32_t* cand_id, void* stream) {
   CLM_REQUIRE(q_bf16 && index_bf16 && cand_score && cand_id, "clm_search_topk: null argument");
   CLM_REQUIRE(nq > 0 && n > 0 && dim > 0 && dim % 8 == 0, "clm_search_topk: bad shape nq=%d n=%d dim=%d",
               nq, n, dim);
@@ -403,6 +469,7 @@ extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int n
   p.tiles_n = tiles_n;
   p.kc = kc;
   p.stages = kc <= 32 ? 4 : 3;
+  p.thr_io = thr_io;
   p.cand_score = cand_score;
   p.cand_id = cand_id;
   const int smem = p.stages * kStageBytes + kc * BM * 8 + 256 + 1024;
@@ -448,6 +515,19 @@ extern "C" int clm_cosine_gemv(const float* q_f32, const float* index_f32, int n
   ProfScope prof(CLM_K_SEARCH, 2.0 * n * dim, 4.0 * dim * (static_cast<double>(n) + 1) + 4.0 * n,
                  static_cast<cudaStream_t>(stream));
   gemv_kernel<<<(n + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(q_f32, index_f32, n, dim, out);
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}
+
+extern "C" int clm_kth_largest(const float* x, int rows, int n, int kth, float guard, float* out,
+                               void* stream) {
+  CLM_REQUIRE(x && out && rows > 0 && n > 0 && n <= 16384 && kth >= 1 && kth <= n,
+              "clm_kth_largest: bad argument (rows=%d n=%d kth=%d; n <= 16384)", rows, n, kth);
+  const int smem = n * 4;
+  if (smem > 48 * 1024)
+    CLM_CUDA_CHECK(cudaFuncSetAttribute(kth_largest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  ProfScope prof(CLM_K_MERGE, 0.0, 4.0 * rows * n, static_cast<cudaStream_t>(stream));
+  kth_largest_kernel<<<rows, kSelThreads, smem, static_cast<cudaStream_t>(stream)>>>(x, n, kth, guard, out);
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
 }

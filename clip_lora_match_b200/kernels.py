@@ -82,6 +82,9 @@ def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, causal: bo
     return out
 
 
+SAMPLE_ROWS = 16384  # rows whose exact scores seed the scan thresholds (multiple of 256)
+
+
 def search_topk(q_f32: torch.Tensor, q_bf16: torch.Tensor, index_bf16: torch.Tensor,
                 index_f32: Optional[torch.Tensor], k: int, id_offset: int = 0,
                 margin: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -102,11 +105,23 @@ def search_topk(q_f32: torch.Tensor, q_bf16: torch.Tensor, index_bf16: torch.Ten
         margin = 6 if index_f32 is not None else 0
     kc = max(k, min(64, max(k + margin, 16)))  # candidates kept per (query, split)
     lib = _lib.load()
+    dev = q_bf16.device
+    # Per-query running threshold shared by all work units of the scan (see clm_search_topk).
+    # It is seeded from a sample: scores of the queries against the first SAMPLE_ROWS index rows
+    # (plain tcgen05 GEMM, same bf16 operands as the scan) -> exact kc-th largest per query.
+    if n >= 4 * SAMPLE_ROWS:
+        sample_scores = gemm_epi(q_bf16, index_bf16[:SAMPLE_ROWS], out_dtype=torch.float32)
+        thr = torch.empty((nq,), dtype=torch.float32, device=dev)
+        check(lib.clm_kth_largest(ptr(sample_scores), nq, SAMPLE_ROWS, kc, 1e-6, ptr(thr), cur_stream()),
+              "clm_kth_largest")
+        del sample_scores
+    else:
+        thr = torch.full((nq,), float("-inf"), dtype=torch.float32, device=dev)
     splits = lib.clm_search_num_splits(nq, n)
-    cand_s = torch.empty((nq, splits, kc), dtype=torch.float32, device=q_bf16.device)
-    cand_i = torch.empty((nq, splits, kc), dtype=torch.int32, device=q_bf16.device)
-    check(lib.clm_search_topk(ptr(q_bf16), ptr(index_bf16), nq, n, dim, kc, splits, ptr(cand_s),
-                              ptr(cand_i), cur_stream()), "clm_search_topk")
+    cand_s = torch.empty((nq, splits, kc), dtype=torch.float32, device=dev)
+    cand_i = torch.empty((nq, splits, kc), dtype=torch.int32, device=dev)
+    check(lib.clm_search_topk(ptr(q_bf16), ptr(index_bf16), nq, n, dim, kc, splits, ptr(thr),
+                              ptr(cand_s), ptr(cand_i), cur_stream()), "clm_search_topk")
     out_s = torch.empty((nq, k), dtype=torch.float32, device=q_bf16.device)
     out_i = torch.empty((nq, k), dtype=torch.int64, device=q_bf16.device)
     check(lib.clm_topk_merge(ptr(cand_s), ptr(cand_i), nq, splits, kc, ptr(q_f32), ptr(index_f32), dim,

@@ -187,9 +187,20 @@ int clm_search_num_splits(int num_queries, int num_rows);
 /* First pass (src/embedding/search.py:96 + :99 fused): scores = Q·E^T on tensor cores
  * from the bf16 shadow of the index; the score matrix stays in TMEM; every (query,
  * split) keeps its kc best candidates.  q_bf16 [nq, dim], index_bf16 [n, dim],
- * cand_score fp32 / cand_id int32 [nq, splits, kc].  dim multiple of 64, kc <= 64. */
+ * cand_score fp32 / cand_id int32 [nq, splits, kc].  dim multiple of 64, kc <= 64.
+ * thr_io (fp32 [nq], may be NULL): per-query lower bound of the kc-th best score, shared by all
+ * work units of the scan through atomic max.  The caller initialises it (-inf, or any valid lower
+ * bound such as the result of a previous scan of other rows of the same index); on return it holds
+ * the tightest bound the scan established.  Scores <= bound are never kept, so per-split lists may
+ * hold fewer than kc entries; empty slots are (-inf, -1). */
 int clm_search_topk(const void* q_bf16, const void* index_bf16, int nq, int n, int dim, int kc,
-                    int splits, float* cand_score, int32_t* cand_id, void* stream);
+                    int splits, float* thr_io, float* cand_score, int32_t* cand_id, void* stream);
+
+/* out[r] = (kth largest of x[r, 0..n)) - guard, for each of `rows` rows of a row-major fp32 matrix
+ * (n <= 16384).  Seeds clm_search_topk's thr_io from the exact scores of a sample of index rows
+ * (computed with clm_gemm_epi): the kc-th best over a subset never exceeds the kc-th best over the
+ * whole index, so it is a valid bound; `guard` keeps ties with the bound alive. */
+int clm_kth_largest(const float* x, int rows, int n, int kth, float guard, float* out, void* stream);
 
 /* Second pass: per query merge splits*kc candidates to the kc best by first-pass score,
  * re-score those exactly in fp32 against the fp32 master rows (q_f32·E_f32[id]), sort

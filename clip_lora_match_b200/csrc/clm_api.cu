@@ -63,39 +63,49 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-int clm_make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
-                          uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+int clm_make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                     int elem_bytes, uint32_t box_cols, uint32_t box_rows) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) {
     clm_set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
     return CLM_ERR_CUDA;
   }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) {
+  if (elem_bytes != 2 && elem_bytes != 4) {
+    clm_set_error("TMA element size %d unsupported (bf16 = 2, fp32 = 4)", elem_bytes);
+    return CLM_ERR_INVALID;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * elem_bytes) % 16 != 0) {
     clm_set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row pitch "
                   "(base=%p ld=%llu)", base, (unsigned long long)ld);
     return CLM_ERR_INVALID;
   }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * static_cast<uint64_t>(elem_bytes)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
+  const uint32_t row_bytes = box_cols * static_cast<uint32_t>(elem_bytes);
   CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  if (box_cols * 2 == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
-  else if (box_cols * 2 == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
-  else if (box_cols * 2 != 128) {
-    clm_set_error("unsupported TMA box width %u", box_cols);
+  if (row_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (row_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  else if (row_bytes != 128) {
+    clm_set_error("unsupported TMA box width %u x %d bytes", box_cols, elem_bytes);
     return CLM_ERR_INVALID;
   }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                  2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     clm_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu "
-                  "box=%ux%u)", (int)r, (unsigned long long)rows, (unsigned long long)cols,
-                  (unsigned long long)ld, box_cols, box_rows);
+                  "box=%ux%u elem=%d)", (int)r, (unsigned long long)rows, (unsigned long long)cols,
+                  (unsigned long long)ld, box_cols, box_rows, elem_bytes);
     return CLM_ERR_CUDA;
   }
   return CLM_OK;
+}
+
+int clm_make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                          uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+  return clm_make_tmap_2d(map, base, rows, cols, ld, 2, box_cols, box_rows);
 }
 
 // ---------------------------------------------------------------------------------------

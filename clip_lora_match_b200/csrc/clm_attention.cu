@@ -15,10 +15,15 @@
 //               P written back to TMEM as packed bf16 over the columns S no longer needs;
 //               then O is read from TMEM, scaled by 1/rowsum and stored as bf16.
 //
-// While group A runs softmax on tile t, the tensor core computes S(t+1) and group B starts on it;
-// the TMA warp is one or more items ahead, so HBM latency is off the critical path.
-// TMEM slot layout (columns): [0,Tp) S fp32 -> [0,Tp/2) P bf16x2 (aliases S) ; O fp32 at o_off.
+// The MMA warp runs ahead: S(t+2) is issued right behind PV(t) (the tensor pipe executes in issue
+// order, so it may reuse the S/P columns of tile t without a barrier), and the softmax threads keep
+// the tcgen05.ld of the next 32-column chunk in flight while they work on the current one.
+// The TMA warp is one or more items ahead, so HBM latency is off the critical path.
+// TMEM plan: see clm_attention_launch (S fp32 -> P bf16x2 aliases its first half; O fp32 separate,
+// or inside the dead upper part of its own S region when 512 columns are not enough).
 // Softmax is fp32 (modeling_clip.py:274); scale 1/sqrt(64) (modeling_clip.py:271).
+#include <stdlib.h>
+
 #include "clm_common.cuh"
 
 namespace {
@@ -30,7 +35,14 @@ constexpr int kHeadDim = 64;
 constexpr int kMaxStages = 6;
 
 struct AttnParams {
-  int T, H, Tp, mtiles, num_items, stages, stage_bytes, nslots, slot_cols, o_off;
+  int T, H, Tp, mtiles, num_items, stages, stage_bytes, nslots;
+  int stagger_clks;  // head start of softmax group 0 over group 1 (de-synchronises the two groups)
+  // TMEM column of the S / P region and of the O accumulator used by tiles of parity 0 / 1;
+  // o_alias: O lives inside the same parity's S region (dead by then), so S(t+2) waits for the drain
+  int s_col0, s_col1, o_col0, o_col1, o_alias0, o_alias1;
+  __host__ __device__ int s_col(int par) const { return par ? s_col1 : s_col0; }
+  __host__ __device__ int o_col(int par) const { return par ? o_col1 : o_col0; }
+  __host__ __device__ int o_alias(int par) const { return par ? o_alias1 : o_alias0; }
 };
 
 // MN-major SWIZZLE_128B descriptor (V: rows = keys (K dim), 64 contiguous head-dim elements (N)).
@@ -72,6 +84,49 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// max of 32 scores with four independent chains (the single-chain form serialises on FMNMX latency)
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float m) {
+  float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    m0 = fmaxf(m0, __uint_as_float(v[i]));
+    m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+    m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+    m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+__device__ __forceinline__ float chunk_max_masked(const uint32_t (&v)[32], float m, int base, int valid) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (base + i < valid) m = fmaxf(m, __uint_as_float(v[i]));
+  return m;
+}
+
+// p = 2^(s*c - max*c) for 32 scores -> 16 packed bf16x2 words; returns the chunk's sum of p
+template <bool kMasked>
+__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&pk)[16], float scale,
+                                           float neg_mx, int base, int valid) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float e0 = fast_exp2(fmaf(__uint_as_float(v[i]), scale, neg_mx));
+    float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), scale, neg_mx));
+    float e2 = fast_exp2(fmaf(__uint_as_float(v[i + 2]), scale, neg_mx));
+    float e3 = fast_exp2(fmaf(__uint_as_float(v[i + 3]), scale, neg_mx));
+    if (kMasked) {
+      e0 = (base + i < valid) ? e0 : 0.f;
+      e1 = (base + i + 1 < valid) ? e1 : 0.f;
+      e2 = (base + i + 2 < valid) ? e2 : 0.f;
+      e3 = (base + i + 3 < valid) ? e3 : 0.f;
+    }
+    s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+    pk[i / 2] = pack_bf16x2(e0, e1);
+    pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
 template <bool kCausal>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CUtensorMap map16,
@@ -82,7 +137,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
   uint64_t* stage_full = bars;                     // [kMaxStages]
   uint64_t* stage_empty = bars + kMaxStages;       // [kMaxStages]
-  uint64_t* s_full = bars + 2 * kMaxStages;        // [2] S ready (MMA commit)
+  uint64_t* s_full = bars + 2 * kMaxStages;        // [2] S ready (MMA commit), by tile parity
   uint64_t* p_full = s_full + 2;                   // [2] P written (128 softmax threads)
   uint64_t* o_full = s_full + 4;                   // [2] O ready (MMA commit)
   uint64_t* slot_free = s_full + 6;                // [2] O drained (128 softmax threads)
@@ -92,6 +147,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int T = p.T, H = p.H, Tp = p.Tp, D = p.H * kHeadDim;
   const int kv_bytes = Tp * 128;  // one of Q / K / V in a stage
+  const int n_local = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                      static_cast<int>(gridDim.x);
+  const int n_tiles = n_local * p.mtiles;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map64);
@@ -143,166 +201,191 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
+    // The tensor pipe executes in issue order, so S(t+2) may overwrite the S/P columns of tile t as
+    // soon as PV(t) has been ISSUED; it only waits when O(t) is aliased into those columns.
     const uint32_t idesc_pv = umma_idesc_bf16(128, kHeadDim, 0, 1);
-    int st = 0;
-    uint32_t ph = 0;
-    int t = 0;                 // running tile counter of this CTA
-    int prev_slot = -1, prev_use = 0, prev_stage = 0, prev_last = 0;
-    uint32_t prev_v_addr = 0;
-
-    auto issue_pv = [&]() {
-      // O(prev) = P(prev) V : P from TMEM (written by the softmax group), V MN-major from smem
-      mbar_wait(&p_full[prev_slot], prev_use & 1);
-      tc_fence_after();
+    // cursors: (item, tile-in-item, stage, stage phase) of the next S and of the next PV to issue
+    int smt = 0, sst = 0;
+    uint32_t sph = 0;
+    int pmt = 0, pst = 0;
+    auto issue_s = [&](int t) {
+      if (smt == 0) {
+        mbar_wait(&stage_full[sst], sph);
+        tc_fence_after();
+      }
       if (lane == 0) {
-        const uint32_t sbase = tmem + static_cast<uint32_t>(prev_slot * p.slot_cols);
-        const int ksteps = Tp / 16;
-        for (int ks = 0; ks < ksteps; ++ks)
-          umma_bf16_ts(sbase + p.o_off, sbase + ks * 8, umma_desc_sw128_mn(prev_v_addr + ks * 2048),
-                       idesc_pv, ks != 0 ? 1u : 0u);
-        umma_commit(&o_full[prev_slot]);
-        if (prev_last) umma_commit(&stage_empty[prev_stage]);  // stage reusable once these MMAs retire
+        const uint32_t q_addr = smem_u32(smem + sst * p.stage_bytes);
+        const uint32_t k_addr = q_addr + kv_bytes;
+        const uint32_t sbase = tmem + static_cast<uint32_t>(p.s_col(t & 1));
+        for (int n0 = 0; n0 < Tp; n0 += 256) {
+          const int nn = (Tp - n0) < 256 ? (Tp - n0) : 256;
+          const uint32_t idesc = umma_idesc_bf16(128, nn, 0, 0);
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k)
+            umma_bf16_ss(sbase + n0, umma_desc_sw128(q_addr + smt * 16384 + k * 32, 1024),
+                         umma_desc_sw128(k_addr + n0 * 128 + k * 32, 1024), idesc, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[t & 1]);
       }
       __syncwarp();
-      prev_slot = -1;
-    };
-
-    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-      mbar_wait(&stage_full[st], ph);
-      tc_fence_after();
-      const uint32_t q_addr = smem_u32(smem + st * p.stage_bytes);
-      const uint32_t k_addr = q_addr + kv_bytes;
-      const uint32_t v_addr = k_addr + kv_bytes;
-      for (int mt = 0; mt < p.mtiles; ++mt, ++t) {
-        const int slot = t % p.nslots;
-        const int use = t / p.nslots;
-        if (p.nslots == 1 && prev_slot >= 0) issue_pv();  // single slot: O(t-1) must drain first
-        mbar_wait(&slot_free[slot], (use & 1) ^ 1);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sbase = tmem + static_cast<uint32_t>(slot * p.slot_cols);
-          for (int n0 = 0; n0 < Tp; n0 += 256) {
-            const int nn = (Tp - n0) < 256 ? (Tp - n0) : 256;
-            const uint32_t idesc = umma_idesc_bf16(128, nn, 0, 0);
-#pragma unroll
-            for (int k = 0; k < kHeadDim / 16; ++k)
-              umma_bf16_ss(sbase + n0, umma_desc_sw128(q_addr + mt * 16384 + k * 32, 1024),
-                           umma_desc_sw128(k_addr + n0 * 128 + k * 32, 1024), idesc, k != 0 ? 1u : 0u);
-          }
-          umma_commit(&s_full[slot]);
-        }
-        __syncwarp();
-        if (prev_slot >= 0) issue_pv();
-        prev_slot = slot; prev_use = use; prev_stage = st; prev_v_addr = v_addr;
-        prev_last = (mt == p.mtiles - 1);
+      if (++smt == p.mtiles) {
+        smt = 0;
+        if (++sst == p.stages) { sst = 0; sph ^= 1; }
       }
-      if (++st == p.stages) { st = 0; ph ^= 1; }
+    };
+    auto issue_pv = [&](int t) {
+      // O(t) = P(t) V : P from TMEM (written by the softmax group), V MN-major from smem.  p_full(t)
+      // also implies that the same group has drained O(t-2), whose columns this overwrites.
+      const int b = t & 1;
+      mbar_wait(&p_full[b], static_cast<uint32_t>((t >> 1) & 1));
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t v_addr = smem_u32(smem + pst * p.stage_bytes) + 2 * kv_bytes;
+        const uint32_t pbase = tmem + static_cast<uint32_t>(p.s_col(b));
+        const uint32_t obase = tmem + static_cast<uint32_t>(p.o_col(b));
+        const int ksteps = Tp / 16;
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_bf16_ts(obase, pbase + ks * 8, umma_desc_sw128_mn(v_addr + ks * 2048), idesc_pv,
+                       ks != 0 ? 1u : 0u);
+        umma_commit(&o_full[b]);
+        if (pmt == p.mtiles - 1) umma_commit(&stage_empty[pst]);  // stage reusable once these MMAs retire
+      }
+      __syncwarp();
+      if (++pmt == p.mtiles) {
+        pmt = 0;
+        if (++pst == p.stages) pst = 0;
+      }
+    };
+    if (p.nslots == 2) {
+      if (n_tiles > 0) issue_s(0);
+      if (n_tiles > 1) issue_s(1);
+      for (int t = 0; t < n_tiles; ++t) {
+        issue_pv(t);
+        if (t + 2 < n_tiles) {
+          if (p.o_alias(t & 1)) {
+            mbar_wait(&slot_free[t & 1], static_cast<uint32_t>((t >> 1) & 1));
+            tc_fence_after();
+          }
+          issue_s(t + 2);
+        }
+      }
+    } else {
+      if (n_tiles > 0) issue_s(0);
+      for (int t = 0; t < n_tiles; ++t) {
+        issue_pv(t);
+        if (t + 1 < n_tiles) issue_s(t + 1);
+      }
     }
-    if (prev_slot >= 0) issue_pv();
   } else {
     // ================= softmax groups =================
-    const int g = (warp - 2) >> 2;       // group 0: warps 2-5, group 1: warps 6-9
+    // group g (warps 2-5 / 6-9) owns the tiles of parity g; thread = query row = TMEM lane.
+    const int g = (warp - 2) >> 2;
     const int q = warp & 3;              // TMEM lane quarter of this warp
     const int r = q * 32 + lane;         // row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const int nchunks = (Tp + 31) / 32;
     constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const uint32_t srow = tmem + lane_off + static_cast<uint32_t>(p.s_col(g));
+    const uint32_t orow = tmem + lane_off + static_cast<uint32_t>(p.o_col(g));
+    if (g == 1 && p.stagger_clks > 0) {  // let group 0 run ahead: the groups then alternate instead of
+      const long long t0 = clock64();    // computing and waiting for the tensor pipe in lockstep
+      while (clock64() - t0 < p.stagger_clks) {}
+    }
     int t = 0;
-    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-      const int b = it / H, h = it % H;
-      for (int mt = 0; mt < p.mtiles; ++mt, ++t) {
-        // two TMEM slots: groups ping-pong (tile t -> group t % 2, slot t % 2).  A single slot
-        // (Tp > 256) serialises tiles, so one group takes them all: a group must never wait on a
-        // barrier phase more than one ahead of the one it last consumed.
-        if ((p.nslots == 2 ? (t & 1) : 0) != g) continue;
-        const int slot = t % p.nslots;
-        const uint32_t par = static_cast<uint32_t>((t / p.nslots) & 1);
-        const uint32_t trow = tmem + lane_off + static_cast<uint32_t>(slot * p.slot_cols);
-        const int qi = mt * 128 + r;                     // query position in the sequence
-        const bool warp_live = mt * 128 + q * 32 < T;    // does this warp own any real row?
-        int valid = T;
-        if (kCausal) valid = (qi + 1 < T) ? qi + 1 : T;
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x)
+    for (int mt = 0; mt < p.mtiles; ++mt, ++t) {
+      if ((t & 1) != g) continue;
+      const int b = it / H, h = it - b * H;
+      const uint32_t par = static_cast<uint32_t>((t >> 1) & 1);
+      const int qi = mt * 128 + r;                     // query position in the sequence
+      const bool warp_live = mt * 128 + q * 32 < T;    // does this warp own any real row?
+      int valid = T;
+      if (kCausal) valid = (qi + 1 < T) ? qi + 1 : T;
+      // chunks this warp has to look at: under the causal mask nothing right of its last row counts
+      int nch = nchunks;
+      if (kCausal) {
+        const int wv = (mt * 128 + q * 32 + 32 < T) ? mt * 128 + q * 32 + 32 : T;
+        nch = (wv + 31) / 32;
+      }
 
-        mbar_wait(&s_full[slot], par);
-        tc_fence_after();
-        float sum = 1.f;
-        if (warp_live) {
-          float mx = -INFINITY;
-          for (int c = 0; c < nchunks; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(trow + c * 32, v);
-            tmem_ld_wait();
-            if (c * 32 + 32 <= valid) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-            }
-          }
-          const float neg_mx = -mx * kScaleLog2e;
-          sum = 0.f;
-          for (int c = 0; c < nchunks; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(trow + c * 32, v);
-            tmem_ld_wait();
-            float e[32];
-            if (c * 32 + 32 <= valid) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                e[i] = fast_exp2(fmaf(__uint_as_float(v[i]), kScaleLog2e, neg_mx));
-                sum += e[i];
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float x = fast_exp2(fmaf(__uint_as_float(v[i]), kScaleLog2e, neg_mx));
-                e[i] = (c * 32 + i < valid) ? x : 0.f;
-                sum += e[i];
-              }
-            }
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
-            tmem_st_32x32b_x16(trow + c * 16, pk);  // P aliases the S columns already consumed
-          }
-          tmem_st_wait();
-        }
-        tc_fence_before();
-        mbar_arrive(&p_full[slot]);
-
-        mbar_wait(&o_full[slot], par);
-        tc_fence_after();
-        uint32_t o0[32], o1[32];
-        if (warp_live) {
-          tmem_ld_32x32b_x32(trow + p.o_off, o0);
-          tmem_ld_32x32b_x32(trow + p.o_off + 32, o1);
+      mbar_wait(&s_full[g], par);
+      tc_fence_after();
+      float sum = 1.f;
+      if (warp_live) {
+        // ---- pass 1: row max.  The load of chunk c+1 is in flight while chunk c is reduced.
+        uint32_t va[32], vb[32];
+        float mx = -INFINITY;
+        tmem_ld_32x32b_x32(srow, va);
+        for (int c = 0; c < nch; c += 2) {
           tmem_ld_wait();
+          if (c + 1 < nch) tmem_ld_32x32b_x32(srow + (c + 1) * 32, vb);
+          mx = (c * 32 + 32 <= valid) ? chunk_max(va, mx) : chunk_max_masked(va, mx, c * 32, valid);
+          if (c + 1 < nch) {
+            tmem_ld_wait();
+            if (c + 2 < nch) tmem_ld_32x32b_x32(srow + (c + 2) * 32, va);
+            mx = (c * 32 + 64 <= valid) ? chunk_max(vb, mx) : chunk_max_masked(vb, mx, c * 32 + 32, valid);
+          }
         }
-        tc_fence_before();
-        mbar_arrive(&slot_free[slot]);  // the slot can take S(t + nslots) while we store
-        if (warp_live && qi < T) {
-          const float inv = 1.0f / sum;
-          uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(b * T + qi) * D + h * kHeadDim);
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(o0[8 * jj + 0]) * inv, __uint_as_float(o0[8 * jj + 1]) * inv);
-            o.y = pack_bf16x2(__uint_as_float(o0[8 * jj + 2]) * inv, __uint_as_float(o0[8 * jj + 3]) * inv);
-            o.z = pack_bf16x2(__uint_as_float(o0[8 * jj + 4]) * inv, __uint_as_float(o0[8 * jj + 5]) * inv);
-            o.w = pack_bf16x2(__uint_as_float(o0[8 * jj + 6]) * inv, __uint_as_float(o0[8 * jj + 7]) * inv);
-            o4[jj] = o;
+        // ---- pass 2: p = 2^(s*c - max*c), row sum, P (bf16x2) over the S columns already consumed
+        const float neg_mx = -mx * kScaleLog2e;
+        sum = 0.f;
+        uint32_t pk[16];
+        tmem_ld_32x32b_x32(srow, va);
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nch) tmem_ld_32x32b_x32(srow + (c + 1) * 32, vb);
+          sum += (c * 32 + 32 <= valid) ? chunk_exp<false>(va, pk, kScaleLog2e, neg_mx, c * 32, valid)
+                                        : chunk_exp<true>(va, pk, kScaleLog2e, neg_mx, c * 32, valid);
+          tmem_st_32x32b_x16(srow + c * 16, pk);
+          if (c + 1 < nch) {
+            tmem_ld_wait();
+            if (c + 2 < nch) tmem_ld_32x32b_x32(srow + (c + 2) * 32, va);
+            sum += (c * 32 + 64 <= valid)
+                       ? chunk_exp<false>(vb, pk, kScaleLog2e, neg_mx, c * 32 + 32, valid)
+                       : chunk_exp<true>(vb, pk, kScaleLog2e, neg_mx, c * 32 + 32, valid);
+            tmem_st_32x32b_x16(srow + (c + 1) * 16, pk);
           }
+        }
+        if (kCausal && nch < nchunks) {  // P right of the causal frontier is zero (PV reads all of it)
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(o1[8 * jj + 0]) * inv, __uint_as_float(o1[8 * jj + 1]) * inv);
-            o.y = pack_bf16x2(__uint_as_float(o1[8 * jj + 2]) * inv, __uint_as_float(o1[8 * jj + 3]) * inv);
-            o.z = pack_bf16x2(__uint_as_float(o1[8 * jj + 4]) * inv, __uint_as_float(o1[8 * jj + 5]) * inv);
-            o.w = pack_bf16x2(__uint_as_float(o1[8 * jj + 6]) * inv, __uint_as_float(o1[8 * jj + 7]) * inv);
-            o4[4 + jj] = o;
-          }
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          for (int c = nch; c < nchunks; ++c) tmem_st_32x32b_x16(srow + c * 16, pk);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&p_full[g]);
+
+      mbar_wait(&o_full[g], par);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      if (warp_live) {
+        tmem_ld_32x32b_x32(orow, o0);
+        tmem_ld_32x32b_x32(orow + 32, o1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&slot_free[g]);  // O(t) is in registers: its columns may be overwritten
+      if (warp_live && qi < T) {
+        const float inv = 1.0f / sum;
+        uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(b * T + qi) * D + h * kHeadDim);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(o0[8 * jj + 0]) * inv, __uint_as_float(o0[8 * jj + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(o0[8 * jj + 2]) * inv, __uint_as_float(o0[8 * jj + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(o0[8 * jj + 4]) * inv, __uint_as_float(o0[8 * jj + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(o0[8 * jj + 6]) * inv, __uint_as_float(o0[8 * jj + 7]) * inv);
+          o4[jj] = o;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(o1[8 * jj + 0]) * inv, __uint_as_float(o1[8 * jj + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(o1[8 * jj + 2]) * inv, __uint_as_float(o1[8 * jj + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(o1[8 * jj + 4]) * inv, __uint_as_float(o1[8 * jj + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(o1[8 * jj + 6]) * inv, __uint_as_float(o1[8 * jj + 7]) * inv);
+          o4[4 + jj] = o;
         }
       }
     }
@@ -318,7 +401,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
 int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int heads, int causal,
                          cudaStream_t stream) {
   CLM_REQUIRE(qkv && out && batch >= 0 && tokens > 0 && heads > 0, "clm_attention: bad argument");
-  CLM_REQUIRE(tokens <= 512, "clm_attention: tokens=%d > 512 unsupported (CLIP uses <= 257)", tokens);
+  CLM_REQUIRE(tokens <= 384, "clm_attention: tokens=%d > 384 unsupported (CLIP uses <= 257)", tokens);
   if (batch == 0) return CLM_OK;
   const int T = tokens;
   const int D = heads * kHeadDim;
@@ -328,7 +411,7 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   p.Tp = (T + 15) / 16 * 16;
   p.mtiles = (T + 127) / 128;
   const long long items = static_cast<long long>(batch) * heads;
-  CLM_REQUIRE(items < 2147483647LL, "clm_attention: too many (batch, head) items");
+  CLM_REQUIRE(items < 2147483647LL / 4, "clm_attention: too many (batch, head) items");
   p.num_items = static_cast<int>(items);
   // a stage holds Q, K, V ([Tp,64] bf16 each); the last query tile's 128-row UMMA window may run
   // past Q into K/V (finite values, rows never stored), so a stage is at least mtiles*16 KiB
@@ -341,14 +424,37 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   CLM_REQUIRE(stages >= 1, "clm_attention: tokens=%d needs %d bytes of shared memory per stage", T,
               stage_bytes);
   p.stages = stages;
-  // TMEM slot: S needs round_up(Tp,32) fp32 columns; P (bf16x2) reuses the first Tp/2; O (64
-  // columns) sits at the next multiple of 64 past P
-  p.o_off = ((p.Tp / 2) + 63) / 64 * 64;
+  // group 1 starts ~half a tile period after group 0 (CLM_ATTN_STAGGER overrides, in clocks)
+  static int stagger_env = -2;
+  if (stagger_env == -2) {
+    const char* e = getenv("CLM_ATTN_STAGGER");
+    stagger_env = e ? atoi(e) : -1;
+  }
+  p.stagger_clks = stagger_env >= 0 ? stagger_env : 12 * p.Tp;
+  // TMEM plan (512 columns).  S needs round_up(Tp,32) fp32 columns (the softmax reads 32-column
+  // chunks); P (bf16x2) reuses its first Tp/2; O needs 64.  Tiles alternate between two parities:
+  //   two S regions + two O regions            (T <= 192)
+  //   two S regions, O0 separate, O1 inside S1 (T <= 224: ViT-B/16's 197) -> S(t+2) of odd t waits
+  //   one S region, two O regions              (T <= 384: ViT-L/14's 257)
   const int s_cols = (p.Tp + 31) / 32 * 32;
-  const int need = (s_cols > p.o_off + 64) ? s_cols : p.o_off + 64;
-  CLM_REQUIRE(need <= 512, "clm_attention: tokens=%d needs %d TMEM columns", T, need);
-  p.nslots = need <= 256 ? 2 : 1;
-  p.slot_cols = p.nslots == 2 ? 256 : 512;
+  const int o_in = (p.Tp / 2 + 31) / 32 * 32;  // first column past P inside an S region
+  if (2 * s_cols + 128 <= 512 && stages >= 2) {
+    p.nslots = 2;
+    p.s_col0 = 0; p.s_col1 = s_cols;
+    p.o_col0 = 2 * s_cols; p.o_col1 = 2 * s_cols + 64;
+    p.o_alias0 = 0; p.o_alias1 = 0;
+  } else if (2 * s_cols + 64 <= 512 && o_in + 64 <= s_cols && stages >= 2) {
+    p.nslots = 2;
+    p.s_col0 = 0; p.s_col1 = s_cols;
+    p.o_col0 = 2 * s_cols; p.o_col1 = s_cols + o_in;
+    p.o_alias0 = 0; p.o_alias1 = 1;
+  } else {
+    CLM_REQUIRE(s_cols + 128 <= 512, "clm_attention: tokens=%d needs %d TMEM columns", T, s_cols + 128);
+    p.nslots = 1;
+    p.s_col0 = 0; p.s_col1 = 0;
+    p.o_col0 = s_cols; p.o_col1 = s_cols + 64;
+    p.o_alias0 = 0; p.o_alias1 = 0;
+  }
   const int smem_bytes = stages * stage_bytes + 256 + 1024;
 
   CUtensorMap map64, map16;

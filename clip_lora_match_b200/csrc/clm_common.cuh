@@ -43,6 +43,10 @@ void clm_set_error(const char* fmt, ...);
 int clm_make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                           uint64_t ld, uint32_t box_cols, uint32_t box_rows);
 
+// Same for any 2- or 4-byte element type (fp32 output tiles of the GEMM epilogue).
+int clm_make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                     int elem_bytes, uint32_t box_cols, uint32_t box_rows);
+
 int clm_num_sms();
 
 // Launch accounting + optional per-launch CUDA-event timing (bench.py's roofline numbers).
@@ -141,6 +145,35 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
       : "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// shared -> global tile store / reduction (bulk async-group completion).  Rows and columns of the
+// box that fall outside the tensor are clipped by the hardware, so ragged edges need no guards.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(map), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+// global[tile] += smem[tile], performed by the L2 (fp32 add for a FLOAT32 tensor map)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(map), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest `N` groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // L2 eviction-priority policies (createpolicy encodings used by the TMA cache_hint operand)
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;

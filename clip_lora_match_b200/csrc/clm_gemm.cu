@@ -18,8 +18,12 @@
 // CTA = 320 threads:
 //   warp 0      TMA producer (one elected lane)          smem ring: full[]/empty[] mbarriers
 //   warp 1      TMEM allocator + MMA issuer (one lane)   accumulator ring: tmem_full[]/tmem_empty[]
-//   warps 2..9  epilogue: tcgen05.ld -> smem transpose -> bias/QuickGELU/residual -> coalesced
-//               global stores.  Warp w reads TMEM lane quarter (w % 4), column half ((w - 2) / 4).
+//   warps 2..9  epilogue.  Warp w reads TMEM lane quarter (w % 4), column half ((w - 2) / 4):
+//               tcgen05.ld (lane = accumulator row) -> bias / QuickGELU in registers -> 128-byte
+//               swizzled rows in a private 4 KiB staging buffer -> ONE TMA tile store per 32x64
+//               (bf16) / 32x32 (fp32) slab.  The in-place residual form (out == residual) issues a
+//               TMA reduce-add instead, so the fp32 residual stream is updated inside the L2 and
+//               never travels to the SM.  Ragged M / N edges are clipped by the TMA unit.
 // The accumulator is double buffered in TMEM (2 x BN fp32 columns) so the epilogue of tile i
 // overlaps the MMAs of tile i+1.  The grid is persistent and strides over the tile list (n
 // fastest, so CTAs that run together share A rows through L2).
@@ -48,8 +52,14 @@ struct Cfg {
   static constexpr int kStages = (kStageBytes == 49152) ? 4 : (kStageBytes == 32768 ? 6 : 8);
   static constexpr int kTmemCols = kAccStages * BN;  // 512 / 256 / 128: powers of two
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiWarps * 4096 /*epilogue staging*/;
+      kStages * kStageBytes + 1024 /*align*/ + kEpiWarps * 4096 /*epilogue staging*/ + 256 /*barriers*/;
 };
+
+// epilogue variants (template parameter kEpi)
+constexpr int kEpiLegacy = 0;     // per-thread global loads/stores; residual != out or bf16 out + residual
+constexpr int kEpiStoreBf16 = 1;  // TMA store of bf16 tiles
+constexpr int kEpiStoreF32 = 2;   // TMA store of fp32 tiles
+constexpr int kEpiReduceF32 = 3;  // TMA reduce-add of fp32 tiles: out (== residual) += acc + bias
 
 struct EpiParams {
   void* out;
@@ -123,16 +133,18 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int BN, int kCtas>
+template <int BN, int kCtas, int kEpi>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
-            int M, int N, int kb_main, int kb_ext, EpiParams ep) {
+            const __grid_constant__ CUtensorMap map_out, int M, int N, int kb_main, int kb_ext,
+            EpiParams ep) {
   using C = Cfg<BN, kCtas>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* staging = smem + C::kStages * C::kStageBytes;  // 1024-byte aligned: kEpiWarps x 4 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEpiWarps * 4096);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
@@ -157,6 +169,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       tma_prefetch_desc(&map_a2);
       tma_prefetch_desc(&map_b2);
     }
+    if (kEpi != kEpiLegacy) tma_prefetch_desc(&map_out);
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -250,8 +263,126 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (kEpi != kEpiLegacy) {
+    // ================= epilogue warps (TMA store / reduce path) =================
+    // tcgen05.ld hands each lane one accumulator ROW; a slab is 128 bytes of that row (64 bf16 or
+    // 32 fp32 columns).  Lane r writes its 8 16-byte pieces to staging row r with piece p at slot
+    // p ^ (r & 7) -- the SWIZZLE_128B pattern of the output tensor map, and conflict-free for the
+    // eight lanes of every shared-memory wavefront.  One elected lane then hands the 32-row slab to
+    // the TMA unit; the buffer is reused once the unit has READ it (wait_group.read).
+    constexpr bool kF32 = (kEpi != kEpiStoreBf16);
+    constexpr int kSlabCols = kF32 ? 32 : 64;
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
+    // BN = 64 with bf16 output: one 64-column slab, drained by the half-0 warps only
+    constexpr bool kSplit = (BN / 2 >= kSlabCols);
+    constexpr int kWarpCols = kSplit ? BN / 2 : BN;
+    constexpr int kSlabs = kWarpCols / kSlabCols;
+    const bool active = kSplit || half == 0;
+    const uint32_t stg = smem_u32(staging + (warp - 2) * 4096);
+    const uint32_t my_row = stg + static_cast<uint32_t>(lane) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      const int m0 = (tile / n_tiles) * TM + static_cast<int>(rank) * BM + q * 32;
+      const int n0 = (tile % n_tiles) * BN + (kSplit ? half * (BN / 2) : 0);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                             static_cast<uint32_t>(acc * BN + (kSplit ? half * (BN / 2) : 0));
+      const bool rows_live = active && m0 < M;
+#pragma unroll
+      for (int sl = 0; sl < kSlabs; ++sl) {
+        const int col0 = n0 + sl * kSlabCols;
+        const bool live = rows_live && col0 < N;  // warp-uniform
+        uint32_t pk[32];
+        if (kF32) {
+          uint32_t v[32];
+          if (live) {
+            tmem_ld_32x32b_x32(taddr + sl * kSlabCols, v);
+            tmem_ld_wait();
+          }
+          if (sl == kSlabs - 1) {  // accumulator fully drained: hand the TMEM stage back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (kCtas == 2) mbar_arrive_cta(&tmem_empty[acc], 0);
+              else mbar_arrive(&tmem_empty[acc]);
+            }
+          }
+          if (live) {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ep.bias && col0 + 4 * p < N) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 4 * p));
+              float x0 = __uint_as_float(v[4 * p + 0]) + b.x, x1 = __uint_as_float(v[4 * p + 1]) + b.y;
+              float x2 = __uint_as_float(v[4 * p + 2]) + b.z, x3 = __uint_as_float(v[4 * p + 3]) + b.w;
+              if (ep.act == CLM_EPI_QUICKGELU) {
+                x0 = quick_gelu(x0); x1 = quick_gelu(x1); x2 = quick_gelu(x2); x3 = quick_gelu(x3);
+              }
+              pk[4 * p + 0] = __float_as_uint(x0); pk[4 * p + 1] = __float_as_uint(x1);
+              pk[4 * p + 2] = __float_as_uint(x2); pk[4 * p + 3] = __float_as_uint(x3);
+            }
+          }
+        } else {
+          uint32_t v0[32], v1[32];
+          if (live) {
+            tmem_ld_32x32b_x32(taddr + sl * kSlabCols, v0);
+            tmem_ld_32x32b_x32(taddr + sl * kSlabCols + 32, v1);
+            tmem_ld_wait();
+          }
+          if (sl == kSlabs - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (kCtas == 2) mbar_arrive_cta(&tmem_empty[acc], 0);
+              else mbar_arrive(&tmem_empty[acc]);
+            }
+          }
+          if (live) {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {  // piece p = columns col0 + 8p .. + 7
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+              if (ep.bias && col0 + 8 * p < N) {
+                b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 8 * p));
+                b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 8 * p + 4));
+              }
+              const uint32_t* src = (p < 4) ? &v0[8 * p] : &v1[8 * (p - 4)];
+              float x0 = __uint_as_float(src[0]) + b0.x, x1 = __uint_as_float(src[1]) + b0.y;
+              float x2 = __uint_as_float(src[2]) + b0.z, x3 = __uint_as_float(src[3]) + b0.w;
+              float x4 = __uint_as_float(src[4]) + b1.x, x5 = __uint_as_float(src[5]) + b1.y;
+              float x6 = __uint_as_float(src[6]) + b1.z, x7 = __uint_as_float(src[7]) + b1.w;
+              if (ep.act == CLM_EPI_QUICKGELU) {
+                x0 = quick_gelu(x0); x1 = quick_gelu(x1); x2 = quick_gelu(x2); x3 = quick_gelu(x3);
+                x4 = quick_gelu(x4); x5 = quick_gelu(x5); x6 = quick_gelu(x6); x7 = quick_gelu(x7);
+              }
+              pk[4 * p + 0] = pack_bf16x2(x0, x1); pk[4 * p + 1] = pack_bf16x2(x2, x3);
+              pk[4 * p + 2] = pack_bf16x2(x4, x5); pk[4 * p + 3] = pack_bf16x2(x6, x7);
+            }
+          }
+        }
+        if (live) {
+          if (lane == 0) bulk_wait_read<0>();  // the previous slab has left the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int p = 0; p < 8; ++p)
+            st_shared_v4(my_row + ((static_cast<uint32_t>(p) ^ sw) << 4), pk[4 * p], pk[4 * p + 1],
+                         pk[4 * p + 2], pk[4 * p + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (kEpi == kEpiReduceF32) tma_reduce_add_2d(&map_out, stg, col0, m0);
+            else tma_store_2d(&map_out, stg, col0, m0);
+            bulk_commit();
+          }
+        }
+      }
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) bulk_wait<0>();  // every tile of this warp has reached global memory
   } else {
-    // ================= epilogue warps =================
+    // ================= epilogue warps (legacy per-thread path) =================
     // TMEM gives each lane one accumulator ROW (32 fp32 columns per tcgen05.ld).  Storing that
     // directly would touch 32 different cache lines per warp instruction, so each warp transposes
     // its 32x32 chunk through a private 4 KiB shared-memory buffer (16-byte pieces XOR-swizzled by
@@ -261,7 +392,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
     constexpr int kChunks = BN / 64;    // 32-column chunks per warp
-    uint8_t* stage = smem + C::kStages * C::kStageBytes + 256 + (warp - 2) * 4096;
+    uint8_t* stage = staging + (warp - 2) * 4096;
     const int piece = lane & 7;         // 16-byte piece (4 fp32 columns) inside the 128-byte chunk row
     const int rsub = lane >> 3;         // row offset inside each group of 4 rows
     int acc = 0;
@@ -348,15 +479,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   }
 }
 
-template <int BN, int kCtas>
+template <int BN, int kCtas, int kEpi>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2,
-                const CUtensorMap& mb2, int M, int N, int kb_main, int kb_ext, const EpiParams& ep,
-                cudaStream_t stream) {
+                const CUtensorMap& mb2, const CUtensorMap& mo, int M, int N, int kb_main, int kb_ext,
+                const EpiParams& ep, cudaStream_t stream) {
   using C = Cfg<BN, kCtas>;
   static bool attr_set = false;
   if (!attr_set) {
-    CLM_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        C::kSmemBytes));
+    CLM_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, kCtas, kEpi>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
   const int tiles = ((M + BM * kCtas - 1) / (BM * kCtas)) * ((N + BN - 1) / BN);
@@ -374,8 +505,21 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, kCtas>, ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep));
+  CLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, kCtas, kEpi>, ma, mb, ma2, mb2, mo, M, N, kb_main,
+                                    kb_ext, ep));
   return CLM_OK;
+}
+
+template <int kEpi>
+int launch_gemm_bn(bool pair, int BN, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2,
+                   const CUtensorMap& mb2, const CUtensorMap& mo, int M, int N, int kb_main, int kb_ext,
+                   const EpiParams& ep, cudaStream_t stream) {
+  if (pair) return launch_gemm<256, 2, kEpi>(ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
+  switch (BN) {
+    case 256: return launch_gemm<256, 1, kEpi>(ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
+    case 128: return launch_gemm<128, 1, kEpi>(ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
+    default: return launch_gemm<64, 1, kEpi>(ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
+  }
 }
 
 }  // namespace
@@ -431,6 +575,24 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
   ep.ldr = ldr;
   ep.out_f32 = (out_dtype == CLM_OUT_F32);
   ep.act = epilogue;
+  // epilogue variant: TMA tile stores, or a TMA reduce-add for the in-place residual update; the
+  // per-thread legacy path only for residual != out / bf16 out + residual (CLM_GEMM_EPI=legacy forces it)
+  static int force_legacy = -1;
+  if (force_legacy < 0) {
+    const char* e = getenv("CLM_GEMM_EPI");
+    force_legacy = (e && e[0] == 'l') ? 1 : 0;
+  }
+  int epi = ep.out_f32 ? kEpiStoreF32 : kEpiStoreBf16;
+  if (residual) {
+    const bool in_place = ep.out_f32 && residual == static_cast<const float*>(out) && ldr == ldo;
+    epi = in_place ? kEpiReduceF32 : kEpiLegacy;
+  }
+  if (force_legacy) epi = kEpiLegacy;
+  CUtensorMap mo = ma;
+  if (epi != kEpiLegacy) {
+    if ((rc = clm_make_tmap_2d(&mo, out, M, N, ldo, ep.out_f32 ? 4 : 2, ep.out_f32 ? 32 : 64, 32))) return rc;
+    ep.residual = nullptr;  // the reduce-add reads the residual inside the L2
+  }
   const int kb_main = (K + BK - 1) / BK;
   const int kb_ext = has_ext ? (K2 + BK - 1) / BK : 0;
   const double flops = 2.0 * M * N * (static_cast<double>(K) + (has_ext ? K2 : 0));
@@ -438,11 +600,15 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
                        static_cast<double>(M) * N * (ep.out_f32 ? 4 : 2) +
                        (residual ? 4.0 * M * N : 0.0);
   ProfScope prof(CLM_K_GEMM, flops, bytes, stream);
-  if (pair) return launch_gemm<256, 2>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);
-  switch (BN) {
-    case 256: return launch_gemm<256, 1>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);
-    case 128: return launch_gemm<128, 1>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);
-    default: return launch_gemm<64, 1>(ma, mb, ma2, mb2, M, N, kb_main, kb_ext, ep, stream);
+  switch (epi) {
+    case kEpiStoreBf16:
+      return launch_gemm_bn<kEpiStoreBf16>(pair, BN, ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
+    case kEpiStoreF32:
+      return launch_gemm_bn<kEpiStoreF32>(pair, BN, ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
+    case kEpiReduceF32:
+      return launch_gemm_bn<kEpiReduceF32>(pair, BN, ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
+    default:
+      return launch_gemm_bn<kEpiLegacy>(pair, BN, ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
   }
 }
 

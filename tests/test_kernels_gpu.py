@@ -120,7 +120,11 @@ def test_gemm_identity_layout(cuda_device):
     _close("gemm_identity", out, ref, atol=1e-3, rtol=0, a=a, w=w)
 
 
-@pytest.mark.parametrize("M,N,Kd", [(197 * 2, 768, 768), (300, 3072, 768)])
+@pytest.mark.parametrize("M,N,Kd", [(197 * 2, 768, 768), (300, 3072, 768),
+                                    (300, 64, 768),    # BN=64: one bf16 slab drained by half the epilogue warps
+                                    (130, 136, 512),   # ragged N inside a slab (TMA clips columns >= N)
+                                    (77, 40, 128),     # N < one slab, M < one tile
+                                    (1000, 1024, 256)])
 def test_gemm_epilogues(cuda_device, M, N, Kd):
     a = _randn((M, Kd), 20).bfloat16()
     w = _randn((N, Kd), 21, Kd ** -0.5).bfloat16()
@@ -137,6 +141,19 @@ def test_gemm_epilogues(cuda_device, M, N, Kd):
     res_d = res.to(d).clone()
     out = K.gemm_epi(a.to(d), w.to(d), bias=bias.to(d), residual=res_d, out=res_d)
     _close(f"gemm_residual_{N}", out, _gemm_ref(a, w, bias, res), atol=2e-3, rtol=1e-3)
+    # residual in a different buffer than the output (per-thread epilogue path), fp32 and bf16 out
+    out = K.gemm_epi(a.to(d), w.to(d), bias=bias.to(d), residual=res.to(d), out_dtype=torch.float32)
+    _close(f"gemm_residual_sep_{N}", out, _gemm_ref(a, w, bias, res), atol=2e-3, rtol=1e-3)
+    out = K.gemm_epi(a.to(d), w.to(d), bias=bias.to(d), residual=res.to(d), act=K.EPI_QUICKGELU)
+    _close(f"gemm_residual_sep_bf16_{N}", out, _gemm_ref(a, w, bias, res, act=K.EPI_QUICKGELU), atol=3e-2, rtol=8e-3)
+    # fp32 out without residual, with activation
+    out = K.gemm_epi(a.to(d), w.to(d), bias=bias.to(d), act=K.EPI_QUICKGELU, out_dtype=torch.float32)
+    _close(f"gemm_gelu_f32_{N}", out, _gemm_ref(a, w, bias, act=K.EPI_QUICKGELU), atol=3e-3, rtol=2e-3)
+    # output written into a column slice of a wider buffer (ldo > N): neighbours must stay untouched
+    wide = torch.full((M, N + 64), 7.0, dtype=torch.float32, device=d)
+    K.gemm_epi(a.to(d), w.to(d), bias=bias.to(d), out=wide[:, 32:32 + N])
+    _close(f"gemm_slice_{N}", wide[:, 32:32 + N], _gemm_ref(a, w, bias), atol=2e-3, rtol=1e-3)
+    assert bool((wide[:, :32] == 7.0).all()) and bool((wide[:, 32 + N:] == 7.0).all())
 
 
 def test_gemm_lora_extension(cuda_device):

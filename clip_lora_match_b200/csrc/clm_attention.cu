@@ -7,17 +7,18 @@
 //   warp 0      TMA producer: Q, K, V of the next items (128-byte-swizzled boxes straight out of
 //               the fused QKV activation [B*T, 3D]) into a ring of shared-memory stages.
 //               K and V are loaded ONCE per (batch, head) and shared by all its query tiles.
-//   warp 1      MMA issuer.  Per 128-query tile t:  S = Q K^T  (SS form, K-major A and B) into
-//               TMEM slot t % 2;  later  O = P V  (TS form: P is read from TMEM, V is an MN-major
-//               shared-memory operand, so neither P nor V^T is ever materialised in smem/HBM).
-//   warps 2-5 / 6-9   two softmax groups that alternate tiles (ping-pong): thread = query row;
+//   warp 1      MMA issuer.  Per 128-query tile t:  S = Q K^T  (SS form, K-major A and B) into the
+//               TMEM region of parity t % 2;  later  O = P V  (TS form: P is read from TMEM, V is an
+//               MN-major shared-memory operand, so neither P nor V^T is ever materialised).  Tiles of
+//               the two parities are independent streams; the warp polls their barriers and issues
+//               whatever is ready (the tensor pipe executes in issue order, so S(t+2) may reuse the
+//               S/P columns of tile t as soon as PV(t) has been issued).
+//   warps 2-17  softmax: 2 groups (tile parity) x 2 threads per query row x 4 TMEM lane quarters.
 //               pass 1 row max, pass 2 p = 2^(s*c - max*c) (one FFMA + one MUFU.EX2), row sum,
-//               P written back to TMEM as packed bf16 over the columns S no longer needs;
-//               then O is read from TMEM, scaled by 1/rowsum and stored as bf16.
+//               P written back to TMEM as packed bf16 over the S columns already consumed; the two
+//               threads of a row take alternate 32-column chunks and exchange max / sum through
+//               shared memory.  Then each reads its half of O, scales by 1/rowsum, stores bf16.
 //
-// The MMA warp runs ahead: S(t+2) is issued right behind PV(t) (the tensor pipe executes in issue
-// order, so it may reuse the S/P columns of tile t without a barrier), and the softmax threads keep
-// the tcgen05.ld of the next 32-column chunk in flight while they work on the current one.
 // The TMA warp is one or more items ahead, so HBM latency is off the critical path.
 // TMEM plan: see clm_attention_launch (S fp32 -> P bf16x2 aliases its first half; O fp32 separate,
 // or inside the dead upper part of its own S region when 512 columns are not enough).
@@ -30,13 +31,13 @@ namespace {
 
 using namespace clm;
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 576;  // TMA warp + MMA warp + 16 softmax warps
+constexpr int kXchBytes = 4096;   // row max / row sum exchanged between the two threads of a query row
 constexpr int kHeadDim = 64;
 constexpr int kMaxStages = 6;
 
 struct AttnParams {
   int T, H, Tp, mtiles, num_items, stages, stage_bytes, nslots;
-  int stagger_clks;  // head start of softmax group 0 over group 1 (de-synchronises the two groups)
   // TMEM column of the S / P region and of the O accumulator used by tiles of parity 0 / 1;
   // o_alias: O lives inside the same parity's S region (dead by then), so S(t+2) waits for the drain
   int s_col0, s_col1, o_col0, o_col1, o_alias0, o_alias1;
@@ -142,6 +143,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
   uint64_t* o_full = s_full + 4;                   // [2] O ready (MMA commit)
   uint64_t* slot_free = s_full + 6;                // [2] O drained (128 softmax threads)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
+  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [group][half][128]
+  float* xsum = xmax + 2 * 2 * 128;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -160,9 +163,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 128);
+      mbar_init(&p_full[s], 256);
       mbar_init(&o_full[s], 1);
-      mbar_init(&slot_free[s], 128);
+      mbar_init(&slot_free[s], 256);
     }
     fence_barrier_init();
   }
@@ -204,43 +207,52 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
     // The tensor pipe executes in issue order, so S(t+2) may overwrite the S/P columns of tile t as
     // soon as PV(t) has been ISSUED; it only waits when O(t) is aliased into those columns.
     const uint32_t idesc_pv = umma_idesc_bf16(128, kHeadDim, 0, 1);
-    // cursors: (item, tile-in-item, stage, stage phase) of the next S and of the next PV to issue
-    int smt = 0, sst = 0;
-    uint32_t sph = 0;
-    int pmt = 0, pst = 0;
-    auto issue_s = [&](int t) {
-      if (smt == 0) {
-        mbar_wait(&stage_full[sst], sph);
-        tc_fence_after();
+    // A tile goes S -> (softmax) -> PV; tiles of the two parities are independent streams.  With two S
+    // regions the warp polls both streams and issues whatever is ready, so one group never waits
+    // behind the other group's barrier (ViT-B/16: the odd stream must wait for its aliased O to drain).
+    struct Cursor {  // position of a stream inside the CTA's tile list
+      int t, mt, st;
+      uint32_t ph;
+      __device__ void init(int t0, const AttnParams& p) {
+        t = t0; mt = t0; st = 0; ph = 0;
+        while (mt >= p.mtiles) { mt -= p.mtiles; bump(p); }
       }
+      __device__ void bump(const AttnParams& p) {
+        if (++st == p.stages) { st = 0; ph ^= 1; }
+      }
+      __device__ void advance(int step, const AttnParams& p) {
+        t += step; mt += step;
+        while (mt >= p.mtiles) { mt -= p.mtiles; bump(p); }
+      }
+    };
+    auto do_s = [&](const Cursor& c) {
       if (lane == 0) {
-        const uint32_t q_addr = smem_u32(smem + sst * p.stage_bytes);
+        const uint32_t q_addr = smem_u32(smem + c.st * p.stage_bytes);
         const uint32_t k_addr = q_addr + kv_bytes;
-        const uint32_t sbase = tmem + static_cast<uint32_t>(p.s_col(t & 1));
+        const uint32_t sbase = tmem + static_cast<uint32_t>(p.s_col(c.t & 1));
         for (int n0 = 0; n0 < Tp; n0 += 256) {
           const int nn = (Tp - n0) < 256 ? (Tp - n0) : 256;
           const uint32_t idesc = umma_idesc_bf16(128, nn, 0, 0);
 #pragma unroll
           for (int k = 0; k < kHeadDim / 16; ++k)
-            umma_bf16_ss(sbase + n0, umma_desc_sw128(q_addr + smt * 16384 + k * 32, 1024),
+            umma_bf16_ss(sbase + n0, umma_desc_sw128(q_addr + c.mt * 16384 + k * 32, 1024),
                          umma_desc_sw128(k_addr + n0 * 128 + k * 32, 1024), idesc, k != 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[t & 1]);
+        umma_commit(&s_full[c.t & 1]);
       }
       __syncwarp();
-      if (++smt == p.mtiles) {
-        smt = 0;
-        if (++sst == p.stages) { sst = 0; sph ^= 1; }
-      }
     };
-    auto issue_pv = [&](int t) {
+    int pv_cnt[kMaxStages];  // PVs issued per stage: the last one of an item releases its stage
+#pragma unroll
+    for (int i = 0; i < kMaxStages; ++i) pv_cnt[i] = 0;
+    auto do_pv = [&](const Cursor& c) {
       // O(t) = P(t) V : P from TMEM (written by the softmax group), V MN-major from smem.  p_full(t)
       // also implies that the same group has drained O(t-2), whose columns this overwrites.
-      const int b = t & 1;
-      mbar_wait(&p_full[b], static_cast<uint32_t>((t >> 1) & 1));
-      tc_fence_after();
+      const int b = c.t & 1;
+      const bool last = (++pv_cnt[c.st] == p.mtiles);
+      if (last) pv_cnt[c.st] = 0;
       if (lane == 0) {
-        const uint32_t v_addr = smem_u32(smem + pst * p.stage_bytes) + 2 * kv_bytes;
+        const uint32_t v_addr = smem_u32(smem + c.st * p.stage_bytes) + 2 * kv_bytes;
         const uint32_t pbase = tmem + static_cast<uint32_t>(p.s_col(b));
         const uint32_t obase = tmem + static_cast<uint32_t>(p.o_col(b));
         const int ksteps = Tp / 16;
@@ -248,49 +260,79 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
           umma_bf16_ts(obase, pbase + ks * 8, umma_desc_sw128_mn(v_addr + ks * 2048), idesc_pv,
                        ks != 0 ? 1u : 0u);
         umma_commit(&o_full[b]);
-        if (pmt == p.mtiles - 1) umma_commit(&stage_empty[pst]);  // stage reusable once these MMAs retire
+        if (last) umma_commit(&stage_empty[c.st]);  // stage reusable once these MMAs retire
       }
       __syncwarp();
-      if (++pmt == p.mtiles) {
-        pmt = 0;
-        if (++pst == p.stages) pst = 0;
-      }
     };
     if (p.nslots == 2) {
-      if (n_tiles > 0) issue_s(0);
-      if (n_tiles > 1) issue_s(1);
-      for (int t = 0; t < n_tiles; ++t) {
-        issue_pv(t);
-        if (t + 2 < n_tiles) {
-          if (p.o_alias(t & 1)) {
-            mbar_wait(&slot_free[t & 1], static_cast<uint32_t>((t >> 1) & 1));
+      Cursor sc[2], pc[2];  // next S / next PV of each stream
+      sc[0].init(0, p); sc[1].init(1, p); pc[0].init(0, p); pc[1].init(1, p);
+      while (pc[0].t < n_tiles || pc[1].t < n_tiles) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          // PV(t): S(t) has been issued and the group has published P(t)
+          if (pc[b].t < sc[b].t && mbar_try_wait(&p_full[b], static_cast<uint32_t>((pc[b].t >> 1) & 1))) {
             tc_fence_after();
+            do_pv(pc[b]);
+            pc[b].advance(2, p);
           }
-          issue_s(t + 2);
+          // S(t): PV(t-2) has been issued (in-order pipe: its P columns are safe); an aliased O(t-2)
+          // has been drained; the item's Q/K/V have landed
+          if (sc[b].t < n_tiles && sc[b].t - 2 < pc[b].t) {
+            bool ok = true;
+            if (p.o_alias(b) && sc[b].t >= 2)
+              ok = mbar_try_wait(&slot_free[b], static_cast<uint32_t>(((sc[b].t - 2) >> 1) & 1));
+            if (ok) ok = mbar_try_wait(&stage_full[sc[b].st], sc[b].ph);
+            if (ok) {
+              tc_fence_after();
+              do_s(sc[b]);
+              sc[b].advance(2, p);
+            }
+          }
         }
       }
     } else {
-      if (n_tiles > 0) issue_s(0);
-      for (int t = 0; t < n_tiles; ++t) {
-        issue_pv(t);
-        if (t + 1 < n_tiles) issue_s(t + 1);
+      // one S region: strictly S(t), PV(t), S(t+1), ... (the groups alternate)
+      Cursor c;
+      c.init(0, p);
+      if (n_tiles > 0) {
+        mbar_wait(&stage_full[c.st], c.ph);
+        tc_fence_after();
+        do_s(c);
+      }
+      while (c.t < n_tiles) {
+        mbar_wait(&p_full[c.t & 1], static_cast<uint32_t>((c.t >> 1) & 1));
+        tc_fence_after();
+        do_pv(c);
+        c.advance(1, p);
+        if (c.t < n_tiles) {
+          mbar_wait(&stage_full[c.st], c.ph);
+          tc_fence_after();
+          do_s(c);
+        }
       }
     }
   } else {
     // ================= softmax groups =================
-    // group g (warps 2-5 / 6-9) owns the tiles of parity g; thread = query row = TMEM lane.
-    const int g = (warp - 2) >> 2;
+    // 16 warps = 2 groups (tile parity) x 2 column halves x 4 TMEM lane quarters.  A query row is
+    // shared by two threads (same lane of two warps with the same quarter): each reduces / exponentiates
+    // every other 32-column chunk of the row and they exchange row max and row sum through shared memory.
+    // Twice the warps per tile halves the latency of the softmax phase that the tensor pipe waits on.
+    const int sel = (warp - 2) >> 2;
+    const int g = sel & 1;               // group = parity of the tiles it owns
+    const int hf = sel >> 1;             // which half of the row's chunks (and of O's columns)
     const int q = warp & 3;              // TMEM lane quarter of this warp
     const int r = q * 32 + lane;         // row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const int nchunks = (Tp + 31) / 32;
     constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     const uint32_t srow = tmem + lane_off + static_cast<uint32_t>(p.s_col(g));
-    const uint32_t orow = tmem + lane_off + static_cast<uint32_t>(p.o_col(g));
-    if (g == 1 && p.stagger_clks > 0) {  // let group 0 run ahead: the groups then alternate instead of
-      const long long t0 = clock64();    // computing and waiting for the tensor pipe in lockstep
-      while (clock64() - t0 < p.stagger_clks) {}
-    }
+    const uint32_t orow = tmem + lane_off + static_cast<uint32_t>(p.o_col(g)) + static_cast<uint32_t>(hf * 32);
+    float* my_max = xmax + (g * 2 + hf) * 128 + r;
+    float* other_max = xmax + (g * 2 + (hf ^ 1)) * 128 + r;
+    float* my_sum = xsum + (g * 2 + hf) * 128 + r;
+    float* other_sum = xsum + (g * 2 + (hf ^ 1)) * 128 + r;
+    const int pair_bar = 1 + g * 4 + q;  // named barrier of the two warps that share these 32 rows
     int t = 0;
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x)
     for (int mt = 0; mt < p.mtiles; ++mt, ++t) {
@@ -301,91 +343,81 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       const bool warp_live = mt * 128 + q * 32 < T;    // does this warp own any real row?
       int valid = T;
       if (kCausal) valid = (qi + 1 < T) ? qi + 1 : T;
-      // chunks this warp has to look at: under the causal mask nothing right of its last row counts
+      // chunks this warp pair has to look at: under the causal mask nothing right of its last row counts
       int nch = nchunks;
       if (kCausal) {
         const int wv = (mt * 128 + q * 32 + 32 < T) ? mt * 128 + q * 32 + 32 : T;
         nch = (wv + 31) / 32;
       }
+      // the two threads of a row take alternate chunks: thread hf owns chunks 2i + hf
+      const int niter = (nch + 1) >> 1;
 
       mbar_wait(&s_full[g], par);
       tc_fence_after();
-      float sum = 1.f;
+      uint32_t v[32];
+      // ---- pass 1: max over this thread's chunks, then the row max
+      float mx = -INFINITY;
       if (warp_live) {
-        // ---- pass 1: row max.  The load of chunk c+1 is in flight while chunk c is reduced.
-        uint32_t va[32], vb[32];
-        float mx = -INFINITY;
-        tmem_ld_32x32b_x32(srow, va);
-        for (int c = 0; c < nch; c += 2) {
+        for (int c = hf; c < nch; c += 2) {
+          tmem_ld_32x32b_x32(srow + c * 32, v);
           tmem_ld_wait();
-          if (c + 1 < nch) tmem_ld_32x32b_x32(srow + (c + 1) * 32, vb);
-          mx = (c * 32 + 32 <= valid) ? chunk_max(va, mx) : chunk_max_masked(va, mx, c * 32, valid);
-          if (c + 1 < nch) {
-            tmem_ld_wait();
-            if (c + 2 < nch) tmem_ld_32x32b_x32(srow + (c + 2) * 32, va);
-            mx = (c * 32 + 64 <= valid) ? chunk_max(vb, mx) : chunk_max_masked(vb, mx, c * 32 + 32, valid);
-          }
+          mx = (c * 32 + 32 <= valid) ? chunk_max(v, mx) : chunk_max_masked(v, mx, c * 32, valid);
         }
-        // ---- pass 2: p = 2^(s*c - max*c), row sum, P (bf16x2) over the S columns already consumed
+      }
+      *my_max = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      mx = fmaxf(mx, *other_max);
+      // ---- pass 2: p = 2^(s*c - max*c), partial row sum, P (bf16x2) written over S.  P(c) lands in the
+      // columns of S chunk c/2, so the pair synchronises once per iteration: by then both threads hold
+      // every chunk up to 2i+1 in registers and the columns of chunk i are dead.
+      float sum = 0.f;
+      if (warp_live) {
         const float neg_mx = -mx * kScaleLog2e;
-        sum = 0.f;
         uint32_t pk[16];
-        tmem_ld_32x32b_x32(srow, va);
-        for (int c = 0; c < nch; c += 2) {
-          tmem_ld_wait();
-          if (c + 1 < nch) tmem_ld_32x32b_x32(srow + (c + 1) * 32, vb);
-          sum += (c * 32 + 32 <= valid) ? chunk_exp<false>(va, pk, kScaleLog2e, neg_mx, c * 32, valid)
-                                        : chunk_exp<true>(va, pk, kScaleLog2e, neg_mx, c * 32, valid);
-          tmem_st_32x32b_x16(srow + c * 16, pk);
-          if (c + 1 < nch) {
+        for (int i = 0; i < niter; ++i) {
+          const int c = 2 * i + hf;
+          if (c < nch) {
+            tmem_ld_32x32b_x32(srow + c * 32, v);
             tmem_ld_wait();
-            if (c + 2 < nch) tmem_ld_32x32b_x32(srow + (c + 2) * 32, va);
-            sum += (c * 32 + 64 <= valid)
-                       ? chunk_exp<false>(vb, pk, kScaleLog2e, neg_mx, c * 32 + 32, valid)
-                       : chunk_exp<true>(vb, pk, kScaleLog2e, neg_mx, c * 32 + 32, valid);
-            tmem_st_32x32b_x16(srow + (c + 1) * 16, pk);
+            sum += (c * 32 + 32 <= valid) ? chunk_exp<false>(v, pk, kScaleLog2e, neg_mx, c * 32, valid)
+                                          : chunk_exp<true>(v, pk, kScaleLog2e, neg_mx, c * 32, valid);
           }
+          tc_fence_before();
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          tc_fence_after();
+          if (c < nch) tmem_st_32x32b_x16(srow + c * 16, pk);
         }
-        if (kCausal && nch < nchunks) {  // P right of the causal frontier is zero (PV reads all of it)
+        if (kCausal && hf == 1 && nch < nchunks) {  // P right of the causal frontier is zero (PV reads it)
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[i] = 0u;
           for (int c = nch; c < nchunks; ++c) tmem_st_32x32b_x16(srow + c * 16, pk);
         }
         tmem_st_wait();
       }
+      *my_sum = sum;
       tc_fence_before();
       mbar_arrive(&p_full[g]);
 
       mbar_wait(&o_full[g], par);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
+      sum += *other_sum;  // published before the partner's p_full arrive, which o_full transitively follows
       if (warp_live) {
-        tmem_ld_32x32b_x32(orow, o0);
-        tmem_ld_32x32b_x32(orow + 32, o1);
+        tmem_ld_32x32b_x32(orow, v);
         tmem_ld_wait();
       }
       tc_fence_before();
-      mbar_arrive(&slot_free[g]);  // O(t) is in registers: its columns may be overwritten
+      mbar_arrive(&slot_free[g]);  // this half of O(t) is in registers: its columns may be overwritten
       if (warp_live && qi < T) {
         const float inv = 1.0f / sum;
-        uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(b * T + qi) * D + h * kHeadDim);
+        uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(b * T + qi) * D + h * kHeadDim + hf * 32);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(o0[8 * jj + 0]) * inv, __uint_as_float(o0[8 * jj + 1]) * inv);
-          o.y = pack_bf16x2(__uint_as_float(o0[8 * jj + 2]) * inv, __uint_as_float(o0[8 * jj + 3]) * inv);
-          o.z = pack_bf16x2(__uint_as_float(o0[8 * jj + 4]) * inv, __uint_as_float(o0[8 * jj + 5]) * inv);
-          o.w = pack_bf16x2(__uint_as_float(o0[8 * jj + 6]) * inv, __uint_as_float(o0[8 * jj + 7]) * inv);
+          o.x = pack_bf16x2(__uint_as_float(v[8 * jj + 0]) * inv, __uint_as_float(v[8 * jj + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(v[8 * jj + 2]) * inv, __uint_as_float(v[8 * jj + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(v[8 * jj + 4]) * inv, __uint_as_float(v[8 * jj + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(v[8 * jj + 6]) * inv, __uint_as_float(v[8 * jj + 7]) * inv);
           o4[jj] = o;
-        }
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(o1[8 * jj + 0]) * inv, __uint_as_float(o1[8 * jj + 1]) * inv);
-          o.y = pack_bf16x2(__uint_as_float(o1[8 * jj + 2]) * inv, __uint_as_float(o1[8 * jj + 3]) * inv);
-          o.z = pack_bf16x2(__uint_as_float(o1[8 * jj + 4]) * inv, __uint_as_float(o1[8 * jj + 5]) * inv);
-          o.w = pack_bf16x2(__uint_as_float(o1[8 * jj + 6]) * inv, __uint_as_float(o1[8 * jj + 7]) * inv);
-          o4[4 + jj] = o;
         }
       }
     }
@@ -418,19 +450,12 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   int stage_bytes = 3 * p.Tp * 128;
   if (stage_bytes < p.mtiles * 16384) stage_bytes = p.mtiles * 16384;
   p.stage_bytes = stage_bytes;
-  const int smem_budget = 227 * 1024 - 1024 - 256;
+  const int smem_budget = 227 * 1024 - 1024 - 256 - kXchBytes;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   CLM_REQUIRE(stages >= 1, "clm_attention: tokens=%d needs %d bytes of shared memory per stage", T,
               stage_bytes);
   p.stages = stages;
-  // group 1 starts ~half a tile period after group 0 (CLM_ATTN_STAGGER overrides, in clocks)
-  static int stagger_env = -2;
-  if (stagger_env == -2) {
-    const char* e = getenv("CLM_ATTN_STAGGER");
-    stagger_env = e ? atoi(e) : -1;
-  }
-  p.stagger_clks = stagger_env >= 0 ? stagger_env : 12 * p.Tp;
   // TMEM plan (512 columns).  S needs round_up(Tp,32) fp32 columns (the softmax reads 32-column
   // chunks); P (bf16x2) reuses its first Tp/2; O needs 64.  Tiles alternate between two parities:
   //   two S regions + two O regions            (T <= 192)
@@ -455,7 +480,7 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
     p.o_col0 = s_cols; p.o_col1 = s_cols + 64;
     p.o_alias0 = 0; p.o_alias1 = 0;
   }
-  const int smem_bytes = stages * stage_bytes + 256 + 1024;
+  const int smem_bytes = stages * stage_bytes + 256 + kXchBytes + 1024;
 
   CUtensorMap map64, map16;
   int rc = clm_make_tmap_bf16_2d(&map64, qkv, static_cast<uint64_t>(batch) * T, 3ull * D, 3ull * D,

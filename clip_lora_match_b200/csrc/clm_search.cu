@@ -15,6 +15,7 @@
 //   bf16 scores only ever *nominate*; every returned score is an fp32 dot product, which is
 //   what makes the ids match the fp32 reference.
 #include <math.h>
+#include <stdlib.h>
 
 #include "clm_common.cuh"
 
@@ -28,21 +29,95 @@ constexpr int BK = 64;
 constexpr int kThreads = 192;
 constexpr int kAccStages = 2;
 constexpr int kABytes = BM * BK * 2;
-constexpr int kBBytes = BN * BK * 2;
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 6;
 constexpr int kTmemCols = kAccStages * BN;
+// per-CTA stage: its 128 query rows + its share of the 256-row index tile (all of it, or half in a CTA pair)
+template <int kCtas>
+struct SCfg {
+  static constexpr int kBBytes = (BN / kCtas) * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+};
 
 struct SearchParams {
-  int nq, n, kblocks, q_tiles, splits, tiles_n, kc, stages;
+  int nq, n, kblocks, q_tiles, splits, tiles_n, kc, stages;  // q_tiles: tiles of BM * kCtas queries
   float* thr_io;  // per-query running lower bound of the kc-th best score, shared by all units (or null)
   float* cand_score;
   int32_t* cand_id;
 };
 
+// ---- cta_group::2 helpers (same protocol as clm_gemm.cu) --------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                     int c0, int c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      :
+      : "r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32  remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64  _, [remAddr32];\n\t"
+      "}"
+      :
+      : "r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// kCtas = 2: a CTA pair (cluster of 2, cta_group::2) scores 256 queries x 256 index rows per
+// accumulator; each CTA loads its own 128 queries and HALF of the index tile, so the operand bytes
+// pulled from L2 per FLOP drop by a third (the Q >= 256 regime is L2-to-SM-bandwidth bound).
+template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
               SearchParams p) {
+  constexpr int kStageBytes = SCfg<kCtas>::kStageBytes;
+  constexpr int kBBytes = SCfg<kCtas>::kBBytes;
+  constexpr int TM = BM * kCtas;  // queries per work unit
+  const uint32_t rank = (kCtas == 2) ? cluster_ctarank() : 0u;
+  const int worker = (kCtas == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int num_workers = (kCtas == 2) ? (gridDim.x >> 1) : gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -68,16 +143,21 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], 4 * kCtas);  // one arrive per epilogue warp of the pair
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (kCtas == 2) {
+      tmem_alloc_2sm(tmem_slot, kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -86,31 +166,39 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      for (int u = worker; u < num_units; u += num_workers) {
         const int split = u / p.q_tiles;
-        const int q0 = (u % p.q_tiles) * BM;
+        const int q0 = (u % p.q_tiles) * TM + static_cast<int>(rank) * BM;
         const int t0 = static_cast<int>(static_cast<long long>(split) * p.tiles_n / p.splits);
         const int t1 = static_cast<int>(static_cast<long long>(split + 1) * p.tiles_n / p.splits);
         for (int t = t0; t < t1; ++t) {
+          const int e0 = t * BN + static_cast<int>(rank) * (BN / kCtas);
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * kStageBytes;
-            mbar_arrive_expect_tx(&full[stage], kStageBytes);
-            tma_load_2d_hint(sa, &map_q, &full[stage], kb * BK, q0, kEvictLast);
-            tma_load_2d_hint(sa + kABytes, &map_e, &full[stage], kb * BK, t * BN, kEvictFirst);
+            if (kCtas == 2) {
+              // the leader's barrier collects the bytes of BOTH CTAs
+              if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * kStageBytes);
+              tma_load_2d_2sm_hint(sa, &map_q, &full[stage], kb * BK, q0, kEvictLast);
+              tma_load_2d_2sm_hint(sa + kABytes, &map_e, &full[stage], kb * BK, e0, kEvictFirst);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], kStageBytes);
+              tma_load_2d_hint(sa, &map_q, &full[stage], kb * BK, q0, kEvictLast);
+              tma_load_2d_hint(sa + kABytes, &map_e, &full[stage], kb * BK, e0, kEvictFirst);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+    // ================= MMA issuer (leader CTA only) =================
+    constexpr uint32_t idesc = umma_idesc_bf16(TM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    for (int u = worker; rank == 0 && u < num_units; u += num_workers) {
       const int split = u / p.q_tiles;
       const int t0 = static_cast<int>(static_cast<long long>(split) * p.tiles_n / p.splits);
       const int t1 = static_cast<int>(static_cast<long long>(split + 1) * p.tiles_n / p.splits);
@@ -126,11 +214,18 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16_ss(tmem_d, umma_desc_sw128(a_addr + k * 32, 1024),
-                           umma_desc_sw128(b_addr + k * 32, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+              const uint64_t da = umma_desc_sw128(a_addr + k * 32, 1024);
+              const uint64_t db = umma_desc_sw128(b_addr + k * 32, 1024);
+              if (kCtas == 2) umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty[stage]);
-            if (kb == p.kblocks - 1) umma_commit(&tmem_full[acc]);
+            if (kCtas == 2) {
+              umma_commit_2sm(&empty[stage]);                             // frees the slot in both CTAs
+              if (kb == p.kblocks - 1) umma_commit_2sm(&tmem_full[acc]);  // scores ready (both CTAs)
+            } else {
+              umma_commit(&empty[stage]);
+              if (kb == p.kblocks - 1) umma_commit(&tmem_full[acc]);
+            }
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -147,11 +242,12 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const int kc = p.kc;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    for (int u = worker; u < num_units; u += num_workers) {
       const int split = u / p.q_tiles;
-      const int q0 = (u % p.q_tiles) * BM;
+      const int q0 = (u % p.q_tiles) * TM + static_cast<int>(rank) * BM;
       const int t0 = static_cast<int>(static_cast<long long>(split) * p.tiles_n / p.splits);
       const int t1 = static_cast<int>(static_cast<long long>(split + 1) * p.tiles_n / p.splits);
+      const bool warp_live = q0 + q * 32 < p.nq;  // rows past the last query: nothing to scan
       int cnt = 0;
       int minpos = 0;
       // thr is a lower bound of this query's kc-th best score over the WHOLE index: the k-th best of
@@ -174,7 +270,7 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const int row0 = t * BN;
         const bool ragged = row0 + BN > p.n;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; warp_live && c < BN / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + c * 32, v);
           tmem_ld_wait();
@@ -217,7 +313,10 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if (kCtas == 2) mbar_arrive_cta(&tmem_empty[acc], 0);  // the leader's MMA thread waits on it
+          else mbar_arrive(&tmem_empty[acc]);
+        }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
       // flush this unit's list: [query][split][kc], padded with (-inf, -1)
@@ -234,8 +333,31 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if (kCtas == 2) tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int kCtas>
+int launch_search(const CUtensorMap& mq, const CUtensorMap& me, const SearchParams& p, int smem, int workers,
+                  cudaStream_t stream) {
+  CLM_CUDA_CHECK(cudaFuncSetAttribute(search_kernel<kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(workers * kCtas);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, search_kernel<kCtas>, mq, me, p));
+  return CLM_OK;
 }
 
 // -----------------------------------------------------------------------------------------
@@ -434,12 +556,24 @@ int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } ret
 
 }  // namespace
 
+// CTA pairs (256 queries per work unit) once there are more than 128 queries; the streaming regime
+// (<= 128 queries, HBM-bound) keeps the single-CTA kernel.  CLM_SEARCH_1CTA=1 forces the latter.
+static int search_ctas(int num_queries) {
+  static int force_1cta = -1;
+  if (force_1cta < 0) {
+    const char* e = getenv("CLM_SEARCH_1CTA");
+    force_1cta = (e && e[0] == '1') ? 1 : 0;
+  }
+  return (!force_1cta && num_queries > BM) ? 2 : 1;
+}
+
 extern "C" int clm_search_num_splits(int num_queries, int num_rows) {
   if (num_queries <= 0 || num_rows <= 0) return 1;
-  const int q_tiles = (num_queries + BM - 1) / BM;
+  const int ctas = search_ctas(num_queries);
+  const int q_tiles = (num_queries + BM * ctas - 1) / (BM * ctas);
   const int tiles_n = (num_rows + BN - 1) / BN;
-  const int sms = clm_num_sms();
-  int splits = sms / gcd_int(q_tiles, sms);  // q_tiles*splits is a multiple of the SM count
+  const int workers = clm_num_sms() / ctas;
+  int splits = workers / gcd_int(q_tiles, workers);  // q_tiles*splits is a multiple of the worker count
   if (splits > tiles_n) splits = tiles_n;
   if (splits < 1) splits = 1;
   return splits;
@@ -452,14 +586,15 @@ extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int n
   CLM_REQUIRE(nq > 0 && n > 0 && dim > 0 && dim % 8 == 0, "clm_search_topk: bad shape nq=%d n=%d dim=%d",
               nq, n, dim);
   CLM_REQUIRE(kc >= 1 && kc <= kMaxKc, "clm_search_topk: kc=%d must be in [1,%d]", kc, kMaxKc);
-  const int q_tiles = (nq + BM - 1) / BM;
+  const int ctas = search_ctas(nq);
+  const int q_tiles = (nq + BM * ctas - 1) / (BM * ctas);
   const int tiles_n = (n + BN - 1) / BN;
   CLM_REQUIRE(splits >= 1 && splits <= tiles_n, "clm_search_topk: splits=%d must be in [1,%d]", splits,
               tiles_n);
   CUtensorMap mq, me;
   int rc;
   if ((rc = clm_make_tmap_bf16_2d(&mq, q_bf16, nq, dim, dim, BK, BM))) return rc;
-  if ((rc = clm_make_tmap_bf16_2d(&me, index_bf16, n, dim, dim, BK, BN))) return rc;
+  if ((rc = clm_make_tmap_bf16_2d(&me, index_bf16, n, dim, dim, BK, BN / ctas))) return rc;
   SearchParams p;
   p.nq = nq;
   p.n = n;
@@ -468,21 +603,25 @@ extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int n
   p.splits = splits;
   p.tiles_n = tiles_n;
   p.kc = kc;
-  p.stages = kc <= 32 ? 4 : 3;
   p.thr_io = thr_io;
   p.cand_score = cand_score;
   p.cand_id = cand_id;
-  const int smem = p.stages * kStageBytes + kc * BM * 8 + 256 + 1024;
-  CLM_CUDA_CHECK(cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int stage_bytes = ctas == 2 ? SCfg<2>::kStageBytes : SCfg<1>::kStageBytes;
+  const int fixed = kc * BM * 8 + 256 + 1024;
+  int stages = (227 * 1024 - fixed) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (ctas == 1 && stages > 4) stages = 4;
+  p.stages = stages;
+  const int smem = stages * stage_bytes + fixed;
   const long long units = static_cast<long long>(q_tiles) * splits;
-  const int grid = units < clm_num_sms() ? static_cast<int>(units) : clm_num_sms();
+  const int max_workers = clm_num_sms() / ctas;
+  const int workers = units < max_workers ? static_cast<int>(units) : max_workers;
   // algorithmic bytes: index once + queries once + candidate lists
   ProfScope prof(CLM_K_SEARCH, 2.0 * nq * static_cast<double>(n) * dim,
                  2.0 * dim * (static_cast<double>(n) + nq) + 8.0 * nq * splits * kc,
                  static_cast<cudaStream_t>(stream));
-  search_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(mq, me, p);
-  CLM_CUDA_CHECK(cudaGetLastError());
-  return CLM_OK;
+  if (ctas == 2) return launch_search<2>(mq, me, p, smem, workers, static_cast<cudaStream_t>(stream));
+  return launch_search<1>(mq, me, p, smem, workers, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int clm_topk_merge(const float* cand_score, const int32_t* cand_id, int nq, int lists, int kc,

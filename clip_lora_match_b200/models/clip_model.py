@@ -131,6 +131,7 @@ class B200ClipModel:
         self._keep: Dict[str, list] = {}
         self._workspace: Optional[torch.Tensor] = None
         self._dummy = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._stage = None  # host->device staging (encode_images of host tensors)
         self.set_lora(lora)
 
     # ---- reference-compat surface ------------------------------------------------------
@@ -286,21 +287,54 @@ class B200ClipModel:
             self._workspace = torch.empty(want, dtype=torch.uint8, device=self.device)
         return self._workspace
 
-    def encode_images(self, pixel_values: torch.Tensor, normalize: bool = True) -> torch.Tensor:
-        """[B,3,H,W] fp32 (any device) -> [B, proj_dim] fp32 on the GPU; the batched form of
-        reference encode_image (models/clip_model.py:107-116)."""
-        a = self.arch
-        if pixel_values.dim() != 4 or tuple(pixel_values.shape[1:]) != (3, a.image, a.image):
-            raise ValueError(f"pixel_values must be [B,3,{a.image},{a.image}], got {tuple(pixel_values.shape)}")
-        pv = pixel_values.to(device=self.device, dtype=torch.float32).contiguous()
+    H2D_CHUNK = 256  # images per host->device chunk when the input lives in host memory
+
+    def _encode_images_dev(self, pv: torch.Tensor, out: torch.Tensor, normalize: bool) -> None:
         b = pv.shape[0]
-        out = torch.empty((b, a.proj_dim), dtype=torch.float32, device=self.device)
-        if b == 0:
-            return out
         ws = self._ensure_workspace("vision", b)
         _lib.check(self._lib.clm_encode_image(self._towers["vision"], pv.data_ptr(), b, out.data_ptr(),
                                               int(normalize), ws.data_ptr(), ws.numel(), _lib.cur_stream()),
                    "clm_encode_image")
+
+    def encode_images(self, pixel_values: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+        """[B,3,H,W] fp32 (any device) -> [B, proj_dim] fp32 on the GPU; the batched form of
+        reference encode_image (models/clip_model.py:107-116).
+
+        Host inputs are streamed: the batch is cut into H2D_CHUNK-image chunks and the copy of chunk
+        i+1 (second stream, two staging buffers) overlaps the encoder kernels of chunk i, so PCIe
+        time hides behind compute instead of adding to it (pin the tensor for the copy to be async)."""
+        a = self.arch
+        if pixel_values.dim() != 4 or tuple(pixel_values.shape[1:]) != (3, a.image, a.image):
+            raise ValueError(f"pixel_values must be [B,3,{a.image},{a.image}], got {tuple(pixel_values.shape)}")
+        b = pixel_values.shape[0]
+        out = torch.empty((b, a.proj_dim), dtype=torch.float32, device=self.device)
+        if b == 0:
+            return out
+        if pixel_values.is_cuda or b <= self.H2D_CHUNK:
+            pv = pixel_values.to(device=self.device, dtype=torch.float32).contiguous()
+            self._encode_images_dev(pv, out, normalize)
+            return out
+        src = pixel_values.to(dtype=torch.float32).contiguous()
+        cs = self.H2D_CHUNK
+        if self._stage is None:
+            self._stage = [torch.empty((cs, 3, a.image, a.image), dtype=torch.float32, device=self.device)
+                           for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._ev_ready = [torch.cuda.Event() for _ in range(2)]
+            self._ev_free = [torch.cuda.Event() for _ in range(2)]
+        cur = torch.cuda.current_stream(self.device)
+        for k in range(2):
+            self._ev_free[k].record(cur)  # both staging buffers are free as of now on this stream
+        for i, b0 in enumerate(range(0, b, cs)):
+            k = i & 1
+            n = min(cs, b - b0)
+            self._copy_stream.wait_event(self._ev_free[k])
+            with torch.cuda.stream(self._copy_stream):
+                self._stage[k][:n].copy_(src[b0:b0 + n], non_blocking=True)
+                self._ev_ready[k].record(self._copy_stream)
+            cur.wait_event(self._ev_ready[k])
+            self._encode_images_dev(self._stage[k][:n], out[b0:b0 + n], normalize)
+            self._ev_free[k].record(cur)
         return out
 
     def encode_texts(self, input_ids: torch.Tensor, normalize: bool = True) -> torch.Tensor:

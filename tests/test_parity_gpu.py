@@ -153,6 +153,20 @@ def test_micro_batching_is_invisible(cuda_device):
     assert torch.equal(full, split)
 
 
+def test_host_inputs_are_streamed_in_chunks(cuda_device):
+    """encode_images of a (pinned) host tensor copies chunk i+1 while chunk i is encoded; the result
+    is the same as for a device-resident batch, also with a ragged last chunk and when called twice."""
+    model = O.build_model("tiny-test", seed=0)
+    gpu = _b200_model("tiny-test", model, {}, 8, 16, (), cuda_device)
+    gpu.H2D_CHUNK = 8
+    pv = O.synth_images(29, seed=2)
+    ref = gpu.encode_images(pv.to(cuda_device)).cpu()
+    got = gpu.encode_images(pv.pin_memory()).cpu()
+    assert torch.equal(ref, got)
+    got2 = gpu.encode_images(pv).cpu()  # pageable host memory, staging buffers reused
+    assert torch.equal(ref, got2)
+
+
 # ------------------------------------------------------------------------------------------
 # search
 # ------------------------------------------------------------------------------------------

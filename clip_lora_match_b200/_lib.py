@@ -58,6 +58,7 @@ SIGNATURES = {
     "clm_version": (_I, []),
     "clm_device_check": (_I, []),
     "clm_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
+    "clm_fuse_normalize": (_I, [_P, _F, _P, _F, _P, _P, _I, _I, _P]),
     "clm_l2norm": (_I, [_P, _P, _P, _I, _I, _P]),
     "clm_embed_text": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "clm_patch_im2col": (_I, [_P, _P, _I, _I, _I, _I, _P]),

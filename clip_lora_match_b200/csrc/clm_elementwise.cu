@@ -177,6 +177,48 @@ l2norm_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16*
   }
 }
 
+// seeker query fusion: v = wa*a (+ wb*b), out = v/||v|| (seeker_service.py:146-157); warp per row
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+fuse_normalize_kernel(const float* __restrict__ a, float wa, const float* __restrict__ b, float wb,
+                      float* __restrict__ y, __nv_bfloat16* __restrict__ yb, int rows, int dim) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* a4 = reinterpret_cast<const float4*>(a + static_cast<size_t>(row) * dim);
+  const float4* b4 = b ? reinterpret_cast<const float4*>(b + static_cast<size_t>(row) * dim) : nullptr;
+  const int n4 = dim >> 2;
+  auto fused = [&](int i) {
+    float4 v = a4[i];
+    // the reference computes w*e per modality and then sums (python sum: 0 + w_t*e_t + w_i*e_i):
+    // separate roundings of the two products, no FMA contraction
+    v.x = __fmul_rn(wa, v.x); v.y = __fmul_rn(wa, v.y); v.z = __fmul_rn(wa, v.z); v.w = __fmul_rn(wa, v.w);
+    if (b4) {
+      const float4 u = b4[i];
+      v.x = __fadd_rn(v.x, __fmul_rn(wb, u.x)); v.y = __fadd_rn(v.y, __fmul_rn(wb, u.y));
+      v.z = __fadd_rn(v.z, __fmul_rn(wb, u.z)); v.w = __fadd_rn(v.w, __fmul_rn(wb, u.w));
+    }
+    return v;
+  };
+  float s = 0.f;
+  for (int i = lane_id(); i < n4; i += 32) {
+    const float4 v = fused(i);
+    s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  const float nrm = sqrtf(warp_sum(s));
+  float4* y4 = reinterpret_cast<float4*>(y + static_cast<size_t>(row) * dim);
+  uint2* yb2 = yb ? reinterpret_cast<uint2*>(yb + static_cast<size_t>(row) * dim) : nullptr;
+  for (int i = lane_id(); i < n4; i += 32) {
+    float4 v = fused(i);
+    v.x /= nrm; v.y /= nrm; v.z /= nrm; v.w /= nrm;
+    y4[i] = v;
+    if (yb2) {
+      uint2 o;
+      o.x = pack_bf16x2(v.x, v.y);
+      o.y = pack_bf16x2(v.z, v.w);
+      yb2[i] = o;
+    }
+  }
+}
+
 // im2col for a stride==kernel conv: out[(b*g*g + gy*g + gx), c*P*P + py*P + px] =
 // pix[b, c, gy*P+py, gx*P+px].  One thread produces 8 consecutive output columns (16 B).
 __global__ void __launch_bounds__(256)
@@ -251,6 +293,17 @@ extern "C" int clm_l2norm(const float* x, float* y, void* y_bf16_or_null, int ro
   ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 8.0 * rows * dim, static_cast<cudaStream_t>(stream));
   l2norm_kernel<<<blocks_for(rows), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       x, y, static_cast<__nv_bfloat16*>(y_bf16_or_null), rows, dim);
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}
+
+extern "C" int clm_fuse_normalize(const float* a, float wa, const float* b_or_null, float wb, float* out,
+                                  void* out_bf16_or_null, int rows, int dim, void* stream) {
+  if (rows == 0) return CLM_OK;
+  CLM_REQUIRE(a && out && rows > 0 && dim > 0 && dim % 4 == 0, "clm_fuse_normalize: bad argument");
+  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, (b_or_null ? 12.0 : 8.0) * rows * dim, static_cast<cudaStream_t>(stream));
+  fuse_normalize_kernel<<<blocks_for(rows), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, wa, b_or_null, wb, out, static_cast<__nv_bfloat16*>(out_bf16_or_null), rows, dim);
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
 }

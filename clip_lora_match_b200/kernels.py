@@ -42,6 +42,22 @@ def l2norm(x: torch.Tensor, want_bf16: bool = False):
     return (y, yb) if want_bf16 else y
 
 
+def fuse_normalize(a: torch.Tensor, wa: float = 1.0, b: Optional[torch.Tensor] = None, wb: float = 0.0,
+                   want_bf16: bool = False):
+    """normalize(wa*a (+ wb*b)) per row — the seeker query fusion (seeker_service.py:146-157)."""
+    _req(a, torch.float32, "a")
+    if b is not None:
+        _req(b, torch.float32, "b")
+        if b.shape != a.shape:
+            raise ValueError(f"a is {tuple(a.shape)} but b is {tuple(b.shape)}")
+    rows, dim = a.shape
+    y = torch.empty_like(a)
+    yb = torch.empty((rows, dim), dtype=torch.bfloat16, device=a.device) if want_bf16 else None
+    check(_lib.load().clm_fuse_normalize(ptr(a), float(wa), ptr(b), float(wb), ptr(y), ptr(yb), rows, dim,
+                                         cur_stream()), "clm_fuse_normalize")
+    return (y, yb) if want_bf16 else y
+
+
 def gemm_epi(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
              residual: Optional[torch.Tensor] = None, act: int = EPI_NONE,
              out_dtype: torch.dtype = torch.bfloat16, a2: Optional[torch.Tensor] = None,

@@ -139,6 +139,25 @@ class TextSearchIndex:
             self.embeddings, self.embeddings_bf16 = local, local.to(torch.bfloat16)
         self.local_rows = self.embeddings.shape[0]
 
+    @classmethod
+    def from_directory(cls, directory: Union[str, Path], device: Union[str, torch.device] = "cuda",
+                       distributed: bool = False, verbose: bool = True) -> "TextSearchIndex":
+        """Open a sharded index directory (index_store.py).  With distributed=True every rank reads
+        only the shard files that intersect its row block shard_bounds(N, rank, world) — no rank ever
+        holds the whole index — and keeps the (small) metadata of all rows for result lookup."""
+        from . import index_store as IS
+
+        man = IS.read_manifest(directory)
+        n_total = int(man["rows"])
+        rank, world = _dist_info(distributed)
+        lo, hi = shard_bounds(n_total, rank, world) if distributed else (0, n_total)
+        embs, _, _ = IS.load_rows(directory, lo, hi)
+        paths, texts = IS.load_metadata(directory)
+        if embs.shape[1] == 0 and int(man["dim"]) > 0:
+            embs = torch.empty((0, int(man["dim"])), dtype=torch.float32)
+        return cls(embeddings=embs, image_paths=paths, texts=texts, device=device, distributed=distributed,
+                   row_offset=lo, total_rows=n_total, verbose=verbose)
+
     # ---- batched search (extension) ------------------------------------------------------
     def search_batch(self, queries: torch.Tensor, top_k: int = 5) -> Tuple[torch.Tensor, torch.Tensor]:
         """queries [Q, d] (any device) -> (scores fp32 [Q,k], global ids int64 [Q,k]) on the GPU,

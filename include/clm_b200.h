@@ -56,6 +56,13 @@ int clm_layernorm(const float* x, const float* gamma, const float* beta, void* y
  * src/embedding/search.py:68,93).  fp32 in, fp32 out (may alias), optional bf16 copy. */
 int clm_l2norm(const float* x, float* y, void* y_bf16_or_null, int rows, int dim, void* stream);
 
+/* Query fusion of the seeker path (src/embedding/seeker_service.py:146-157):
+ *   v = wa * a (+ wb * b);  out = v / ||v||   (no epsilon, as the reference)
+ * a, b fp32 [rows, dim] L2-normalised text / image embeddings; b may be NULL (single modality:
+ * :148-151, pass wa = 1).  out fp32 (may alias a or b), optional bf16 copy for the scan. */
+int clm_fuse_normalize(const float* a, float wa, const float* b_or_null, float wb, float* out,
+                       void* out_bf16_or_null, int rows, int dim, void* stream);
+
 /* Text embeddings: h[b,t,:] = tok_emb[ids[b,t]] + pos_emb[t]  (modeling_clip.py:249-256).
  * ids int32 [batch, tokens]; tables fp32; h fp32 [batch*tokens, dim].
  * Also writes eos_pos[b] = first t with ids[b,t] == eos_id (0 if none), the pooling

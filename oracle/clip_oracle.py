@@ -215,6 +215,24 @@ def search_topk(index_embeddings: torch.Tensor, queries: torch.Tensor, k: int) -
     return torch.topk(sims, k=k, dim=-1, largest=True, sorted=True)
 
 
+def fuse_query(text_emb: Optional[torch.Tensor], image_emb: Optional[torch.Tensor],
+               w_text: float = 0.5, w_image: float = 0.5) -> torch.Tensor:
+    """reference src/embedding/seeker_service.py:139-157 restated: one modality -> renormalise;
+    two -> python `sum(w * e ...)` (0 + w_t*e_t + w_i*e_i) -> renormalise.  Works on (d,) or [Q,d]."""
+    embs = []
+    if text_emb is not None:
+        embs.append((text_emb.float(), w_text))
+    if image_emb is not None:
+        embs.append((image_emb.float(), w_image))
+    if not embs:
+        raise ValueError("Minimal harus ada query_text atau query_image_path.")
+    if len(embs) == 1:
+        emb, _ = embs[0]
+        return emb / emb.norm(dim=-1, keepdim=True)
+    weighted = sum(w * e for e, w in embs)
+    return weighted / weighted.norm(dim=-1, keepdim=True)
+
+
 def ids_match_with_ties(ref_scores: torch.Tensor, ref_ids: torch.Tensor, got_ids: torch.Tensor,
                         sims: torch.Tensor, tol: float = 1e-4) -> bool:
     """north_star's rule: ids identical except where the oracle scores tie within `tol`."""

@@ -198,12 +198,53 @@ def encoder_golden(ref_cm, ref_la):
     np.savez_compressed(GOLD / "encoder_golden.npz", **out)
 
 
+def fusion_golden():
+    """Run the reference's OWN SeekerService._build_query_embedding (src/embedding/seeker_service.py:84-157)
+    on given text / image embeddings: `ultralytics` (YOLO) is absent, so yolo_cropper is stubbed; the
+    module's encode_text / encode_image are replaced by table look-ups so that only the fusion
+    arithmetic under test runs (it is the unmodified reference method)."""
+    import types
+
+    stub = types.ModuleType("src.preprocessing.yolo_cropper")
+    stub.YoloCropper = object
+    sys.modules["src.preprocessing.yolo_cropper"] = stub
+    import src.embedding.seeker_service as ref_ss
+
+    d, n = 64, 12
+    txt = O.synth_unit_rows(n, d, 11)
+    img = O.synth_unit_rows(n, d, 12)
+    table_t = {f"q{i}": txt[i] for i in range(n)}
+    table_i = {Path(f"/img{i}.png"): img[i] for i in range(n)}
+    ref_ss.encode_text = lambda text, model, processor, device: table_t[text].clone()
+    ref_ss.encode_image = lambda path, model, processor, device: table_i[Path(path)].clone()
+    svc = ref_ss.SeekerService.__new__(ref_ss.SeekerService)
+    svc.model = svc.processor = svc.device = None
+    svc.yolo_cropper = None
+    svc.yolo_crop_dir = None
+    weights = [(0.5, 0.5), (0.7, 0.3), (1.0, 0.25)]
+    both = np.stack([np.stack([svc._build_query_embedding(f"q{i}", Path(f"/img{i}.png"), wt, wi).numpy()
+                               for i in range(n)]) for wt, wi in weights])
+    only_t = np.stack([svc._build_query_embedding(f"q{i}", None).numpy() for i in range(n)])
+    only_i = np.stack([svc._build_query_embedding("  ", Path(f"/img{i}.png")).numpy() for i in range(n)])
+    try:
+        svc._build_query_embedding(None, None)
+        raised = ""
+    except ValueError as e:
+        raised = str(e)
+    np.savez_compressed(GOLD / "fusion_golden.npz", text=txt.numpy(), image=img.numpy(),
+                        weights=np.array(weights, dtype=np.float32), both=both, only_text=only_t,
+                        only_image=only_i, error=np.array(raised))
+    print(f"fusion golden: {both.shape} fused rows, error message {raised!r}")
+
+
 def main():
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     ref_cm, ref_la, ref_search, ref_sim = import_reference()
-    search_golden(ref_search, ref_sim)
-    encoder_golden(ref_cm, ref_la)
+    if "--fusion-only" not in sys.argv:
+        search_golden(ref_search, ref_sim)
+        encoder_golden(ref_cm, ref_la)
+    fusion_golden()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,123 @@
+"""CPU tests of the sharded on-disk index: shard files stay readable as
+reference-format indices, appends are O(new rows), rank-wise writers need no coordination, and a
+row range touches only the shards it intersects."""
+import json
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from clip_lora_match_b200.src.embedding import index_store as IS
+from clip_lora_match_b200.src.embedding.search import shard_bounds
+from oracle import clip_oracle as O
+
+
+def _rows(n, d, seed):
+    return O.synth_unit_rows(n, d, seed)
+
+
+def test_append_scan_manifest_roundtrip(tmp_path):
+    w = IS.ShardedIndexWriter(tmp_path / "idx", dim=32)
+    a, b = _rows(5, 32, 1), _rows(3, 32, 2)
+    p0 = w.append(a, [f"a{i}.jpg" for i in range(5)], [f"ta{i}" for i in range(5)])
+    w.append(b, [f"b{i}.jpg" for i in range(3)], None)
+    man = IS.read_manifest(tmp_path / "idx")
+    assert man["format"] == IS.FORMAT and man["rows"] == 8 and man["dim"] == 32 and len(man["shards"]) == 2
+    # every shard is a valid index of the reference: the dict finder_service.py:95-102 writes
+    obj = torch.load(p0, map_location="cpu")
+    assert set(obj) == {"embeddings", "image_paths", "texts"} and obj["embeddings"].dtype == torch.float32
+    e, paths, texts = IS.load_rows(tmp_path / "idx", 0, 8)
+    assert torch.equal(e, torch.cat([a, b])) and paths[5] == "b0.jpg" and texts[:5] == [f"ta{i}" for i in range(5)]
+    assert texts[5:] == ["", "", ""]
+    # a range inside the second shard reads only that shard's rows
+    e2, p2, _ = IS.load_rows(tmp_path / "idx", 6, 8)
+    assert torch.equal(e2, b[1:]) and p2 == ["b1.jpg", "b2.jpg"]
+
+
+def test_append_after_manifest_is_picked_up_and_writer_resumes(tmp_path):
+    d = tmp_path / "idx"
+    IS.ShardedIndexWriter(d, dim=16).append(_rows(4, 16, 1))
+    assert IS.read_manifest(d)["rows"] == 4
+    w2 = IS.ShardedIndexWriter(d, dim=16)          # a new process appends later (FinderService.report_item)
+    w2.append(_rows(1, 16, 2)[0])                  # a single (d,) vector
+    man = IS.read_manifest(d)                      # stale manifest is rebuilt from the sidecars
+    assert man["rows"] == 5 and [s["order"][1] for s in man["shards"]] == [0, 1]
+
+
+def test_export_single_file_matches_reference_layouts(tmp_path):
+    d = tmp_path / "idx"
+    w = IS.ShardedIndexWriter(d, dim=8)
+    a = _rows(6, 8, 3)
+    w.append(a[:2], ["x", "y"], ["tx", "ty"]); w.append(a[2:], list("abcd"), list("ABCD"))
+    obj = IS.export_single_file(d, tmp_path / "one.pt")
+    assert set(obj) == {"embeddings", "image_paths", "texts"} and torch.equal(obj["embeddings"], a)
+    obj2 = IS.export_single_file(d, tmp_path / "two.pt", plural_keys=False)
+    assert set(obj2) == {"embeddings", "image_path", "text"}      # scripts/build_text_index.py:69-73 spelling
+    back = torch.load(tmp_path / "two.pt", map_location="cpu")
+    assert back["text"] == ["tx", "ty", "A", "B", "C", "D"]
+
+
+def test_errors(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        IS.read_manifest(tmp_path / "missing")
+    w = IS.ShardedIndexWriter(tmp_path / "idx", dim=8)
+    with pytest.raises(ValueError):
+        w.append(_rows(2, 16, 1))
+    with pytest.raises(ValueError):
+        w.append(_rows(2, 8, 1), ["only-one"], None)
+    IS.ShardedIndexWriter(tmp_path / "idx", dim=8).append(_rows(1, 8, 1))
+    IS.ShardedIndexWriter(tmp_path / "idx", dim=4, order_major=1).append(_rows(1, 4, 1))
+    with pytest.raises(ValueError):
+        IS.write_manifest(tmp_path / "idx")        # mixed widths
+
+
+def test_empty_directory_and_empty_ranges(tmp_path):
+    (tmp_path / "idx").mkdir()
+    man = IS.read_manifest(tmp_path / "idx")
+    assert man["rows"] == 0 and man["shards"] == []
+    IS.ShardedIndexWriter(tmp_path / "idx", dim=8).append(_rows(3, 8, 1))
+    e, p, t = IS.load_rows(tmp_path / "idx", 3, 3)
+    assert e.shape == (0, 8) and p == [] and t == []
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _rank_writer(rank, world, port, d, n, dim, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = _rows(n, dim, 7)
+        lo, hi = shard_bounds(n, rank, world)
+        w = IS.ShardedIndexWriter(d, dim, order_major=rank)
+        mid = (lo + hi) // 2                      # two shards per rank, written without any collective
+        w.append(full[lo:mid], [f"img{i}" for i in range(lo, mid)], None)
+        w.append(full[mid:hi], [f"img{i}" for i in range(mid, hi)], None)
+        dist.barrier()
+        if rank == 0:
+            IS.write_manifest(d)
+        dist.barrier()
+        # every rank reloads ITS row block of the merged index: exactly the rows it would scan
+        man = IS.read_manifest(d)
+        e, paths, _ = IS.load_rows(d, lo, hi)
+        ret[rank] = bool(man["rows"] == n and torch.equal(e, full[lo:hi]) and paths[0] == f"img{lo}")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_data_parallel_build(tmp_path):
+    port, mgr = _free_port(), mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_rank_writer, args=(2, port, str(tmp_path / "idx"), 1001, 24, ret), nprocs=2, join=True)
+    assert all(ret.get(r) for r in range(2)), dict(ret)
+    man = json.loads((tmp_path / "idx" / "manifest.json").read_text())
+    assert [tuple(s["order"]) for s in man["shards"]] == [(0, 0), (0, 1), (1, 0), (1, 1)]
+    e, _, _ = IS.load_rows(tmp_path / "idx", 0, 1001)
+    assert torch.equal(e, _rows(1001, 24, 7))

@@ -121,3 +121,17 @@ def test_synth_captions_shape_and_framing():
     assert lengths.min() >= 3 and lengths.max() <= 77
     first_eos = (ids == O.EOS_ID).int().argmax(dim=-1)
     assert torch.equal(first_eos, lengths - 1)
+
+
+def test_fusion_oracle_matches_reference_seeker_service():
+    """oracle.fuse_query == the reference's SeekerService._build_query_embedding (bit for bit: same torch ops)."""
+    g = np.load(os.path.join(GOLD, "fusion_golden.npz"))
+    txt, img = torch.from_numpy(g["text"]), torch.from_numpy(g["image"])
+    for wi, (wt, wim) in enumerate(g["weights"].tolist()):
+        got = torch.stack([O.fuse_query(txt[i], img[i], wt, wim) for i in range(txt.shape[0])])
+        assert torch.equal(got, torch.from_numpy(g["both"][wi]))
+        assert torch.allclose(O.fuse_query(txt, img, wt, wim), torch.from_numpy(g["both"][wi]), atol=1e-7)
+    assert torch.equal(torch.stack([O.fuse_query(t, None) for t in txt]), torch.from_numpy(g["only_text"]))
+    assert torch.equal(torch.stack([O.fuse_query(None, t) for t in img]), torch.from_numpy(g["only_image"]))
+    with pytest.raises(ValueError, match=str(g["error"])):
+        O.fuse_query(None, None)

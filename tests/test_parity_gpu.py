@@ -280,3 +280,67 @@ def test_search_at_scale_properties(cuda_device, n, nq, k):
     ref_s, ref_i = torch.topk(sims, k, dim=-1)
     assert torch.allclose(s[sample], ref_s, atol=2e-6, rtol=1e-5)
     assert O.ids_match_with_ties(ref_s.cpu(), ref_i.cpu(), i[sample].cpu(), sims.cpu()), "(d) ids differ"
+
+
+# ------------------------------------------------------------------------------------------
+# next rows: seeker query fusion, sharded index build + resident service
+# ------------------------------------------------------------------------------------------
+def test_query_fusion_matches_reference_golden(cuda_device):
+    """clm_fuse_normalize vs the reference's own SeekerService._build_query_embedding outputs."""
+    from clip_lora_match_b200.src.embedding.seeker_service import fuse_queries
+
+    g = np.load(os.path.join(GOLD, "fusion_golden.npz"))
+    txt, img = torch.from_numpy(g["text"]), torch.from_numpy(g["image"])
+    for wi, (wt, wim) in enumerate(g["weights"].tolist()):
+        got = fuse_queries(txt, img, wt, wim, cuda_device).cpu()
+        assert torch.allclose(got, torch.from_numpy(g["both"][wi]), atol=2e-7, rtol=0)
+    assert torch.allclose(fuse_queries(txt, None, device=cuda_device).cpu(), torch.from_numpy(g["only_text"]), atol=2e-7)
+    assert torch.allclose(fuse_queries(None, img, device=cuda_device).cpu(), torch.from_numpy(g["only_image"]), atol=2e-7)
+    assert fuse_queries(txt[0], img[0], device=cuda_device).shape == (1, 64)       # (d,) inputs
+    with pytest.raises(ValueError, match=str(g["error"])):
+        fuse_queries(None, None, device=cuda_device)
+    # empty batch and full-size rows
+    assert fuse_queries(torch.empty((0, 768)), None, device=cuda_device).shape == (0, 768)
+    big_t, big_i = O.synth_unit_rows(4096, 768, 21), O.synth_unit_rows(4096, 768, 22)
+    got = fuse_queries(big_t, big_i, 0.5, 0.5, cuda_device).cpu()
+    assert torch.allclose(got, O.fuse_query(big_t, big_i), atol=2e-7)
+
+
+def test_sharded_image_index_build_then_resident_seeker_search(cuda_device, tmp_path):
+    """configs[2]/[4] in miniature: data-parallel-style image index build into shards (two 'ranks'
+    written one after the other), reopened from the directory, searched through the resident
+    SeekerService with fused text+image queries; everything checked against the oracle."""
+    from clip_lora_match_b200.scripts.build_image_index import build_image_index
+    from clip_lora_match_b200.src.embedding import index_store as IS
+    from clip_lora_match_b200.src.embedding.search import TextSearchIndex, shard_bounds
+    from clip_lora_match_b200.src.embedding.seeker_service import SeekerService
+
+    model = O.build_model("tiny-test", seed=0)
+    gpu = _b200_model("tiny-test", model, {}, 8, 16, (), cuda_device)
+    n = 53
+    pv = O.synth_images(n, seed=2)
+    ref = O.encode_images(model, pv)
+    d = tmp_path / "idx"
+    for rank in range(2):
+        lo, hi = shard_bounds(n, rank, 2)
+        batches = ((pv[i:min(i + 8, hi)], [f"img{j}.png" for j in range(i, min(i + 8, hi))],
+                    [f"item {j}" for j in range(i, min(i + 8, hi))]) for i in range(lo, hi, 8))
+        assert build_image_index(batches, d, gpu, rank=rank, rows_per_shard=16, log=lambda m: None) == hi - lo
+    man = IS.write_manifest(d)
+    assert man["rows"] == n and man["dim"] == 64 and len(man["shards"]) >= 4
+    emb, paths, texts = IS.load_rows(d, 0, n)
+    _assert_parity("sharded_index_rows", emb, ref)
+    assert paths[37] == "img37.png" and texts[52] == "item 52"
+
+    idx = TextSearchIndex.from_directory(d, device=cuda_device, verbose=False)
+    assert idx.num_items == n and idx.image_paths[5] == "img5.png"
+    svc = SeekerService(model=gpu, processor=None, device=cuda_device, index=idx)
+    txt_q, img_q = O.synth_unit_rows(7, 64, 31), ref[:7]
+    s, i = svc.search_batch(txt_q, img_q, top_k=5, w_text=0.2, w_image=0.8)
+    fused = O.fuse_query(txt_q, img_q, 0.2, 0.8)
+    ref_s, ref_i = O.search_topk(emb, fused, 5)
+    assert torch.allclose(s.cpu(), ref_s, atol=3e-6)
+    assert O.ids_match_with_ties(ref_s, ref_i, i.cpu(), fused @ O.normalize_rows(emb).T)
+    res = idx.search_with_embedding(fused[3], top_k=3)    # reference-style single query: metadata by global row
+    top = int(ref_i[3, 0])
+    assert res[0].index == top and res[0].image_path == f"img{top}.png" and res[0].text == f"item {top}"

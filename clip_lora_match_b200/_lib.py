@@ -40,6 +40,10 @@ _TOWER_FIELDS = [
 ]
 
 
+class ImageDesc(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("height", C.c_int32), ("width", C.c_int32), ("row_stride_bytes", C.c_int32)]
+
+
 class LayerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _LAYER_FIELDS]
 
@@ -59,6 +63,8 @@ SIGNATURES = {
     "clm_device_check": (_I, []),
     "clm_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "clm_fuse_normalize": (_I, [_P, _F, _P, _F, _P, _P, _I, _I, _P]),
+    "clm_preprocess_workspace_bytes": (C.c_size_t, [_P, _I, _I]),
+    "clm_preprocess_images": (_I, [_P, _I, _I, _P, _P, _P, _P, C.c_size_t, _P]),
     "clm_l2norm": (_I, [_P, _P, _P, _I, _I, _P]),
     "clm_embed_text": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "clm_patch_im2col": (_I, [_P, _P, _I, _I, _I, _I, _P]),

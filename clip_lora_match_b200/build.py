@@ -18,6 +18,7 @@ LIB_PATH = CSRC / "libclm_b200.so"
 SOURCES = [
     "clm_api.cu",
     "clm_elementwise.cu",
+    "clm_preprocess.cu",
     "clm_gemm.cu",
     "clm_attention.cu",
     "clm_search.cu",

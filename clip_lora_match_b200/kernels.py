@@ -58,6 +58,38 @@ def fuse_normalize(a: torch.Tensor, wa: float = 1.0, b: Optional[torch.Tensor] =
     return (y, yb) if want_bf16 else y
 
 
+def preprocess_images(images, out_size: int = 224,
+                      mean=(0.48145466, 0.4578275, 0.40821073), std=(0.26862954, 0.26130258, 0.27577711),
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decoded RGB images (list of uint8 CUDA tensors [H, W, 3], any sizes) -> pixel_values fp32
+    [B, 3, S, S]: Pillow-exact bicubic shortest-edge resize, centre crop, 1/255, (x-mean)/std."""
+    import ctypes as C
+
+    lib = _lib.load()
+    b = len(images)
+    dev = images[0].device if b else torch.device("cuda")
+    if out is None:
+        out = torch.empty((b, 3, out_size, out_size), dtype=torch.float32, device=dev)
+    if b == 0:
+        return out
+    descs = (_lib.ImageDesc * b)()
+    for i, im in enumerate(images):
+        if not im.is_cuda or im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3 or im.stride(2) != 1 \
+                or im.stride(1) != 3:
+            raise ValueError(f"image {i} must be a uint8 CUDA tensor [H, W, 3] with packed pixels, got "
+                             f"{tuple(im.shape)} {im.dtype} strides {im.stride()}")
+        descs[i].data, descs[i].height, descs[i].width = im.data_ptr(), im.shape[0], im.shape[1]
+        descs[i].row_stride_bytes = im.stride(0)
+    need = lib.clm_preprocess_workspace_bytes(descs, b, out_size)
+    if need == 0:
+        raise ValueError("clm_preprocess_workspace_bytes rejected the image descriptors")
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    mean_a, std_a = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    check(lib.clm_preprocess_images(descs, b, out_size, mean_a, std_a, ptr(out), ptr(ws), need, cur_stream()),
+          "clm_preprocess_images")
+    return out
+
+
 def gemm_epi(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
              residual: Optional[torch.Tensor] = None, act: int = EPI_NONE,
              out_dtype: torch.dtype = torch.bfloat16, a2: Optional[torch.Tensor] = None,

@@ -434,6 +434,34 @@ class ClmProcessor:
             print(f"[clip_model] no CLIP BPE vocabulary on disk for '{name}': using the hashed "
                   f"FallbackTokenizer (shapes only; see DESIGN.md)")
 
+    def preprocess_images_gpu(self, images, device: Union[str, torch.device] = "cuda") -> torch.Tensor:
+        """The same pixel_values as processor(images=...) but resized / cropped / normalised on the
+        GPU (clm_preprocess_images): the decoded uint8 pixels travel over PCIe in ONE packed copy and
+        the host never resamples.  `images`: PIL images or uint8 numpy HWC arrays, any sizes."""
+        import numpy as np
+
+        from .. import kernels as K
+
+        ip = self.image_processor
+        size = ip.size["shortest_edge"] if "shortest_edge" in ip.size else ip.size["height"]
+        arrs = []
+        for im in (images if isinstance(images, (list, tuple)) else [images]):
+            a = np.asarray(im.convert("RGB")) if hasattr(im, "convert") else np.asarray(im)
+            if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+                raise ValueError(f"images must be RGB uint8 [H, W, 3], got {a.shape} {a.dtype}")
+            arrs.append(np.ascontiguousarray(a))
+        offs, total = [], 0
+        for a in arrs:
+            offs.append(total)
+            total += (a.size + 255) // 256 * 256
+        host = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
+        hv = host.numpy()
+        for a, o in zip(arrs, offs):
+            hv[o:o + a.size] = a.reshape(-1)
+        devbuf = host.to(device, non_blocking=True)
+        views = [devbuf[o:o + a.size].view(a.shape[0], a.shape[1], 3) for a, o in zip(arrs, offs)]
+        return K.preprocess_images(views, out_size=size, mean=tuple(ip.image_mean), std=tuple(ip.image_std))
+
     def __call__(self, text=None, images=None, return_tensors="pt", padding=True, truncation=True, **kw):
         out = {}
         if text is not None:

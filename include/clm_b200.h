@@ -91,6 +91,21 @@ int clm_pool_ln(const float* h, const int32_t* row_idx_or_null, const float* gam
                 const float* beta, void* y_bf16, int batch, int tokens, int dim, float eps,
                 void* stream);
 
+/* CLIP image preprocessing on the GPU: decoded uint8 RGB (HWC) images of any size ->
+ * pixel_values fp32 [batch, 3, S, S].  Replaces processor(images=...) of models/clip_model.py:105-107
+ * (resize shortest edge to S with Pillow's antialiased bicubic — bit exact on the uint8 stage —
+ * centre crop S x S, rescale 1/255, (x - mean) / std; config/clip_config.yaml:7-14).
+ * descs_host is a HOST array; .data are DEVICE pointers; the workspace is caller-owned device memory. */
+typedef struct {
+  const uint8_t* data;      /* device pointer, RGB interleaved */
+  int32_t height, width;
+  int32_t row_stride_bytes; /* >= 3 * width */
+} clm_image_desc;
+size_t clm_preprocess_workspace_bytes(const clm_image_desc* descs_host, int batch, int out_size);
+int clm_preprocess_images(const clm_image_desc* descs_host, int batch, int out_size,
+                          const float* mean3_host, const float* std3_host, float* pixel_values,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * tcgen05 / TMEM GEMM fed by TMA, with fused epilogue
  * ---------------------------------------------------------------------------------- */

@@ -344,3 +344,46 @@ def test_sharded_image_index_build_then_resident_seeker_search(cuda_device, tmp_
     res = idx.search_with_embedding(fused[3], top_k=3)    # reference-style single query: metadata by global row
     top = int(ref_i[3, 0])
     assert res[0].index == top and res[0].image_path == f"img{top}.png" and res[0].text == f"item {top}"
+
+
+def test_gpu_preprocessing_is_bit_exact_with_the_pillow_oracle(cuda_device):
+    """clm_preprocess_images vs oracle/pil_resample.c (itself pinned bit-exact against Pillow): the
+    uint8 stage and the float stage must agree to the bit, for a ragged batch of image sizes
+    (down- and up-scaling, portrait / landscape / square, extreme aspect ratios)."""
+    from clip_lora_match_b200 import kernels as K
+    from oracle.preprocess_oracle import clip_preprocess as oracle_preprocess
+
+    sizes = [(300, 260), (260, 300), (224, 224), (225, 224), (1080, 1920), (768, 1024), (100, 80), (50, 333),
+             (480, 640), (223, 500), (641, 479), (1536, 2048)]
+    rs = np.random.RandomState(11)
+    arrs = [rs.randint(0, 256, size=(h, w, 3), dtype=np.uint8) for h, w in sizes]
+    smooth = (np.add.outer(np.arange(500), np.arange(700))[..., None] * np.array([1, 2, 3]) % 256).astype(np.uint8)
+    arrs.append(np.ascontiguousarray(smooth))
+    got = K.preprocess_images([torch.from_numpy(a).to(cuda_device) for a in arrs]).cpu().numpy()
+    for i, a in enumerate(arrs):
+        ref, _ = oracle_preprocess(a)
+        assert np.array_equal(got[i], ref), f"image {i} {a.shape}: {np.abs(got[i] - ref).max()} max diff, " \
+                                            f"{(got[i] != ref).sum()} elements"
+    assert K.preprocess_images([]).shape == (0, 3, 224, 224)
+    with pytest.raises(ValueError):
+        K.preprocess_images([torch.zeros((10, 10, 4), dtype=torch.uint8, device=cuda_device)])
+
+
+def test_gpu_preprocessing_through_the_processor_feeds_the_encoder(cuda_device):
+    """ClmProcessor.preprocess_images_gpu -> encode_images == host CLIPImageProcessor -> encode_images
+    within the encoder tolerance (the two resamplers may differ by one uint8 level on some pixels)."""
+    from PIL import Image
+
+    from clip_lora_match_b200.models import clip_model as CM
+
+    model = O.build_model("tiny-test", seed=0)
+    gpu = _b200_model("tiny-test", model, {}, 8, 16, (), cuda_device)
+    proc = CM.ClmProcessor("openai/clip-vit-base-patch32")
+    rs = np.random.RandomState(5)
+    imgs = [Image.fromarray(rs.randint(0, 256, size=(h, w, 3), dtype=np.uint8), "RGB")
+            for h, w in [(300, 260), (240, 320), (224, 224), (500, 375)]]
+    pv_gpu = proc.preprocess_images_gpu(imgs, cuda_device)
+    pv_host = proc(images=imgs, return_tensors="pt")["pixel_values"]
+    one_level = (1 / 255) / 0.26130258
+    assert (pv_gpu.cpu() - pv_host).abs().max() <= one_level * 1.001
+    _assert_parity("gpu_preprocess_embeddings", gpu.encode_images(pv_gpu).cpu(), O.encode_images(model, pv_host))

@@ -38,6 +38,7 @@ constexpr int kMaxStages = 6;
 
 struct AttnParams {
   int T, H, Tp, mtiles, num_items, stages, stage_bytes, nslots;
+  int blocks, nb0, nb1;  // key blocks per tile (2 = online softmax over two blocks of nb0 / nb1 keys)
   // TMEM column of the S / P region and of the O accumulator used by tiles of parity 0 / 1;
   // o_alias: O lives inside the same parity's S region (dead by then), so S(t+2) waits for the drain
   int s_col0, s_col1, o_col0, o_col1, o_alias0, o_alias1;
@@ -79,6 +80,18 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
         "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
         "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() {
@@ -264,7 +277,71 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       }
       __syncwarp();
     };
-    if (p.nslots == 2) {
+    if (p.blocks == 2) {
+      // Two key blocks per tile (T > 224: the whole score row does not fit twice in TMEM).  Per stream:
+      //   S0 -> [softmax blk 0] -> PV0 (O = P0 V0), S1 -> [softmax blk 1 + rescale of O] -> PV1 (O += P1 V1)
+      // Every barrier of a stream completes twice per tile, so block 0 always waits parity 0, block 1 parity 1.
+      auto mma_s = [&](const Cursor& c, int key0, int nk) {
+        if (lane == 0) {
+          const uint32_t q_addr = smem_u32(smem + c.st * p.stage_bytes);
+          const uint32_t k_addr = q_addr + kv_bytes + static_cast<uint32_t>(key0) * 128u;
+          const uint32_t sbase = tmem + static_cast<uint32_t>(p.s_col(c.t & 1));
+          const uint32_t idesc = umma_idesc_bf16(128, nk, 0, 0);
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k)
+            umma_bf16_ss(sbase, umma_desc_sw128(q_addr + c.mt * 16384 + k * 32, 1024),
+                         umma_desc_sw128(k_addr + k * 32, 1024), idesc, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[c.t & 1]);
+        }
+        __syncwarp();
+      };
+      auto mma_pv = [&](const Cursor& c, int key0, int nk, bool first, bool release) {
+        if (lane == 0) {
+          const int b = c.t & 1;
+          const uint32_t v_addr = smem_u32(smem + c.st * p.stage_bytes) + 2 * kv_bytes + static_cast<uint32_t>(key0) * 128u;
+          const uint32_t pbase = tmem + static_cast<uint32_t>(p.s_col(b));
+          const uint32_t obase = tmem + static_cast<uint32_t>(p.o_col(b));
+          for (int ks = 0; ks < nk / 16; ++ks)
+            umma_bf16_ts(obase, pbase + ks * 8, umma_desc_sw128_mn(v_addr + ks * 2048), idesc_pv,
+                         (!first || ks != 0) ? 1u : 0u);
+          umma_commit(&o_full[b]);
+          if (release) umma_commit(&stage_empty[c.st]);
+        }
+        __syncwarp();
+      };
+      Cursor cur[2];
+      int step[2] = {0, 0};  // 0: S0 pending, 1: PV0 + S1 pending, 2: PV1 pending
+      cur[0].init(0, p); cur[1].init(1, p);
+      while (cur[0].t < n_tiles || cur[1].t < n_tiles) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          if (cur[b].t >= n_tiles) continue;
+          if (step[b] == 0) {
+            if (mbar_try_wait(&stage_full[cur[b].st], cur[b].ph)) {
+              tc_fence_after();
+              mma_s(cur[b], 0, p.nb0);
+              step[b] = 1;
+            }
+          } else if (step[b] == 1) {
+            if (mbar_try_wait(&p_full[b], 0)) {
+              tc_fence_after();
+              mma_pv(cur[b], 0, p.nb0, true, false);
+              mma_s(cur[b], p.nb0, p.nb1);
+              step[b] = 2;
+            }
+          } else {
+            if (mbar_try_wait(&p_full[b], 1)) {
+              tc_fence_after();
+              const bool last = (++pv_cnt[cur[b].st] == p.mtiles);
+              if (last) pv_cnt[cur[b].st] = 0;
+              mma_pv(cur[b], p.nb0, p.nb1, false, last);
+              cur[b].advance(2, p);
+              step[b] = 0;
+            }
+          }
+        }
+      }
+    } else if (p.nslots == 2) {
       Cursor sc[2], pc[2];  // next S / next PV of each stream
       sc[0].init(0, p); sc[1].init(1, p); pc[0].init(0, p); pc[1].init(1, p);
       while (pc[0].t < n_tiles || pc[1].t < n_tiles) {
@@ -334,6 +411,103 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
     float* other_sum = xsum + (g * 2 + (hf ^ 1)) * 128 + r;
     const int pair_bar = 1 + g * 4 + q;  // named barrier of the two warps that share these 32 rows
     int t = 0;
+    if (p.blocks == 2) {
+      // ---- online softmax over two key blocks (see the MMA warp).  m_run / l_part are the running row
+      // max and this thread's share of the row sum (in units of 2^(-m_run*c)).
+      for (int it = blockIdx.x; it < p.num_items; it += gridDim.x)
+      for (int mt = 0; mt < p.mtiles; ++mt, ++t) {
+        if ((t & 1) != g) continue;
+        const int b = it / H, h = it - b * H;
+        const int qi = mt * 128 + r;
+        const bool warp_live = mt * 128 + q * 32 < T;
+        int valid = T;
+        if (kCausal) valid = (qi + 1 < T) ? qi + 1 : T;
+        float m_run = -INFINITY, l_part = 0.f;
+        uint32_t v[32];
+#pragma unroll 1
+        for (int blk = 0; blk < 2; ++blk) {
+          const int key0 = blk ? p.nb0 : 0, nk = blk ? p.nb1 : p.nb0;
+          const int nchb = (nk + 31) / 32;
+          int vb = valid - key0;  // valid keys of this block for this row
+          vb = vb < 0 ? 0 : (vb > nk ? nk : vb);
+          const int niter = (nchb + 1) >> 1;
+          mbar_wait(&s_full[g], static_cast<uint32_t>(blk));
+          tc_fence_after();
+          float mx = -INFINITY;
+          if (warp_live) {
+            for (int c = hf; c < nchb; c += 2) {
+              tmem_ld_32x32b_x32(srow + c * 32, v);
+              tmem_ld_wait();
+              mx = (c * 32 + 32 <= vb) ? chunk_max(v, mx) : chunk_max_masked(v, mx, c * 32, vb);
+            }
+          }
+          *my_max = mx;
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          mx = fmaxf(mx, *other_max);
+          const float m_new = fmaxf(m_run, mx);
+          if (blk == 1) {
+            // O = P0 V0 was accumulated relative to m_run: bring it (and l) to the new maximum
+            const float alpha = fast_exp2((m_run - m_new) * kScaleLog2e);
+            mbar_wait(&o_full[g], 0);
+            tc_fence_after();
+            if (warp_live && __any_sync(0xffffffffu, alpha != 1.0f)) {
+              tmem_ld_32x32b_x32(orow, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st_32x32b_x32(orow, v);
+              tmem_st_wait();
+            }
+            l_part *= alpha;
+          }
+          m_run = m_new;
+          float sum = 0.f;
+          if (warp_live) {
+            const float neg_mx = -m_run * kScaleLog2e;
+            uint32_t pk[16];
+            for (int i = 0; i < niter; ++i) {
+              const int c = 2 * i + hf;
+              if (c < nchb) {
+                tmem_ld_32x32b_x32(srow + c * 32, v);
+                tmem_ld_wait();
+                sum += (c * 32 + 32 <= vb) ? chunk_exp<false>(v, pk, kScaleLog2e, neg_mx, c * 32, vb)
+                                           : chunk_exp<true>(v, pk, kScaleLog2e, neg_mx, c * 32, vb);
+              }
+              tc_fence_before();
+              asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+              tc_fence_after();
+              if (c < nchb) tmem_st_32x32b_x16(srow + c * 16, pk);
+            }
+            tmem_st_wait();
+          }
+          l_part += sum;
+          if (blk == 1) *my_sum = l_part;
+          tc_fence_before();
+          mbar_arrive(&p_full[g]);
+        }
+        mbar_wait(&o_full[g], 1);
+        tc_fence_after();
+        const float total = l_part + *other_sum;
+        if (warp_live) {
+          tmem_ld_32x32b_x32(orow, v);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        if (warp_live && qi < T) {
+          const float inv = 1.0f / total;
+          uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(b * T + qi) * D + h * kHeadDim + hf * 32);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[8 * jj + 0]) * inv, __uint_as_float(v[8 * jj + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(v[8 * jj + 2]) * inv, __uint_as_float(v[8 * jj + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(v[8 * jj + 4]) * inv, __uint_as_float(v[8 * jj + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(v[8 * jj + 6]) * inv, __uint_as_float(v[8 * jj + 7]) * inv);
+            o4[jj] = o;
+          }
+        }
+      }
+    } else
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x)
     for (int mt = 0; mt < p.mtiles; ++mt, ++t) {
       if ((t & 1) != g) continue;
@@ -460,7 +634,9 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   // chunks); P (bf16x2) reuses its first Tp/2; O needs 64.  Tiles alternate between two parities:
   //   two S regions + two O regions            (T <= 192)
   //   two S regions, O0 separate, O1 inside S1 (T <= 224: ViT-B/16's 197) -> S(t+2) of odd t waits
-  //   one S region, two O regions              (T <= 384: ViT-L/14's 257)
+  //   two key blocks per tile, two S regions of one block + two O regions (T <= 384: ViT-L/14's 257)
+//   [fallback: one S region, two O regions, tiles strictly in sequence]
+  p.blocks = 1; p.nb0 = p.Tp; p.nb1 = 0;
   const int s_cols = (p.Tp + 31) / 32 * 32;
   const int o_in = (p.Tp / 2 + 31) / 32 * 32;  // first column past P inside an S region
   if (2 * s_cols + 128 <= 512 && stages >= 2) {
@@ -474,11 +650,28 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
     p.o_col0 = 2 * s_cols; p.o_col1 = s_cols + o_in;
     p.o_alias0 = 0; p.o_alias1 = 1;
   } else {
-    CLM_REQUIRE(s_cols + 128 <= 512, "clm_attention: tokens=%d needs %d TMEM columns", T, s_cols + 128);
-    p.nslots = 1;
-    p.s_col0 = 0; p.s_col1 = 0;
-    p.o_col0 = s_cols; p.o_col1 = s_cols + 64;
-    p.o_alias0 = 0; p.o_alias1 = 0;
+    // the score row does not fit twice: two key blocks per tile with an online-softmax rescale of O,
+    // so that two S regions (one per stream) fit again.  CLM_ATTN_BLOCKS=1 keeps the one-region plan.
+    static int one_block = -1;
+    if (one_block < 0) {
+      const char* e = getenv("CLM_ATTN_BLOCKS");
+      one_block = (e && e[0] == '1') ? 1 : 0;
+    }
+    const int nb0 = (p.Tp / 2 + 15) / 16 * 16, nb1 = p.Tp - nb0;
+    const int b_cols = (nb0 + 31) / 32 * 32;
+    if (!one_block && !causal && stages >= 2 && nb1 >= 16 && 2 * b_cols + 128 <= 512) {
+      p.blocks = 2; p.nb0 = nb0; p.nb1 = nb1;
+      p.nslots = 2;
+      p.s_col0 = 0; p.s_col1 = b_cols;
+      p.o_col0 = 2 * b_cols; p.o_col1 = 2 * b_cols + 64;
+      p.o_alias0 = 0; p.o_alias1 = 0;
+    } else {
+      CLM_REQUIRE(s_cols + 128 <= 512, "clm_attention: tokens=%d needs %d TMEM columns", T, s_cols + 128);
+      p.nslots = 1;
+      p.s_col0 = 0; p.s_col1 = 0;
+      p.o_col0 = s_cols; p.o_col1 = s_cols + 64;
+      p.o_alias0 = 0; p.o_alias1 = 0;
+    }
   }
   const int smem_bytes = stages * stage_bytes + 256 + kXchBytes + 1024;
 

@@ -108,6 +108,33 @@ int clm_make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uin
   return clm_make_tmap_2d(map, base, rows, cols, ld, 2, box_cols, box_rows);
 }
 
+// bf16 [d2][d1][d0] with byte strides of dims 1 and 2; box {box0 (64 = one 128-byte swizzled row), box1, 1}
+int clm_make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                          uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    clm_set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return CLM_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || stride1_bytes % 16 != 0 || stride2_bytes % 16 != 0 ||
+      box0 * 2 != 128) {
+    clm_set_error("3-D TMA operand: 16-byte alignment / pitch and a 64-element box are required");
+    return CLM_ERR_INVALID;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    clm_set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+    return CLM_ERR_CUDA;
+  }
+  return CLM_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // launch accounting / event profiler
 // ---------------------------------------------------------------------------------------

@@ -32,12 +32,28 @@ namespace {
 using namespace clm;
 
 constexpr int kThreads = 576;  // TMA warp + MMA warp + 16 softmax warps
+constexpr int kOutStageBytes = 8 * 4096;  // per (group, lane quarter): a 32-row x 128-byte output slab for the TMA store
 constexpr int kXchBytes = 4096;   // row max / row sum exchanged between the two threads of a query row
 constexpr int kHeadDim = 64;
 constexpr int kMaxStages = 6;
 
+// Optional timeline tracing (compile with -DCLM_ATTN_TRACE; tools/attn_trace.py): lane 0 of every warp of
+// CTA 0 stamps clock64() at the hand-off points of its first tiles.
+#ifdef CLM_ATTN_TRACE
+__device__ unsigned long long* g_trace = nullptr;
+constexpr int kTraceTiles = 12, kTraceEvents = 8;
+#define TRACE(tile_seq, ev)                                                                        \
+  do {                                                                                             \
+    if (g_trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile_seq) < kTraceTiles)         \
+      g_trace[((threadIdx.x >> 5) * kTraceTiles + (tile_seq)) * kTraceEvents + (ev)] = clock64();  \
+  } while (0)
+#else
+#define TRACE(tile_seq, ev) do {} while (0)
+#endif
+
 struct AttnParams {
   int T, H, Tp, mtiles, num_items, stages, stage_bytes, nslots;
+  int stage_out;  // output rows leave through shared memory + TMA tile stores (needs kOutStageBytes)
   int blocks, nb0, nb1;  // key blocks per tile (2 = online softmax over two blocks of nb0 / nb1 keys)
   // TMEM column of the S / P region and of the O accumulator used by tiles of parity 0 / 1;
   // o_alias: O lives inside the same parity's S region (dead by then), so S(t+2) waits for the drain
@@ -144,11 +160,12 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&p
 template <bool kCausal>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CUtensorMap map16,
-                 __nv_bfloat16* __restrict__ out, AttnParams p) {
+                 const __grid_constant__ CUtensorMap map_out, __nv_bfloat16* __restrict__ out, AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  uint8_t* ostage = smem + p.stages * p.stage_bytes;  // 1024-byte aligned (stage_bytes is a multiple of 6144)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + (p.stage_out ? kOutStageBytes : 0));
   uint64_t* stage_full = bars;                     // [kMaxStages]
   uint64_t* stage_empty = bars + kMaxStages;       // [kMaxStages]
   uint64_t* s_full = bars + 2 * kMaxStages;        // [2] S ready (MMA commit), by tile parity
@@ -350,6 +367,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
           // PV(t): S(t) has been issued and the group has published P(t)
           if (pc[b].t < sc[b].t && mbar_try_wait(&p_full[b], static_cast<uint32_t>((pc[b].t >> 1) & 1))) {
             tc_fence_after();
+            TRACE(pc[b].t, 1);
             do_pv(pc[b]);
             pc[b].advance(2, p);
           }
@@ -362,6 +380,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
             if (ok) ok = mbar_try_wait(&stage_full[sc[b].st], sc[b].ph);
             if (ok) {
               tc_fence_after();
+              TRACE(sc[b].t, 0);
               do_s(sc[b]);
               sc[b].advance(2, p);
             }
@@ -526,8 +545,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       // the two threads of a row take alternate chunks: thread hf owns chunks 2i + hf
       const int niter = (nch + 1) >> 1;
 
+      TRACE(t, 0);
       mbar_wait(&s_full[g], par);
       tc_fence_after();
+      TRACE(t, 1);
       uint32_t v[32];
       // ---- pass 1: max over this thread's chunks, then the row max
       float mx = -INFINITY;
@@ -538,9 +559,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
           mx = (c * 32 + 32 <= valid) ? chunk_max(v, mx) : chunk_max_masked(v, mx, c * 32, valid);
         }
       }
+      TRACE(t, 2);
       *my_max = mx;
+      if (p.stage_out && hf == 0 && lane == 0) bulk_wait_read<0>();  // the previous tile's slab has left smem
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
       mx = fmaxf(mx, *other_max);
+      TRACE(t, 3);
       // ---- pass 2: p = 2^(s*c - max*c), partial row sum, P (bf16x2) written over S.  P(c) lands in the
       // columns of S chunk c/2, so the pair synchronises once per iteration: by then both threads hold
       // every chunk up to 2i+1 in registers and the columns of chunk i are dead.
@@ -570,18 +594,43 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       }
       *my_sum = sum;
       tc_fence_before();
+      TRACE(t, 4);
       mbar_arrive(&p_full[g]);
 
       mbar_wait(&o_full[g], par);
       tc_fence_after();
+      TRACE(t, 5);
       sum += *other_sum;  // published before the partner's p_full arrive, which o_full transitively follows
       if (warp_live) {
         tmem_ld_32x32b_x32(orow, v);
         tmem_ld_wait();
       }
       tc_fence_before();
+      TRACE(t, 6);
       mbar_arrive(&slot_free[g]);  // this half of O(t) is in registers: its columns may be overwritten
-      if (warp_live && qi < T) {
+      if (p.stage_out) {
+        // A thread owns 64 bytes of one output row; writing them straight to global memory costs 32
+        // scattered 16-byte transactions per warp instruction (measured: ~1.7k clocks per tile).  The
+        // two warps of a row quarter assemble their 32 x 128-byte slab in shared memory (SWIZZLE_128B
+        // pattern of the output map) and one lane hands it to the TMA unit; rows >= T are clipped.
+        const uint32_t ost = smem_u32(ostage + (g * 4 + q) * 4096);
+        if (warp_live) {
+          const float inv = 1.0f / sum;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            st_shared_v4(ost + static_cast<uint32_t>(lane) * 128u + ((static_cast<uint32_t>(hf * 4 + jj) ^ (lane & 7)) << 4),
+                         pack_bf16x2(__uint_as_float(v[8 * jj + 0]) * inv, __uint_as_float(v[8 * jj + 1]) * inv),
+                         pack_bf16x2(__uint_as_float(v[8 * jj + 2]) * inv, __uint_as_float(v[8 * jj + 3]) * inv),
+                         pack_bf16x2(__uint_as_float(v[8 * jj + 4]) * inv, __uint_as_float(v[8 * jj + 5]) * inv),
+                         pack_bf16x2(__uint_as_float(v[8 * jj + 6]) * inv, __uint_as_float(v[8 * jj + 7]) * inv));
+          fence_proxy_async_smem();
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        if (warp_live && hf == 0 && lane == 0) {
+          tma_store_3d(&map_out, ost, h * kHeadDim, mt * 128 + q * 32, b);
+          bulk_commit();
+        }
+      } else if (warp_live && qi < T) {
         const float inv = 1.0f / sum;
         uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(b * T + qi) * D + h * kHeadDim + hf * 32);
 #pragma unroll
@@ -595,6 +644,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
         }
       }
     }
+    if (p.stage_out && hf == 0 && lane == 0) bulk_wait<0>();  // every slab of this warp pair has reached memory
   }
 
   tc_fence_before();
@@ -624,7 +674,10 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   int stage_bytes = 3 * p.Tp * 128;
   if (stage_bytes < p.mtiles * 16384) stage_bytes = p.mtiles * 16384;
   p.stage_bytes = stage_bytes;
-  const int smem_budget = 227 * 1024 - 1024 - 256 - kXchBytes;
+  // output staging for the TMA stores if two pipeline stages still fit beside it (not at T = 257)
+  int smem_budget = 227 * 1024 - 1024 - 256 - kXchBytes;
+  p.stage_out = ((smem_budget - kOutStageBytes) / stage_bytes >= 2) ? 1 : 0;
+  if (p.stage_out) smem_budget -= kOutStageBytes;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   CLM_REQUIRE(stages >= 1, "clm_attention: tokens=%d needs %d bytes of shared memory per stage", T,
@@ -673,7 +726,8 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
       p.o_alias0 = 0; p.o_alias1 = 0;
     }
   }
-  const int smem_bytes = stages * stage_bytes + 256 + kXchBytes + 1024;
+  if (p.blocks == 2) p.stage_out = 0;  // the two-block path (T > 224) keeps per-thread stores
+  const int smem_bytes = stages * stage_bytes + (p.stage_out ? kOutStageBytes : 0) + 256 + kXchBytes + 1024;
 
   CUtensorMap map64, map16;
   int rc = clm_make_tmap_bf16_2d(&map64, qkv, static_cast<uint64_t>(batch) * T, 3ull * D, 3ull * D,
@@ -682,6 +736,12 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   rc = clm_make_tmap_bf16_2d(&map16, qkv, static_cast<uint64_t>(batch) * T, 3ull * D, 3ull * D,
                              kHeadDim, 16);
   if (rc) return rc;
+  CUtensorMap map_out = map64;
+  if (p.stage_out) {
+    rc = clm_make_tmap_bf16_3d(&map_out, out, static_cast<uint64_t>(D), static_cast<uint64_t>(T),
+                               static_cast<uint64_t>(batch), 2ull * D, 2ull * D * T, kHeadDim, 32);
+    if (rc) return rc;
+  }
   const int grid = p.num_items < clm_num_sms() ? p.num_items : clm_num_sms();
   // algorithmic work: QK^T and PV at the true T (causal not discounted)
   ProfScope prof(CLM_K_ATTENTION, 4.0 * batch * heads * static_cast<double>(T) * T * kHeadDim,
@@ -690,16 +750,24 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
     CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attention_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(
-        map64, map16, static_cast<__nv_bfloat16*>(out), p);
+        map64, map16, map_out, static_cast<__nv_bfloat16*>(out), p);
   } else {
     CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attention_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(
-        map64, map16, static_cast<__nv_bfloat16*>(out), p);
+        map64, map16, map_out, static_cast<__nv_bfloat16*>(out), p);
   }
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
 }
+
+#ifdef CLM_ATTN_TRACE
+extern "C" int clm_attention_set_trace(void* dev_buf) {
+  unsigned long long* ptr = static_cast<unsigned long long*>(dev_buf);
+  CLM_CUDA_CHECK(cudaMemcpyToSymbol(g_trace, &ptr, sizeof(ptr)));
+  return CLM_OK;
+}
+#endif
 
 extern "C" int clm_attention(const void* qkv_bf16, void* out_bf16, int batch, int tokens, int heads,
                              int causal, void* stream) {

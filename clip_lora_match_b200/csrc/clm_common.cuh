@@ -47,6 +47,9 @@ int clm_make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uin
 int clm_make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                      int elem_bytes, uint32_t box_cols, uint32_t box_rows);
 
+int clm_make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                          uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
+
 int clm_num_sms();
 
 // Launch accounting + optional per-launch CUDA-event timing (bench.py's roofline numbers).
@@ -109,6 +112,21 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+// Non-blocking probe (try_wait may suspend the thread up to a system time limit while the phase is
+// pending, which is wrong for a loop that polls several barriers): true once the phase has completed.
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -151,6 +169,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sm
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                :
                : "l"(map), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 // global[tile] += smem[tile], performed by the L2 (fp32 add for a FLOAT32 tensor map)

@@ -203,6 +203,11 @@ def _attn_ref(qkv, batch, tokens, heads, causal):
     (2, 257, 16, False),  # ViT-L/14: S wider than one UMMA N (256 + 16)
     (5, 77, 8, True),     # text tower, causal
     (2, 77, 12, True),
+    (3, 16, 2, False),    # one 16-key chunk: the second thread of every row has nothing to do
+    (2, 130, 4, False),   # second query tile with 2 live rows; two S regions + two O regions
+    (2, 225, 2, False),   # two key blocks of 128 + 112 keys (online softmax), per-thread output stores
+    (1, 320, 2, True),    # causal and longer than 224: one S region, tiles strictly in sequence, one stage
+    (1, 384, 1, False),   # the longest supported sequence (one pipeline stage -> one-region plan)
 ])
 def test_attention(cuda_device, batch, tokens, heads, causal):
     D = heads * 64

@@ -11,7 +11,7 @@ OUT = os.path.join(ROOT, "tools", "_trace", "libclm_trace.so")
 
 def build():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    srcs = [os.path.join(CSRC, f) for f in ("clm_api.cu", "clm_attention.cu")]
+    srcs = [os.path.join(CSRC, "clm_api.cu"), os.environ.get("CLM_TRACE_SRC", os.path.join(CSRC, "clm_attention.cu"))]
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DCLM_ATTN_TRACE", "-Xcompiler", "-fPIC",
            "-shared", "-cudart", "static", "-o", OUT] + srcs
     subprocess.run(cmd, check=True)
@@ -41,7 +41,7 @@ def main():
     names = ["wait_S", "got_S", "pass1_done", "max_xchg", "P_published", "got_O", "O_in_regs", "-"]
     print(f"# T={a.T} H={a.H} B={a.B}: clocks relative to the first stamp; MMA warp (1): ev0 = S issued, ev1 = PV issued")
     for t in range(NT):
-        print(f"tile {t}: MMA S_issue={int(tr[1,t,0])-t0 if tr[1,t,0] else None} PV_issue={int(tr[1,t,1])-t0 if tr[1,t,1] else None}")
+        print(f"tile {t}: MMA S_issue={int(tr[1,t,0])-t0 if tr[1,t,0] else None} PV_issue={int(tr[1,t,1])-t0 if tr[1,t,1] else None} other={[int(x)-t0 if x else None for x in tr[1,t,2:].tolist()]}")
         for w in range(2, NW):
             ev = [int(x) - t0 if x else None for x in tr[w, t].tolist()]
             if any(e is not None for e in ev):

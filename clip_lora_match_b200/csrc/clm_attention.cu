@@ -31,7 +31,9 @@ namespace {
 
 using namespace clm;
 
-constexpr int kThreads = 576;  // TMA warp + MMA warp + 16 softmax warps
+constexpr int kThreads = 640;  // TMA warp + MMA warp + 16 softmax warps + 2 extra-token warps
+constexpr int kTailWarp = 18;  // warps 18, 19 compute the extra query row (T = 128k + 1) on the CUDA cores
+constexpr int kXtBytes = 5504;  // extra-token scratch: partial dots [2][2][128] f32, v_x halves 16 x 64 B, 2 p rows of 288 f32
 constexpr int kOutStageBytes = 8 * 4096;  // per (group, lane quarter): a 32-row x 128-byte output slab for the TMA store
 constexpr int kXchBytes = 4096;   // row max / row sum exchanged between the two threads of a query row
 constexpr int kHeadDim = 64;
@@ -55,6 +57,11 @@ struct AttnParams {
   int T, H, Tp, mtiles, num_items, stages, stage_bytes, nslots;
   int stage_out;  // output rows leave through shared memory + TMA tile stores (needs kOutStageBytes)
   int blocks, nb0, nb1;  // key blocks per tile (2 = online softmax over two blocks of nb0 / nb1 keys)
+  // T = 128k + 1 (a ViT's class token on top of a 128-multiple of patches): the tensor cores see Tk = T - 1
+  // queries x Tk keys; the extra KEY is added by the softmax threads (one 64-long dot product and a rank-1
+  // update of O per row) and the extra QUERY row is computed by a dedicated warp, both from the staged
+  // shared-memory tiles.  Otherwise Tk == Tp.
+  int Tk, xt;
   // TMEM column of the S / P region and of the O accumulator used by tiles of parity 0 / 1;
   // o_alias: O lives inside the same parity's S region (dead by then), so S(t+2) waits for the drain
   int s_col0, s_col1, o_col0, o_col1, o_alias0, o_alias1;
@@ -114,6 +121,26 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// dot product of 8 bf16 pairs, two chains
+__device__ __forceinline__ void dot8(const uint4& a, const uint4& b, float& s0, float& s1) {
+  s0 = fmaf(bf16_lo(a.x), bf16_lo(b.x), s0); s1 = fmaf(bf16_hi(a.x), bf16_hi(b.x), s1);
+  s0 = fmaf(bf16_lo(a.y), bf16_lo(b.y), s0); s1 = fmaf(bf16_hi(a.y), bf16_hi(b.y), s1);
+  s0 = fmaf(bf16_lo(a.z), bf16_lo(b.z), s0); s1 = fmaf(bf16_hi(a.z), bf16_hi(b.z), s1);
+  s0 = fmaf(bf16_lo(a.w), bf16_lo(b.w), s0); s1 = fmaf(bf16_hi(a.w), bf16_hi(b.w), s1);
+}
+
 // max of 32 scores with four independent chains (the single-chain form serialises on FMNMX latency)
 __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float m) {
   float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
@@ -157,6 +184,84 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&p
   return (s0 + s1) + (s2 + s3);
 }
 
+// The extra query row (index Tk = 32 kNF) of one (batch, head) item, from the staged Q / K / V tiles at `sb`
+// (SWIZZLE_128B rows of 128 bytes).  Lane j scores keys j, j + 32, ... and, redundantly, the extra key Tk;
+// the warp reduces max and sum; lane l then accumulates output dimensions 2l, 2l+1 over all keys (for one
+// key the 32 lanes read the 128 contiguous bytes of its V row).  P stays fp32 on this path.
+template <int kNF>
+__device__ __forceinline__ void tail_row(uint32_t sb, int kv_bytes, float* prow, int lane, uint32_t* out_row) {
+  constexpr int Tk = 32 * kNF;
+  constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
+  const uint32_t kb = sb + static_cast<uint32_t>(kv_bytes), vb = kb + static_cast<uint32_t>(kv_bytes);
+  const uint32_t lsw = static_cast<uint32_t>(lane & 7);
+  float sc[kNF], sx = 0.f;
+#pragma unroll
+  for (int i = 0; i < kNF; ++i) sc[i] = 0.f;
+  const uint32_t k_lane = kb + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {  // 8 dimensions of the query at a time (row Tk starts a swizzle group: chunks in place)
+    const uint4 qw = ld_shared_v4(sb + static_cast<uint32_t>(Tk * 128 + (c << 4)));
+    const float q0 = bf16_lo(qw.x), q1 = bf16_hi(qw.x), q2 = bf16_lo(qw.y), q3 = bf16_hi(qw.y);
+    const float q4 = bf16_lo(qw.z), q5 = bf16_hi(qw.z), q6 = bf16_lo(qw.w), q7 = bf16_hi(qw.w);
+    const uint32_t koff = k_lane + ((static_cast<uint32_t>(c) ^ lsw) << 4);  // (j & 7) == (lane & 7)
+    uint4 w[kNF + 1];
+#pragma unroll
+    for (int i = 0; i < kNF; ++i) w[i] = ld_shared_v4(koff + static_cast<uint32_t>(i) * 4096u);
+    w[kNF] = ld_shared_v4(kb + static_cast<uint32_t>(Tk * 128 + (c << 4)));
+#pragma unroll
+    for (int i = 0; i <= kNF; ++i) {
+      float a = (i < kNF) ? sc[i < kNF ? i : 0] : sx;
+      a = fmaf(bf16_lo(w[i].x), q0, a); a = fmaf(bf16_hi(w[i].x), q1, a);
+      a = fmaf(bf16_lo(w[i].y), q2, a); a = fmaf(bf16_hi(w[i].y), q3, a);
+      a = fmaf(bf16_lo(w[i].z), q4, a); a = fmaf(bf16_hi(w[i].z), q5, a);
+      a = fmaf(bf16_lo(w[i].w), q6, a); a = fmaf(bf16_hi(w[i].w), q7, a);
+      if (i < kNF) sc[i < kNF ? i : 0] = a; else sx = a;
+    }
+  }
+  float mx = sx;
+#pragma unroll
+  for (int i = 0; i < kNF; ++i) mx = fmaxf(mx, sc[i]);
+  mx = warp_max(mx);
+  const float neg_mx = -mx * kScaleLog2e;
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < kNF; ++i) {
+    const float pj = fast_exp2(fmaf(sc[i], kScaleLog2e, neg_mx));
+    l += pj;
+    prow[lane + 32 * i] = pj;
+  }
+  const float p_x = fast_exp2(fmaf(sx, kScaleLog2e, neg_mx));
+  l = warp_sum(l) + p_x;
+  __syncwarp();
+  const uint32_t pr = smem_u32(prow);
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+  const uint32_t vl = vb + static_cast<uint32_t>((lane & 3) * 4);
+  const uint32_t hi3 = static_cast<uint32_t>(lane >> 2);
+#pragma unroll 2
+  for (int j0 = 0; j0 < Tk; j0 += 8) {
+    const uint4 pa = ld_shared_v4(pr + static_cast<uint32_t>(j0) * 4u);
+    const uint4 pb = ld_shared_v4(pr + static_cast<uint32_t>(j0 + 4) * 4u);
+    const uint32_t row = vl + static_cast<uint32_t>(j0) * 128u;
+    uint32_t w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w[u] = ld_shared_u32(row + u * 128 + ((hi3 ^ static_cast<uint32_t>(u)) << 4));
+    o0 = fmaf(__uint_as_float(pa.x), bf16_lo(w[0]), o0); o1 = fmaf(__uint_as_float(pa.x), bf16_hi(w[0]), o1);
+    o2 = fmaf(__uint_as_float(pa.y), bf16_lo(w[1]), o2); o3 = fmaf(__uint_as_float(pa.y), bf16_hi(w[1]), o3);
+    o0 = fmaf(__uint_as_float(pa.z), bf16_lo(w[2]), o0); o1 = fmaf(__uint_as_float(pa.z), bf16_hi(w[2]), o1);
+    o2 = fmaf(__uint_as_float(pa.w), bf16_lo(w[3]), o2); o3 = fmaf(__uint_as_float(pa.w), bf16_hi(w[3]), o3);
+    o0 = fmaf(__uint_as_float(pb.x), bf16_lo(w[4]), o0); o1 = fmaf(__uint_as_float(pb.x), bf16_hi(w[4]), o1);
+    o2 = fmaf(__uint_as_float(pb.y), bf16_lo(w[5]), o2); o3 = fmaf(__uint_as_float(pb.y), bf16_hi(w[5]), o3);
+    o0 = fmaf(__uint_as_float(pb.z), bf16_lo(w[6]), o0); o1 = fmaf(__uint_as_float(pb.z), bf16_hi(w[6]), o1);
+    o2 = fmaf(__uint_as_float(pb.w), bf16_lo(w[7]), o2); o3 = fmaf(__uint_as_float(pb.w), bf16_hi(w[7]), o3);
+  }
+  {  // the extra key itself
+    const uint32_t w = ld_shared_u32(vl + static_cast<uint32_t>(Tk) * 128u + (hi3 << 4));
+    o0 = fmaf(p_x, bf16_lo(w), o0); o1 = fmaf(p_x, bf16_hi(w), o1);
+  }
+  const float inv = 1.0f / l;
+  out_row[lane] = pack_bf16x2((o0 + o2) * inv, (o1 + o3) * inv);
+}
+
 template <bool kCausal>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CUtensorMap map16,
@@ -165,7 +270,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* ostage = smem + p.stages * p.stage_bytes;  // 1024-byte aligned (stage_bytes is a multiple of 6144)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + (p.stage_out ? kOutStageBytes : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + (p.stage_out == 1 ? kOutStageBytes : 0));
   uint64_t* stage_full = bars;                     // [kMaxStages]
   uint64_t* stage_empty = bars + kMaxStages;       // [kMaxStages]
   uint64_t* s_full = bars + 2 * kMaxStages;        // [2] S ready (MMA commit), by tile parity
@@ -175,11 +280,14 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
   float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [group][half][128]
   float* xsum = xmax + 2 * 2 * 128;
+  float* xdot = xsum + 2 * 2 * 128;                         // extra-token scratch (only when p.xt)
+  uint8_t* vxs = reinterpret_cast<uint8_t*>(xdot + 2 * 2 * 128);
+  float* prow = reinterpret_cast<float*>(vxs + 16 * 64);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int T = p.T, H = p.H, Tp = p.Tp, D = p.H * kHeadDim;
-  const int kv_bytes = Tp * 128;  // one of Q / K / V in a stage
+  const int T = p.T, H = p.H, Tp = p.Tp, Tk = p.Tk, D = p.H * kHeadDim;
+  const int kv_bytes = Tp * 128;  // one of Q / K / V in a stage (Tp rows are loaded; the MMAs see Tk keys)
   const int n_local = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                       static_cast<int>(gridDim.x);
   const int n_tiles = n_local * p.mtiles;
@@ -189,7 +297,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
     tma_prefetch_desc(&map16);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&stage_full[s], 1);
-      mbar_init(&stage_empty[s], 1);
+      // last PV's commit (+ the extra-token warp that owns the item) (+ the 4 warp pairs of each of the
+      // item's tiles once their output slab, staged in the tile's dead Q rows, has been read by the TMA unit)
+      mbar_init(&stage_empty[s], 1 + p.xt + (p.stage_out == 2 ? 4 * p.mtiles : 0));
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
@@ -260,8 +370,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
         const uint32_t q_addr = smem_u32(smem + c.st * p.stage_bytes);
         const uint32_t k_addr = q_addr + kv_bytes;
         const uint32_t sbase = tmem + static_cast<uint32_t>(p.s_col(c.t & 1));
-        for (int n0 = 0; n0 < Tp; n0 += 256) {
-          const int nn = (Tp - n0) < 256 ? (Tp - n0) : 256;
+        for (int n0 = 0; n0 < Tk; n0 += 256) {
+          const int nn = (Tk - n0) < 256 ? (Tk - n0) : 256;
           const uint32_t idesc = umma_idesc_bf16(128, nn, 0, 0);
 #pragma unroll
           for (int k = 0; k < kHeadDim / 16; ++k)
@@ -285,7 +395,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
         const uint32_t v_addr = smem_u32(smem + c.st * p.stage_bytes) + 2 * kv_bytes;
         const uint32_t pbase = tmem + static_cast<uint32_t>(p.s_col(b));
         const uint32_t obase = tmem + static_cast<uint32_t>(p.o_col(b));
-        const int ksteps = Tp / 16;
+        const int ksteps = Tk / 16;
         for (int ks = 0; ks < ksteps; ++ks)
           umma_bf16_ts(obase, pbase + ks * 8, umma_desc_sw128_mn(v_addr + ks * 2048), idesc_pv,
                        ks != 0 ? 1u : 0u);
@@ -408,7 +518,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
         }
       }
     }
-  } else {
+  } else if (warp < kTailWarp) {
     // ================= softmax groups =================
     // 16 warps = 2 groups (tile parity) x 2 column halves x 4 TMEM lane quarters.  A query row is
     // shared by two threads (same lane of two warps with the same quarter): each reduces / exponentiates
@@ -420,7 +530,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
     const int q = warp & 3;              // TMEM lane quarter of this warp
     const int r = q * 32 + lane;         // row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const int nchunks = (Tp + 31) / 32;
+    const int nchunks = (Tk + 31) / 32;
     constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     const uint32_t srow = tmem + lane_off + static_cast<uint32_t>(p.s_col(g));
     const uint32_t orow = tmem + lane_off + static_cast<uint32_t>(p.o_col(g)) + static_cast<uint32_t>(hf * 32);
@@ -526,16 +636,44 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
           }
         }
       }
-    } else
-    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x)
+    } else {
+    const bool xt = !kCausal && p.xt != 0;
+    const uint32_t vx_w = smem_u32(vxs + (warp - 2) * 64);  // this warp's copy of its half of the extra V row
+    float* my_dot = xdot + (g * 2 + hf) * 128 + r;
+    int li = 0;  // items seen by this CTA: item li sits in stage li % stages
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, ++li)
     for (int mt = 0; mt < p.mtiles; ++mt, ++t) {
       if ((t & 1) != g) continue;
       const int b = it / H, h = it - b * H;
       const uint32_t par = static_cast<uint32_t>((t >> 1) & 1);
       const int qi = mt * 128 + r;                     // query position in the sequence
       const bool warp_live = mt * 128 + q * 32 < T;    // does this warp own any real row?
-      int valid = T;
+      int valid = T < Tk ? T : Tk;
       if (kCausal) valid = (qi + 1 < T) ? qi + 1 : T;
+      // ---- extra key (row Tk of K / V): this thread's half of q_row . k_x, and a private copy of its
+      // half of v_x (the stage may be refilled before the output phase of the item's last tile)
+      float px = 0.f;
+      if (xt) {
+        const int st = li % p.stages;
+        mbar_wait(&stage_full[st], static_cast<uint32_t>((li / p.stages) & 1));
+        const uint32_t sb = smem_u32(smem + st * p.stage_bytes);
+        const uint32_t qa = sb + static_cast<uint32_t>(qi) * 128u;
+        const uint32_t ka = sb + static_cast<uint32_t>(kv_bytes + Tk * 128);
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint32_t c = static_cast<uint32_t>(hf * 4 + jj);
+          const uint4 a = ld_shared_v4(qa + ((c ^ static_cast<uint32_t>(r & 7)) << 4));
+          const uint4 kx = ld_shared_v4(ka + (c << 4));
+          dot8(a, kx, d0, d1);
+        }
+        *my_dot = d0 + d1;
+        if (lane < 4) {
+          const uint4 w = ld_shared_v4(sb + static_cast<uint32_t>(2 * kv_bytes + Tk * 128 + ((hf * 4 + lane) << 4)));
+          st_shared_v4(vx_w + (lane << 4), w.x, w.y, w.z, w.w);
+        }
+        __syncwarp();
+      }
       // chunks this warp pair has to look at: under the causal mask nothing right of its last row counts
       int nch = nchunks;
       if (kCausal) {
@@ -561,9 +699,14 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       }
       TRACE(t, 2);
       *my_max = mx;
-      if (p.stage_out && hf == 0 && lane == 0) bulk_wait_read<0>();  // the previous tile's slab has left smem
+      if (p.stage_out == 1 && hf == 0 && lane == 0) bulk_wait_read<0>();  // the previous tile's slab has left smem
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
       mx = fmaxf(mx, *other_max);
+      float sx = 0.f;
+      if (xt) {  // both threads of the row add the two halves in the same order
+        sx = xdot[(g * 2 + 0) * 128 + r] + xdot[(g * 2 + 1) * 128 + r];
+        mx = fmaxf(mx, sx);
+      }
       TRACE(t, 3);
       // ---- pass 2: p = 2^(s*c - max*c), partial row sum, P (bf16x2) written over S.  P(c) lands in the
       // columns of S chunk c/2, so the pair synchronises once per iteration: by then both threads hold
@@ -571,6 +714,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       float sum = 0.f;
       if (warp_live) {
         const float neg_mx = -mx * kScaleLog2e;
+        if (xt) {
+          px = fast_exp2(fmaf(sx, kScaleLog2e, neg_mx));  // fp32 weight of the extra key (not rounded to bf16)
+          if (hf == 0) sum = px;
+        }
         uint32_t pk[16];
         for (int i = 0; i < niter; ++i) {
           const int c = 2 * i + hf;
@@ -608,12 +755,31 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       tc_fence_before();
       TRACE(t, 6);
       mbar_arrive(&slot_free[g]);  // this half of O(t) is in registers: its columns may be overwritten
+      if (xt && warp_live) {  // O += p_x * v_x
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint4 w = ld_shared_v4(vx_w + (jj << 4));
+          v[8 * jj + 0] = __float_as_uint(fmaf(px, bf16_lo(w.x), __uint_as_float(v[8 * jj + 0])));
+          v[8 * jj + 1] = __float_as_uint(fmaf(px, bf16_hi(w.x), __uint_as_float(v[8 * jj + 1])));
+          v[8 * jj + 2] = __float_as_uint(fmaf(px, bf16_lo(w.y), __uint_as_float(v[8 * jj + 2])));
+          v[8 * jj + 3] = __float_as_uint(fmaf(px, bf16_hi(w.y), __uint_as_float(v[8 * jj + 3])));
+          v[8 * jj + 4] = __float_as_uint(fmaf(px, bf16_lo(w.z), __uint_as_float(v[8 * jj + 4])));
+          v[8 * jj + 5] = __float_as_uint(fmaf(px, bf16_hi(w.z), __uint_as_float(v[8 * jj + 5])));
+          v[8 * jj + 6] = __float_as_uint(fmaf(px, bf16_lo(w.w), __uint_as_float(v[8 * jj + 6])));
+          v[8 * jj + 7] = __float_as_uint(fmaf(px, bf16_hi(w.w), __uint_as_float(v[8 * jj + 7])));
+        }
+      }
       if (p.stage_out) {
         // A thread owns 64 bytes of one output row; writing them straight to global memory costs 32
         // scattered 16-byte transactions per warp instruction (measured: ~1.7k clocks per tile).  The
         // two warps of a row quarter assemble their 32 x 128-byte slab in shared memory (SWIZZLE_128B
         // pattern of the output map) and one lane hands it to the TMA unit; rows >= T are clipped.
-        const uint32_t ost = smem_u32(ostage + (g * 4 + q) * 4096);
+        // stage_out == 2: no room for a staging buffer; the slab goes into this warp pair's 32 rows of the
+        // tile's own Q block, which nothing reads after S has been computed (same swizzled row layout)
+        const int st_cur = li % p.stages;
+        const uint32_t ost = (p.stage_out == 2)
+                                 ? smem_u32(smem + st_cur * p.stage_bytes) + static_cast<uint32_t>(mt * 128 + q * 32) * 128u
+                                 : smem_u32(ostage + (g * 4 + q) * 4096);
         if (warp_live) {
           const float inv = 1.0f / sum;
 #pragma unroll
@@ -630,6 +796,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
           tma_store_3d(&map_out, ost, h * kHeadDim, mt * 128 + q * 32, b);
           bulk_commit();
         }
+        if (p.stage_out == 2 && hf == 0 && lane == 0) {
+          // release this pair's share of the stage as soon as the TMA unit has read the slab: the refill of
+          // the stage (two stages only) is on the critical path of the tile after next
+          bulk_wait_read<0>();
+          mbar_arrive(&stage_empty[st_cur]);
+        }
       } else if (warp_live && qi < T) {
         const float inv = 1.0f / sum;
         uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(b * T + qi) * D + h * kHeadDim + hf * 32);
@@ -644,7 +816,32 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
         }
       }
     }
+    }
     if (p.stage_out && hf == 0 && lane == 0) bulk_wait<0>();  // every slab of this warp pair has reached memory
+  } else if (!kCausal && p.xt) {
+    // ================= extra-token warps: the query row Tk of every item, on the CUDA cores =================
+    // (one row per (batch, head): a third 128-row tensor-core tile would be 1/128 used).  The two warps take
+    // alternate items; see tail_row.
+    const int tw = warp - kTailWarp;
+    float* my_prow = prow + tw * 288;
+    int st = 0, tl = 0;
+    uint32_t ph = 0;
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, ++tl) {
+      if ((tl & 1) == tw) {
+        const int b = it / H, h = it - b * H;
+        TRACE(tl, 0);
+        mbar_wait(&stage_full[st], ph);
+        TRACE(tl, 1);
+        const uint32_t sb = smem_u32(smem + st * p.stage_bytes);
+        uint32_t* orow = reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * T + Tk) * D + h * kHeadDim);
+        if (Tk == 256) tail_row<8>(sb, kv_bytes, my_prow, lane, orow);
+        else tail_row<4>(sb, kv_bytes, my_prow, lane, orow);
+        __syncwarp();  // every lane is done with the stage and with its p row
+        TRACE(tl, 3);
+        if (lane == 0) mbar_arrive(&stage_empty[st]);
+      }
+      if (++st == p.stages) { st = 0; ph ^= 1; }
+    }
   }
 
   tc_fence_before();
@@ -666,6 +863,16 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   p.H = heads;
   p.Tp = (T + 15) / 16 * 16;
   p.mtiles = (T + 127) / 128;
+  // T = 128k + 1 (ViT-L/14: 256 patches + class token): the tensor cores take the 128k x 128k block, the
+  // extra key and the extra query row are done on the CUDA cores (see AttnParams).  CLM_ATTN_XT=0 disables.
+  static int xt_off = -1;
+  if (xt_off < 0) {
+    const char* e = getenv("CLM_ATTN_XT");
+    xt_off = (e && e[0] == '0') ? 1 : 0;
+  }
+  p.xt = (!xt_off && !causal && T > 128 && T % 128 == 1 && T <= 257) ? 1 : 0;
+  p.Tk = p.xt ? T - 1 : p.Tp;
+  if (p.xt) p.mtiles = p.Tk / 128;
   const long long items = static_cast<long long>(batch) * heads;
   CLM_REQUIRE(items < 2147483647LL / 4, "clm_attention: too many (batch, head) items");
   p.num_items = static_cast<int>(items);
@@ -675,7 +882,7 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   if (stage_bytes < p.mtiles * 16384) stage_bytes = p.mtiles * 16384;
   p.stage_bytes = stage_bytes;
   // output staging for the TMA stores if two pipeline stages still fit beside it (not at T = 257)
-  int smem_budget = 227 * 1024 - 1024 - 256 - kXchBytes;
+  int smem_budget = 227 * 1024 - 1024 - 256 - kXchBytes - (p.xt ? kXtBytes : 0);
   p.stage_out = ((smem_budget - kOutStageBytes) / stage_bytes >= 2) ? 1 : 0;
   if (p.stage_out) smem_budget -= kOutStageBytes;
   int stages = smem_budget / stage_bytes;
@@ -689,10 +896,19 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   //   two S regions, O0 separate, O1 inside S1 (T <= 224: ViT-B/16's 197) -> S(t+2) of odd t waits
   //   two key blocks per tile, two S regions of one block + two O regions (T <= 384: ViT-L/14's 257)
 //   [fallback: one S region, two O regions, tiles strictly in sequence]
-  p.blocks = 1; p.nb0 = p.Tp; p.nb1 = 0;
-  const int s_cols = (p.Tp + 31) / 32 * 32;
-  const int o_in = (p.Tp / 2 + 31) / 32 * 32;  // first column past P inside an S region
-  if (2 * s_cols + 128 <= 512 && stages >= 2) {
+  p.blocks = 1; p.nb0 = p.Tk; p.nb1 = 0;
+  const int s_cols = (p.Tk + 31) / 32 * 32;
+  const int o_in = (p.Tk / 2 + 31) / 32 * 32;  // first column past P inside an S region
+  if (p.xt && p.Tk > 128) {
+    // Tk = 256: two S regions fill the 512 columns; both O accumulators live in the dead upper half of
+    // their own S region, so S(t+2) of either stream waits for the drain of O(t)
+    CLM_REQUIRE(stages >= 2 && 2 * s_cols <= 512 && o_in + 64 <= s_cols, "clm_attention: extra-token plan does not fit");
+    p.nslots = 2;
+    p.s_col0 = 0; p.s_col1 = s_cols;
+    p.o_col0 = o_in; p.o_col1 = s_cols + o_in;
+    p.o_alias0 = 1; p.o_alias1 = 1;
+    if (!p.stage_out) p.stage_out = 2;  // output slabs are staged in the tile's dead Q rows
+  } else if (2 * s_cols + 128 <= 512 && stages >= 2) {
     p.nslots = 2;
     p.s_col0 = 0; p.s_col1 = s_cols;
     p.o_col0 = 2 * s_cols; p.o_col1 = 2 * s_cols + 64;
@@ -710,7 +926,7 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
       const char* e = getenv("CLM_ATTN_BLOCKS");
       one_block = (e && e[0] == '1') ? 1 : 0;
     }
-    const int nb0 = (p.Tp / 2 + 15) / 16 * 16, nb1 = p.Tp - nb0;
+    const int nb0 = (p.Tk / 2 + 15) / 16 * 16, nb1 = p.Tk - nb0;
     const int b_cols = (nb0 + 31) / 32 * 32;
     if (!one_block && !causal && stages >= 2 && nb1 >= 16 && 2 * b_cols + 128 <= 512) {
       p.blocks = 2; p.nb0 = nb0; p.nb1 = nb1;
@@ -727,7 +943,8 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
     }
   }
   if (p.blocks == 2) p.stage_out = 0;  // the two-block path (T > 224) keeps per-thread stores
-  const int smem_bytes = stages * stage_bytes + (p.stage_out ? kOutStageBytes : 0) + 256 + kXchBytes + 1024;
+  const int smem_bytes = stages * stage_bytes + (p.stage_out == 1 ? kOutStageBytes : 0) + 256 + kXchBytes +
+                         (p.xt ? kXtBytes : 0) + 1024;
 
   CUtensorMap map64, map16;
   int rc = clm_make_tmap_bf16_2d(&map64, qkv, static_cast<uint64_t>(batch) * T, 3ull * D, 3ull * D,

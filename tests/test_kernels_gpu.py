@@ -208,6 +208,9 @@ def _attn_ref(qkv, batch, tokens, heads, causal):
     (2, 225, 2, False),   # two key blocks of 128 + 112 keys (online softmax), per-thread output stores
     (1, 320, 2, True),    # causal and longer than 224: one S region, tiles strictly in sequence, one stage
     (1, 384, 1, False),   # the longest supported sequence (one pipeline stage -> one-region plan)
+    (3, 129, 4, False),   # 128 + 1: extra-token path (CUDA-core key / query row) with two S + two O regions
+    (40, 257, 8, False),  # ViT-L/14 extra-token path, 320 items on 148 SMs: stage reuse across items
+    (37, 197, 12, False), # ViT-B/16, three items per CTA (stage / TMEM parity wrap-around)
 ])
 def test_attention(cuda_device, batch, tokens, heads, causal):
     D = heads * 64

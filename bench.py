@@ -31,6 +31,7 @@ if ROOT not in sys.path:
 ARCH = "openai/clip-vit-base-patch16"
 LORA_R, LORA_ALPHA, LORA_TARGETS = 16, 32, ["q_proj", "v_proj"]
 BATCH = 1024
+L14_ARCH, L14_BATCH = "openai/clip-vit-large-patch14", 512
 INDEX_ROWS, INDEX_DIM, QUERY_BATCH, TOP_K = 10_000_000, 768, 4096, 10
 
 
@@ -191,6 +192,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-search", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l14", action="store_true")
     ap.add_argument("--index-rows", type=int, default=INDEX_ROWS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -340,6 +342,38 @@ def main():
     del pv_host, model, pv
     torch.cuda.empty_cache()
 
+    # ---- ViT-L/14 + LoRA r=16 image tower (BASELINE configs[2] / north_star's >= 70 % target) -------
+    # Reported beside the headline: images/s of the index-build encoder at batch 512 per GPU, and its
+    # algorithmic FLOP rate against the measured bf16 peaks.  Same timing rules as the headline.
+    l14 = None
+    if not args.no_l14:
+        arch_l = CM.arch_from_name(L14_ARCH)
+        model_l = CM.B200ClipModel(arch_l, CM.random_init_state_dict(arch_l, seed=0), device=dev)
+        model_l.set_lora(init_lora_adapter(model_l.linear_dims(), LoraConfig(r=LORA_R, lora_alpha=LORA_ALPHA,
+                                                                             target_modules=LORA_TARGETS),
+                                           seed=1, init_b_std=0.02, base_model_name=L14_ARCH))
+        gl = torch.Generator(device=dev).manual_seed(6 + rank)
+        pv_l = torch.randn((L14_BATCH, 3, 224, 224), generator=gl, device=dev)
+        for _ in range(args.warmup):
+            model_l.encode_images(pv_l)
+        ms_l = timed(lambda: model_l.encode_images(pv_l), args.steps)
+        lv = arch_l.vision
+        fl_l = flops_per_item(257, lv.width, lv.layers, lv.mlp, arch_l.proj_dim, LORA_R, 2, 3 * 14 * 14, 256)
+        tf_l = fl_l * L14_BATCH / (ms_l / args.steps * 1e-3) / 1e12
+        lib.clm_prof_enable(1)
+        model_l.encode_images(pv_l)
+        prof_l = {k: _lib.prof_summary(k) for k in ("gemm", "attention", "elementwise")}
+        lib.clm_prof_enable(0)
+        l14 = {"workload": "configs[2]: CLIP ViT-L/14 + LoRA r=16 (q,v) image tower, batch 512 per GPU, random-init weights",
+               "images_per_s": L14_BATCH * world * args.steps / (ms_l / 1e3), "ms_per_step": ms_l / args.steps,
+               "algorithmic_gflop_per_image": fl_l / 1e9, "tflops_per_gpu": tf_l,
+               "frac_of_sustained_peak": tf_l / peaks["tf_sustained"], "frac_of_burst_peak": tf_l / peaks["tf_burst"],
+               "kernel_ms_per_step": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                          "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1)}
+                                      for k, v in prof_l.items()}}
+        del model_l, pv_l
+        torch.cuda.empty_cache()
+
     # ---- search: top-10 over the row-sharded 10M x 768 index ----------------------------
     search = None
     if not args.no_search:
@@ -424,7 +458,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "detail": detail, "search": search,
+            "roofline": roofline, "cpu_baseline": cpu, "detail": detail, "vit_l14": l14, "search": search,
         }
         print(json.dumps(line), flush=True)
 

@@ -324,10 +324,18 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       const int n64 = Tp / 64, n16 = (Tp % 64) / 16;
       int st = 0;
       uint32_t ph = 0;
+#ifdef CLM_ATTN_TRACE
+      int tl = 0;
+#endif
       for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
         const int b = it / H, h = it % H;
         const int row_base = b * T;
+        TRACE(tl, 0);
         mbar_wait(&stage_empty[st], ph ^ 1);
+        TRACE(tl, 1);
+#ifdef CLM_ATTN_TRACE
+        ++tl;
+#endif
         uint8_t* base = smem + st * p.stage_bytes;
         mbar_arrive_expect_tx(&stage_full[st], static_cast<uint32_t>(3 * kv_bytes));
         for (int part = 0; part < 3; ++part) {  // 0 = Q, 1 = K, 2 = V
@@ -656,6 +664,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       if (xt) {
         const int st = li % p.stages;
         mbar_wait(&stage_full[st], static_cast<uint32_t>((li / p.stages) & 1));
+        TRACE(t, 7);
         const uint32_t sb = smem_u32(smem + st * p.stage_bytes);
         const uint32_t qa = sb + static_cast<uint32_t>(qi) * 128u;
         const uint32_t ka = sb + static_cast<uint32_t>(kv_bytes + Tk * 128);

@@ -40,6 +40,7 @@ struct SCfg {
 
 struct SearchParams {
   int nq, n, kblocks, q_tiles, splits, tiles_n, kc, stages;  // q_tiles: tiles of BM * kCtas queries
+  int a_bytes;  // bytes of the query tile actually loaded per k-block (64-row box when nq <= 64)
   float* thr_io;  // per-query running lower bound of the kc-th best score, shared by all units (or null)
   float* cand_score;
   int32_t* cand_id;
@@ -182,7 +183,7 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
               tma_load_2d_2sm_hint(sa, &map_q, &full[stage], kb * BK, q0, kEvictLast);
               tma_load_2d_2sm_hint(sa + kABytes, &map_e, &full[stage], kb * BK, e0, kEvictFirst);
             } else {
-              mbar_arrive_expect_tx(&full[stage], kStageBytes);
+              mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(p.a_bytes + kBBytes));
               tma_load_2d_hint(sa, &map_q, &full[stage], kb * BK, q0, kEvictLast);
               tma_load_2d_hint(sa + kABytes, &map_e, &full[stage], kb * BK, e0, kEvictFirst);
             }
@@ -593,7 +594,15 @@ extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int n
               tiles_n);
   CUtensorMap mq, me;
   int rc;
-  if ((rc = clm_make_tmap_bf16_2d(&mq, q_bf16, nq, dim, dim, BK, BM))) return rc;
+  // streaming regime with at most 64 queries: only 64 query rows are (re)loaded per k-block; the other 64
+  // rows of the A tile are never written and feed TMEM lanes that nobody reads.  CLM_SEARCH_QBOX=128 disables.
+  static int qbox_full = -1;
+  if (qbox_full < 0) {
+    const char* e = getenv("CLM_SEARCH_QBOX");
+    qbox_full = (e && e[0] == '1') ? 1 : 0;
+  }
+  const int q_box_rows = (ctas == 1 && nq <= 64 && !qbox_full) ? 64 : BM;
+  if ((rc = clm_make_tmap_bf16_2d(&mq, q_bf16, nq, dim, dim, BK, q_box_rows))) return rc;
   if ((rc = clm_make_tmap_bf16_2d(&me, index_bf16, n, dim, dim, BK, BN / ctas))) return rc;
   SearchParams p;
   p.nq = nq;
@@ -603,6 +612,7 @@ extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int n
   p.splits = splits;
   p.tiles_n = tiles_n;
   p.kc = kc;
+  p.a_bytes = q_box_rows * BK * 2;
   p.thr_io = thr_io;
   p.cand_score = cand_score;
   p.cand_id = cand_id;

@@ -24,7 +24,7 @@ def main():
     if a.build_only: return
     lib = C.CDLL(OUT)
     dev = torch.device("cuda")
-    NW, NT, NE = 20, 12, 8
+    NW, NT, NE = 21, 12, 8
     buf = torch.zeros(NW * NT * NE, dtype=torch.int64, device=dev)
     qkv = torch.randn((a.B * a.T, 3 * a.H * 64), device=dev).bfloat16()
     out = torch.empty((a.B * a.T, a.H * 64), dtype=torch.bfloat16, device=dev)
@@ -38,10 +38,12 @@ def main():
     torch.cuda.synchronize()
     tr = buf.cpu().view(NW, NT, NE)
     t0 = int(tr[tr > 0].min())
-    names = ["wait_S", "got_S", "pass1_done", "max_xchg", "P_published", "got_O", "O_in_regs", "-"]
+    names = ["wait_S", "got_S", "pass1_done", "max_xchg", "P_published", "got_O", "O_in_regs", "stage_ok"]
     print(f"# T={a.T} H={a.H} B={a.B}: clocks relative to the first stamp; MMA warp (1): ev0 = S issued, ev1 = PV issued")
     for t in range(NT):
         print(f"tile {t}: MMA S_issue={int(tr[1,t,0])-t0 if tr[1,t,0] else None} PV_issue={int(tr[1,t,1])-t0 if tr[1,t,1] else None} other={[int(x)-t0 if x else None for x in tr[1,t,2:].tolist()]}")
+        if tr[0, t, 1]:
+            print(f"   TMA warp, item {t}: wants_stage={int(tr[0,t,0])-t0} stage_free={int(tr[0,t,1])-t0}")
         for w in (18, 19):
             ev = [int(x) - t0 if x else None for x in tr[w, t].tolist()]
             if any(e is not None for e in ev):
@@ -49,7 +51,7 @@ def main():
         for w in range(2, 18):
             ev = [int(x) - t0 if x else None for x in tr[w, t].tolist()]
             if any(e is not None for e in ev):
-                print(f"   warp {w:2d} (grp {((w-2)>>2)&1} half {(w-2)>>3} q {w&3}): " + " ".join(f"{n}={e}" for n, e in zip(names[:7], ev[:7])))
+                print(f"   warp {w:2d} (grp {((w-2)>>2)&1} half {(w-2)>>3} q {w&3}): " + " ".join(f"{n}={e}" for n, e in zip(names, ev)))
 
 if __name__ == "__main__":
     main()

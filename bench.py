@@ -321,6 +321,20 @@ def main():
         "kernel_ms_per_step": {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in prof.items()},
     }
 
+    # ---- the reference's own calling pattern: one image + one caption at a time (launch bound; the
+    # host mirror replays a CUDA graph per batch size for small batches) ------------------------------
+    pv1, ids1 = pv[:1].contiguous(), ids[:1].contiguous()
+
+    def one_pair():
+        model.encode_images(pv1)
+        model.encode_texts(ids1)
+
+    for _ in range(5):
+        one_pair()
+    ms_one = timed(one_pair, 50) / 50
+    detail["single_pair_latency_ms"] = ms_one
+    detail["single_pair_note"] = "batch-1 image + caption through encode_images/encode_texts (CUDA-graph replay), device inputs"
+
     # ---- end to end: host (pinned) inputs -> embeddings back on the host, every step ----
     pv_host = pv.cpu().pin_memory()
     ids_host = ids.cpu().pin_memory()

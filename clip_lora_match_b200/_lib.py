@@ -86,6 +86,8 @@ SIGNATURES = {
     "clm_topk_merge_sorted": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "clm_cosine_gemv": (_I, [_P, _P, _I, _I, _P, _P]),
     "clm_launch_count": (C.c_ulonglong, []),
+    "clm_launch_count_add": (None, [C.c_longlong]),
+    "clm_prof_is_enabled": (_I, []),
     "clm_prof_enable": (_I, [_I]),
     "clm_prof_records": (_I, [C.POINTER(C.c_double), _I]),
     "clm_prof_summary": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),

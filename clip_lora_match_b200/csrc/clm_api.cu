@@ -174,6 +174,12 @@ void clm_prof_end(cudaStream_t s) {
 
 extern "C" unsigned long long clm_launch_count(void) { return g_launches.load(); }
 
+// a CUDA graph captured over library calls launches its kernels again on every replay without passing
+// through the library: the host side adds the captured launch count per replay so the total stays true
+extern "C" void clm_launch_count_add(long long n) { g_launches.fetch_add(static_cast<unsigned long long>(n)); }
+
+extern "C" int clm_prof_is_enabled(void) { return g_prof_on.load() ? 1 : 0; }
+
 extern "C" int clm_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& r : g_recs) {

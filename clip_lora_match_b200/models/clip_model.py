@@ -15,7 +15,9 @@ random init of the named architecture) and for the host-side image processor.
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
+import os
 from dataclasses import dataclass
 from pathlib import Path
 from typing import Dict, List, Optional, Tuple, Union
@@ -107,6 +109,17 @@ def hf_config_for(arch: ClipArch):
 # ------------------------------------------------------------------------------------------
 # the model object
 # ------------------------------------------------------------------------------------------
+class _GraphEntry:
+    """A captured tower pass: the graph, the output buffer its kernels write, its launch count."""
+    __slots__ = ("graph", "inp", "out", "launches")
+
+    def __init__(self):
+        self.graph = None
+        self.inp = None
+        self.out = None
+        self.launches = 0
+
+
 class B200ClipModel:
     """CLIP dual encoder whose forward is the C-ABI of include/clm_b200.h.
 
@@ -132,6 +145,10 @@ class B200ClipModel:
         self._workspace: Optional[torch.Tensor] = None
         self._dummy = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._stage = None  # host->device staging (encode_images of host tensors)
+        # CUDA graphs of whole tower passes for small batches, keyed by (tower, batch, ...): see _run_tower.
+        # CLM_GRAPHS=0 disables.
+        self.use_graphs = os.environ.get("CLM_GRAPHS", "1") != "0"
+        self._graphs: "collections.OrderedDict[tuple, _GraphEntry]" = collections.OrderedDict()
         self.set_lora(lora)
 
     # ---- reference-compat surface ------------------------------------------------------
@@ -266,6 +283,7 @@ class B200ClipModel:
         self._keep[kind] = keep
 
     def _destroy_towers(self) -> None:
+        self._graphs.clear()  # captured launches point at the towers' weights
         for h in self._towers.values():
             self._lib.clm_tower_destroy(h)
         self._towers.clear()
@@ -288,13 +306,56 @@ class B200ClipModel:
         return self._workspace
 
     H2D_CHUNK = 256  # images per host->device chunk when the input lives in host memory
+    MAX_GRAPHS = 16
+    GRAPH_MAX_BATCH = 32
+
+    def _run_tower(self, kind: str, inp: torch.Tensor, out: torch.Tensor, normalize: bool) -> None:
+        """One tower pass over a device-resident batch: `inp` -> `out` on the current stream.
+
+        Small batches (<= GRAPH_MAX_BATCH items: the reference's one-item-at-a-time calls) are launch
+        bound -- ~100 kernels of a few microseconds each -- so their pass is captured once per batch size
+        into a CUDA graph over graph-owned input / output buffers and replayed (first call eager, second
+        call captures).  Large batches run eagerly: measured at batch 1024 the step is power bound and a
+        graph changes nothing (tools/graph_probe.py, profiles/r1_notes.md)."""
+        b = inp.shape[0]
+        ws = self._ensure_workspace(kind, b)
+        fn = self._lib.clm_encode_image if kind == "vision" else self._lib.clm_encode_text
+        tower = self._towers[kind]
+
+        def launch(src: torch.Tensor, dst: torch.Tensor) -> None:
+            _lib.check(fn(tower, src.data_ptr(), b, dst.data_ptr(), int(normalize), ws.data_ptr(), ws.numel(),
+                          _lib.cur_stream()), f"clm_encode_{'image' if kind == 'vision' else 'text'}")
+
+        if (not self.use_graphs or b > self.GRAPH_MAX_BATCH or self._lib.clm_prof_is_enabled()
+                or torch.cuda.is_current_stream_capturing()):
+            launch(inp, out)
+            return
+        key = (kind, b, bool(normalize), ws.data_ptr(), ws.numel())
+        ent = self._graphs.get(key)
+        if ent is None:
+            launch(inp, out)  # also performs the kernels' one-time cudaFuncSetAttribute calls outside a capture
+            self._graphs[key] = _GraphEntry()
+            while len(self._graphs) > self.MAX_GRAPHS:
+                self._graphs.popitem(last=False)
+            return
+        self._graphs.move_to_end(key)
+        if ent.graph is None:
+            ent.inp, ent.out = torch.empty_like(inp), torch.empty_like(out)
+            n0 = self._lib.clm_launch_count()
+            graph = torch.cuda.CUDAGraph()
+            # thread_local: another thread (the NCCL watchdog) may touch the CUDA API during the capture
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                launch(ent.inp, ent.out)
+            ent.launches = self._lib.clm_launch_count() - n0
+            self._lib.clm_launch_count_add(-ent.launches)  # counted while capturing, but nothing has run yet
+            ent.graph = graph
+        ent.inp.copy_(inp)
+        ent.graph.replay()
+        self._lib.clm_launch_count_add(ent.launches)
+        out.copy_(ent.out)
 
     def _encode_images_dev(self, pv: torch.Tensor, out: torch.Tensor, normalize: bool) -> None:
-        b = pv.shape[0]
-        ws = self._ensure_workspace("vision", b)
-        _lib.check(self._lib.clm_encode_image(self._towers["vision"], pv.data_ptr(), b, out.data_ptr(),
-                                              int(normalize), ws.data_ptr(), ws.numel(), _lib.cur_stream()),
-                   "clm_encode_image")
+        self._run_tower("vision", pv, out, normalize)
 
     def encode_images(self, pixel_values: torch.Tensor, normalize: bool = True) -> torch.Tensor:
         """[B,3,H,W] fp32 (any device) -> [B, proj_dim] fp32 on the GPU; the batched form of
@@ -353,10 +414,7 @@ class B200ClipModel:
         out = torch.empty((b, a.proj_dim), dtype=torch.float32, device=self.device)
         if b == 0:
             return out
-        ws = self._ensure_workspace("text", b)
-        _lib.check(self._lib.clm_encode_text(self._towers["text"], ids.data_ptr(), b, out.data_ptr(),
-                                             int(normalize), ws.data_ptr(), ws.numel(), _lib.cur_stream()),
-                   "clm_encode_text")
+        self._run_tower("text", ids, out, normalize)
         return out
 
     # transformers-4.x style accessors used by the reference (tensor in, tensor out)

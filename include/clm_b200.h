@@ -253,6 +253,11 @@ int clm_cosine_gemv(const float* q_f32, const float* index_f32, int n, int dim, 
 #define CLM_K_MERGE 4
 /* total number of kernels this library has launched in this process */
 unsigned long long clm_launch_count(void);
+/* adds n (may be negative) to the total: the host mirror adds a captured graph's launch count on every
+ * replay (replayed kernels do not pass through the library) and takes the capture pass itself back out */
+void clm_launch_count_add(long long n);
+/* 1 while per-launch timing is on (graph replay is bypassed then, so every launch gets its events) */
+int clm_prof_is_enabled(void);
 /* on != 0: bracket every subsequent launch with CUDA events on its stream (clears old records) */
 int clm_prof_enable(int on);
 /* device-synchronises, then sums the recorded launches of one kind: total ms, the algorithmic

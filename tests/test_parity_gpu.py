@@ -167,6 +167,63 @@ def test_host_inputs_are_streamed_in_chunks(cuda_device):
     assert torch.equal(ref, got2)
 
 
+def test_graph_replay_is_bit_identical_and_counts_its_launches(cuda_device):
+    """A small-batch tower pass runs eagerly once, is then captured into a CUDA graph and replayed: every
+    call returns the eager result bit for bit (also for new input content and new input tensors), the
+    library's launch count grows by the same amount per call, per-launch profiling bypasses the graphs,
+    large batches never use them."""
+    model = O.build_model("tiny-test", seed=0)
+    weights = O.synthetic_lora(model, 8, 16, ["q_proj", "v_proj"], seed=1)
+    gpu = _b200_model("tiny-test", model, weights, 8, 16, ("q_proj", "v_proj"), cuda_device)
+    lib = gpu._lib
+    pv = O.synth_images(9, seed=2).to(cuda_device)
+    pv2 = O.synth_images(9, seed=7).to(cuda_device)
+    ids = O.synth_captions(11, seed=3)[0].to(cuda_device, torch.int32)
+    gpu.use_graphs = False
+    ref_i, ref_t = gpu.encode_images(pv).cpu(), gpu.encode_texts(ids).cpu()
+    ref_i2 = gpu.encode_images(pv2).cpu()
+    gpu.use_graphs = True
+    counts, outs = [], []
+    for _ in range(4):  # eager, capture + replay, replay, replay
+        n0 = lib.clm_launch_count()
+        outs.append((gpu.encode_images(pv).cpu(), gpu.encode_texts(ids).cpu()))
+        counts.append(lib.clm_launch_count() - n0)
+    assert len(gpu._graphs) == 2 and all(e.graph is not None for e in gpu._graphs.values())
+    assert len(set(counts)) == 1 and counts[0] > 0, counts
+    for oi, ot in outs:
+        assert torch.equal(oi, ref_i) and torch.equal(ot, ref_t)
+    assert torch.equal(gpu.encode_images(pv2).cpu(), ref_i2)  # another tensor of the same batch size: same graph
+    assert len(gpu._graphs) == 2
+    big = O.synth_images(gpu.GRAPH_MAX_BATCH + 1, seed=5).to(cuda_device)
+    gpu.encode_images(big); gpu.encode_images(big); gpu.encode_images(big)
+    assert len(gpu._graphs) == 2  # large batches stay eager
+    pv.copy_(pv2)
+    img_eager = _image_launches(gpu, lib, pv)
+    lib.clm_prof_enable(1)
+    try:
+        n0 = lib.clm_launch_count()
+        assert torch.equal(gpu.encode_images(pv).cpu(), ref_i2)
+        assert lib.clm_launch_count() - n0 == img_eager
+        assert len(_lib_records()) == img_eager  # every launch got its events: no replay under profiling
+    finally:
+        lib.clm_prof_enable(0)
+    gpu.set_lora(None)  # rebuilding the towers drops the captured graphs (they point at the old weights)
+    assert len(gpu._graphs) == 0
+
+
+def _lib_records():
+    from clip_lora_match_b200 import _lib
+    return _lib.prof_records()
+
+
+def _image_launches(gpu, lib, pv):
+    gpu.use_graphs = False
+    n0 = lib.clm_launch_count()
+    gpu.encode_images(pv)
+    gpu.use_graphs = True
+    return lib.clm_launch_count() - n0
+
+
 # ------------------------------------------------------------------------------------------
 # search
 # ------------------------------------------------------------------------------------------

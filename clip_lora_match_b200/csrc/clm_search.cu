@@ -106,6 +106,40 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// State of one thread's candidate list (the list itself is in shared memory, element j at sc[j * BM]).
+struct ListState {
+  int cnt, minpos;
+  float thr, published;
+};
+
+// Insert (s, id) into a thread's list of the kc best; once the list is full, track its minimum (the thread's
+// threshold) and publish it to the query's shared bound.  Deliberately NOT inlined: the scan loop tests 32
+// scores per chunk and an inlined copy per score made the epilogue 32x larger than the instruction cache
+// likes (ncu: ~45 % of the warp samples of the Q = 4096 scan sat on instruction fetch after these blocks).
+__device__ __noinline__ ListState list_insert(ListState st, float s, int id, float* my_sc, int32_t* my_id, int kc,
+                                              float* gthr) {
+  int slot = st.minpos;
+  if (st.cnt < kc) slot = st.cnt++;
+  my_sc[slot * BM] = s;
+  my_id[slot * BM] = id;
+  if (st.cnt == kc) {
+    float m = my_sc[0];
+    int mp = 0;
+    for (int j = 1; j < kc; ++j) {
+      const float x = my_sc[j * BM];
+      if (x < m) { m = x; mp = j; }
+    }
+    st.thr = fmaxf(st.thr, m);
+    st.minpos = mp;
+    if (gthr && m > st.published) {  // publish: float max through the integer atomics
+      st.published = m;
+      if (m >= 0.f) atomicMax(reinterpret_cast<int*>(gthr), __float_as_int(m));
+      else atomicMin(reinterpret_cast<unsigned int*>(gthr), __float_as_uint(m));
+    }
+  }
+  return st;
+}
+
 // kCtas = 2: a CTA pair (cluster of 2, cta_group::2) scores 256 queries x 256 index rows per
 // accumulator; each CTA loads its own 128 queries and HALF of the index tile, so the operand bytes
 // pulled from L2 per FLOP drop by a third (the Q >= 256 regime is L2-to-SM-bandwidth bound).
@@ -249,20 +283,21 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const int t0 = static_cast<int>(static_cast<long long>(split) * p.tiles_n / p.splits);
       const int t1 = static_cast<int>(static_cast<long long>(split + 1) * p.tiles_n / p.splits);
       const bool warp_live = q0 + q * 32 < p.nq;  // rows past the last query: nothing to scan
-      int cnt = 0;
-      int minpos = 0;
+      ListState ls;
+      ls.cnt = 0;
+      ls.minpos = 0;
       // thr is a lower bound of this query's kc-th best score over the WHOLE index: the k-th best of
       // any subset of rows qualifies, so every unit publishes its own list minimum (atomic max in
       // global memory) and re-reads the shared bound once per tile.  Units that start after the
       // first wave inherit a nearly final bound and almost never enter the insert path.
       float* gthr = (p.thr_io != nullptr && q0 + r < p.nq) ? p.thr_io + q0 + r : nullptr;
-      float thr = -INFINITY;
-      float published = -INFINITY;
+      ls.thr = -INFINITY;
+      ls.published = -INFINITY;
       for (int t = t0; t < t1; ++t) {
         if (gthr) {
           const float g = __ldcg(gthr);
-          published = fmaxf(published, g);
-          thr = fmaxf(thr, g);
+          ls.published = fmaxf(ls.published, g);
+          ls.thr = fmaxf(ls.thr, g);
         }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -284,31 +319,11 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           float cmax = __uint_as_float(v[0]);
 #pragma unroll
           for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, __uint_as_float(v[i]));
-          if (cmax > thr) {
+          if (cmax > ls.thr) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float s = __uint_as_float(v[i]);
-              if (s > thr) {
-                int slot = minpos;
-                if (cnt < kc) slot = cnt++;
-                my_sc[slot * BM] = s;
-                my_id[slot * BM] = base + i;
-                if (cnt == kc) {
-                  float m = my_sc[0];
-                  int mp = 0;
-                  for (int j = 1; j < kc; ++j) {
-                    const float x = my_sc[j * BM];
-                    if (x < m) { m = x; mp = j; }
-                  }
-                  thr = fmaxf(thr, m);
-                  minpos = mp;
-                  if (gthr && m > published) {  // publish: float max through the integer atomics
-                    published = m;
-                    if (m >= 0.f) atomicMax(reinterpret_cast<int*>(gthr), __float_as_int(m));
-                    else atomicMin(reinterpret_cast<unsigned int*>(gthr), __float_as_uint(m));
-                  }
-                }
-              }
+              if (s > ls.thr) ls = list_insert(ls, s, base + i, my_sc, my_id, kc, gthr);
             }
           }
         }
@@ -325,7 +340,7 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       if (qrow < p.nq) {
         const size_t o = (static_cast<size_t>(qrow) * p.splits + split) * kc;
         for (int j = 0; j < kc; ++j) {
-          const bool ok = j < cnt;
+          const bool ok = j < ls.cnt;
           p.cand_score[o + j] = ok ? my_sc[j * BM] : -INFINITY;
           p.cand_id[o + j] = ok ? my_id[j * BM] : -1;
         }

@@ -52,9 +52,10 @@ struct Workspace {
   size_t total;
 };
 
-Workspace carve(const clm_tower* tw, int batch, uint8_t* base) {
+Workspace carve(const clm_tower* tw, int batch, uint8_t* base, int tokens = 0) {
   const clm_tower_config& c = tw->cfg;
-  const size_t rows = static_cast<size_t>(batch) * c.tokens;
+  if (tokens <= 0) tokens = c.tokens;  // text passes may run on fewer positions than the context length
+  const size_t rows = static_cast<size_t>(batch) * tokens;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     uint8_t* p = base ? base + off : nullptr;
@@ -84,12 +85,12 @@ Workspace carve(const clm_tower* tw, int batch, uint8_t* base) {
   return ws;
 }
 
-int max_batch_for(const clm_tower* tw, size_t bytes, int want) {
-  if (carve(tw, want, nullptr).total <= bytes) return want;
+int max_batch_for(const clm_tower* tw, size_t bytes, int want, int tokens = 0) {
+  if (carve(tw, want, nullptr, tokens).total <= bytes) return want;
   int lo = 0, hi = want;  // largest batch that fits
   while (lo < hi) {
     const int mid = (lo + hi + 1) / 2;
-    if (carve(tw, mid, nullptr).total <= bytes) lo = mid;
+    if (carve(tw, mid, nullptr, tokens).total <= bytes) lo = mid;
     else hi = mid - 1;
   }
   return lo;
@@ -103,9 +104,10 @@ int max_batch_for(const clm_tower* tw, size_t bytes, int want) {
 
 // the transformer layers + pooling + projection + L2 normalise, on rows already embedded in ws.h
 int run_layers(clm_tower* tw, const Workspace& ws, int batch, const int32_t* pool_idx, float* out_emb,
-               int normalize, cudaStream_t s) {
+               int normalize, cudaStream_t s, int tokens = 0) {
   const clm_tower_config& c = tw->cfg;
-  const int rows = batch * c.tokens;
+  if (tokens <= 0) tokens = c.tokens;
+  const int rows = batch * tokens;
   const int D = c.width;
   void* sv = static_cast<void*>(s);
   for (int l = 0; l < c.layers; ++l) {
@@ -118,7 +120,7 @@ int run_layers(clm_tower* tw, const Workspace& ws, int batch, const int32_t* poo
     CLM_TRY(clm_gemm_launch(ws.x, D, L.w_qkv, D, rows, 3 * D, D, lq ? ws.t : nullptr, kLoraCols,
                             lq ? L.lora_b_qkv : nullptr, kLoraCols, lq ? kLoraCols : 0, ws.qkv, 3 * D,
                             CLM_OUT_BF16, L.b_qkv, nullptr, 0, CLM_EPI_NONE, s));
-    CLM_TRY(clm_attention_launch(ws.qkv, ws.ao, batch, c.tokens, c.heads, c.kind == 1, s));
+    CLM_TRY(clm_attention_launch(ws.qkv, ws.ao, batch, tokens, c.heads, c.kind == 1, s));
     const bool lo = c.lora_cols_out > 0 && L.lora_a_o && L.lora_b_o;
     if (lo)
       CLM_TRY(clm_gemm_launch(ws.ao, D, L.lora_a_o, D, rows, kLoraCols, D, nullptr, 0, nullptr, 0, 0,
@@ -132,7 +134,7 @@ int run_layers(clm_tower* tw, const Workspace& ws, int batch, const int32_t* poo
     CLM_TRY(clm_gemm_launch(ws.g, c.mlp, L.w_fc2, c.mlp, rows, D, c.mlp, nullptr, 0, nullptr, 0, 0,
                             ws.h, D, CLM_OUT_F32, L.b_fc2, ws.h, D, CLM_EPI_NONE, s));
   }
-  CLM_TRY(clm_pool_ln(ws.h, pool_idx, tw->w.final_ln_g, tw->w.final_ln_b, ws.pooled, batch, c.tokens,
+  CLM_TRY(clm_pool_ln(ws.h, pool_idx, tw->w.final_ln_g, tw->w.final_ln_b, ws.pooled, batch, tokens,
                       D, c.ln_eps, sv));
   float* proj_out = normalize ? ws.emb : out_emb;
   CLM_TRY(clm_gemm_launch(ws.pooled, D, tw->w.proj_w, D, batch, c.proj_dim, D, nullptr, 0, nullptr,
@@ -217,23 +219,31 @@ extern "C" int clm_encode_image(clm_tower* t, const float* pixel_values, int bat
   return CLM_OK;
 }
 
-extern "C" int clm_encode_text(clm_tower* t, const int32_t* ids, int batch, float* out_emb,
-                               int normalize, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int clm_encode_text_len(clm_tower* t, const int32_t* ids, int batch, int tokens, float* out_emb,
+                                   int normalize, void* workspace, size_t workspace_bytes, void* stream) {
   CLM_REQUIRE(t && t->cfg.kind == 1, "clm_encode_text: not a text tower");
   CLM_REQUIRE(batch >= 0 && (batch == 0 || (ids && out_emb && workspace)),
               "clm_encode_text: null argument");
+  CLM_REQUIRE(tokens >= 1 && tokens <= t->cfg.tokens, "clm_encode_text: tokens=%d must be in [1,%d]", tokens,
+              t->cfg.tokens);
   if (batch == 0) return CLM_OK;
   const clm_tower_config& c = t->cfg;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int mb = max_batch_for(t, workspace_bytes, batch);
+  const int mb = max_batch_for(t, workspace_bytes, batch, tokens);
   CLM_REQUIRE(mb > 0, "clm_encode_text: workspace of %zu bytes too small for one caption (need %zu)",
-              workspace_bytes, carve(t, 1, nullptr).total);
+              workspace_bytes, carve(t, 1, nullptr, tokens).total);
   for (int b0 = 0; b0 < batch; b0 += mb) {
     const int nb = (batch - b0) < mb ? (batch - b0) : mb;
-    Workspace ws = carve(t, nb, static_cast<uint8_t*>(workspace));
-    CLM_TRY(clm_embed_text(ids + static_cast<size_t>(b0) * c.tokens, t->w.tok_emb, t->w.pos_emb, ws.h,
-                           ws.eos, nb, c.tokens, c.width, c.vocab, c.eos_id, s));
-    CLM_TRY(run_layers(t, ws, nb, ws.eos, out_emb + static_cast<size_t>(b0) * c.proj_dim, normalize, s));
+    Workspace ws = carve(t, nb, static_cast<uint8_t*>(workspace), tokens);
+    CLM_TRY(clm_embed_text(ids + static_cast<size_t>(b0) * tokens, t->w.tok_emb, t->w.pos_emb, ws.h,
+                           ws.eos, nb, tokens, c.width, c.vocab, c.eos_id, s));
+    CLM_TRY(run_layers(t, ws, nb, ws.eos, out_emb + static_cast<size_t>(b0) * c.proj_dim, normalize, s, tokens));
   }
   return CLM_OK;
+}
+
+extern "C" int clm_encode_text(clm_tower* t, const int32_t* ids, int batch, float* out_emb,
+                               int normalize, void* workspace, size_t workspace_bytes, void* stream) {
+  CLM_REQUIRE(t && t->cfg.kind == 1, "clm_encode_text: not a text tower");
+  return clm_encode_text_len(t, ids, batch, t->cfg.tokens, out_emb, normalize, workspace, workspace_bytes, stream);
 }

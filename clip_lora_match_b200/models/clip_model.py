@@ -319,18 +319,23 @@ class B200ClipModel:
         graph changes nothing (tools/graph_probe.py, profiles/r1_notes.md)."""
         b = inp.shape[0]
         ws = self._ensure_workspace(kind, b)
-        fn = self._lib.clm_encode_image if kind == "vision" else self._lib.clm_encode_text
         tower = self._towers[kind]
+        tokens = inp.shape[1] if kind == "text" else 0  # a text pass may cover fewer positions than the context
 
         def launch(src: torch.Tensor, dst: torch.Tensor) -> None:
-            _lib.check(fn(tower, src.data_ptr(), b, dst.data_ptr(), int(normalize), ws.data_ptr(), ws.numel(),
-                          _lib.cur_stream()), f"clm_encode_{'image' if kind == 'vision' else 'text'}")
+            if kind == "vision":
+                rc = self._lib.clm_encode_image(tower, src.data_ptr(), b, dst.data_ptr(), int(normalize),
+                                                ws.data_ptr(), ws.numel(), _lib.cur_stream())
+            else:
+                rc = self._lib.clm_encode_text_len(tower, src.data_ptr(), b, tokens, dst.data_ptr(), int(normalize),
+                                                   ws.data_ptr(), ws.numel(), _lib.cur_stream())
+            _lib.check(rc, f"clm_encode_{'image' if kind == 'vision' else 'text'}")
 
         if (not self.use_graphs or b > self.GRAPH_MAX_BATCH or self._lib.clm_prof_is_enabled()
                 or torch.cuda.is_current_stream_capturing()):
             launch(inp, out)
             return
-        key = (kind, b, bool(normalize), ws.data_ptr(), ws.numel())
+        key = (kind, b, tokens, bool(normalize), ws.data_ptr(), ws.numel())
         ent = self._graphs.get(key)
         if ent is None:
             launch(inp, out)  # also performs the kernels' one-time cudaFuncSetAttribute calls outside a capture
@@ -398,23 +403,81 @@ class B200ClipModel:
             self._ev_free[k].record(cur)
         return out
 
-    def encode_texts(self, input_ids: torch.Tensor, normalize: bool = True) -> torch.Tensor:
-        """[B, L<=77] int (right padded or not) -> [B, proj_dim] fp32 on the GPU.  Rows are padded
-        to the context length with EOS (the pooled EOS row of a causal tower does not see the
-        padding: SURVEY.md §8a, encode_text row)."""
+    BUCKET_MIN_BATCH = 64      # below this a text batch is one pass at its longest caption
+    BUCKET_STEP = 16           # bucket tops are multiples of this (the attention kernel's key granularity)
+    BUCKET_MIN_TOKENS = 24576  # rows x positions a pass needs to stay out of the launch-bound regime
+
+    def _bucket_tops(self, lens: torch.Tensor, width: int) -> torch.Tensor:
+        """Per caption, the number of positions its pass covers.  Captions are grouped by length rounded up
+        to BUCKET_STEP; groups are merged upwards until every pass has BUCKET_MIN_TOKENS rows x positions
+        (a pass is ~100 launches: measured, five ~200-row passes are slower than one padded pass)."""
+        step = self.BUCKET_STEP
+        tops = ((lens + step - 1) // step * step).clamp(max=width)
+        levels = sorted(set(tops.tolist()))
+        counts = {t: int((tops == t).sum()) for t in levels}
+        remap, pending, pending_rows = {}, [], 0
+        rows_left = int(tops.numel())
+        for i, t in enumerate(levels):
+            pending.append(t)
+            pending_rows += counts[t]
+            rows_after = rows_left - pending_rows
+            last = i == len(levels) - 1
+            # close the group at t if it is big enough and what remains can still form a big-enough pass
+            if last or (pending_rows * t >= self.BUCKET_MIN_TOKENS and rows_after * levels[-1] >= self.BUCKET_MIN_TOKENS):
+                for p_ in pending:
+                    remap[p_] = t
+                rows_left -= pending_rows
+                pending, pending_rows = [], 0
+        return torch.tensor([remap[t] for t in tops.tolist()], dtype=torch.int64)
+
+    def encode_texts(self, input_ids: torch.Tensor, normalize: bool = True,
+                     lengths: Optional[Union[torch.Tensor, List[int]]] = None, bucket: bool = True) -> torch.Tensor:
+        """[B, L<=77] int (right padded or not) -> [B, proj_dim] fp32 on the GPU.
+
+        `lengths` (host ints, tokens per caption including its EOS -- what the tokenizer's attention_mask
+        sums to; derived here when `input_ids` is a host tensor) lets the batch run **length-bucketed**:
+        rows are grouped by length and every group is encoded on its first `top` positions only.  The text tower is causal and pooled at the first EOS,
+        so positions after it never reach the output (encode_text row), and the reference
+        itself encodes a single caption unpadded (models/clip_model.py:133-138).  Without `lengths` (device
+        ids) or with bucket=False every row runs on all L positions (padded to the context length with EOS
+        if L is shorter).  Pays off when captions are short (one pass at 16 positions instead of 77); on
+        lengths spread over 3..77 it is a wash against the padded pass (profiles/r1_notes.md)."""
         a = self.arch
         if input_ids.dim() != 2 or input_ids.shape[1] > a.context:
             raise ValueError(f"input_ids must be [B, L<={a.context}], got {tuple(input_ids.shape)}")
-        ids = input_ids.to(device=self.device, dtype=torch.int32)
+        if not bucket:
+            lengths = None
+        elif lengths is None and not input_ids.is_cuda and input_ids.shape[0] > 0:
+            # host ids (the tokenizer's output): the lengths are one cheap host pass away
+            is_eos = input_ids == a.eos_id
+            first = is_eos.int().argmax(dim=1) + 1
+            lengths = torch.where(is_eos.any(dim=1), first, torch.full_like(first, input_ids.shape[1]))
+        ids = input_ids.to(device=self.device, dtype=torch.int32, non_blocking=True)
         b, l = ids.shape
-        if l < a.context:
-            pad = torch.full((b, a.context - l), a.eos_id, dtype=torch.int32, device=self.device)
-            ids = torch.cat([ids, pad], dim=1)
-        ids = ids.contiguous()
         out = torch.empty((b, a.proj_dim), dtype=torch.float32, device=self.device)
         if b == 0:
             return out
-        self._run_tower("text", ids, out, normalize)
+        if lengths is not None:
+            lens = torch.as_tensor(lengths, dtype=torch.int64, device="cpu").reshape(-1)
+            if lens.numel() != b:
+                raise ValueError(f"lengths must have one entry per caption ({b}), got {lens.numel()}")
+            lens = lens.clamp(1, l)
+            if b < self.BUCKET_MIN_BATCH:
+                top = int(lens.max())
+                self._run_tower("text", ids[:, :top].contiguous(), out, normalize)
+                return out
+            tops = self._bucket_tops(lens, l)
+            for top in sorted(set(tops.tolist())):
+                rows = torch.nonzero(tops == top).reshape(-1).to(self.device, non_blocking=True)
+                sub = ids.index_select(0, rows)[:, :top].contiguous()
+                sub_out = torch.empty((rows.numel(), a.proj_dim), dtype=torch.float32, device=self.device)
+                self._run_tower("text", sub, sub_out, normalize)
+                out.index_copy_(0, rows, sub_out)
+            return out
+        if l < a.context:
+            pad = torch.full((b, a.context - l), a.eos_id, dtype=torch.int32, device=self.device)
+            ids = torch.cat([ids, pad], dim=1)
+        self._run_tower("text", ids.contiguous(), out, normalize)
         return out
 
     # transformers-4.x style accessors used by the reference (tensor in, tensor out)
@@ -423,11 +486,15 @@ class B200ClipModel:
 
     def get_text_features(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                           **_) -> torch.Tensor:
+        lengths = None
         if attention_mask is not None:
             # positions masked out are padding: replace by EOS so the first-EOS pooling row is kept
             input_ids = torch.where(attention_mask.to(input_ids.device).bool(), input_ids,
                                     torch.full_like(input_ids, self.arch.eos_id))
-        return self.encode_texts(input_ids, normalize=False)
+            m = attention_mask
+            if not m.is_cuda and bool((m[:, 1:] <= m[:, :-1]).all()):  # a host prefix mask (the tokenizer's)
+                lengths = m.sum(dim=1)
+        return self.encode_texts(input_ids, normalize=False, lengths=lengths)
 
 
 # ------------------------------------------------------------------------------------------

@@ -198,6 +198,12 @@ int clm_encode_image(clm_tower* t, const float* pixel_values, int batch, float* 
  * (right padded with eos) -> L2-normalised embeddings fp32 [batch, P]. */
 int clm_encode_text(clm_tower* t, const int32_t* ids, int batch, float* out_emb,
                     int normalize, void* workspace, size_t workspace_bytes, void* stream);
+/* The same on the first `tokens` <= context positions only: ids int32 [batch, tokens], every row's first
+ * eos inside.  The text tower is causal and pooled at the first eos (modeling_clip.py:546-557,577-584), so
+ * positions after it never reach the output; the reference itself encodes a single caption unpadded
+ * (models/clip_model.py:133-138).  Lets the host mirror run length-bucketed batches. */
+int clm_encode_text_len(clm_tower* t, const int32_t* ids, int batch, int tokens, float* out_emb,
+                        int normalize, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Search: similarity GEMM with fused per-tile top-k, merge, exact fp32 re-score

@@ -211,6 +211,11 @@ def _attn_ref(qkv, batch, tokens, heads, causal):
     (3, 129, 4, False),   # 128 + 1: extra-token path (CUDA-core key / query row) with two S + two O regions
     (40, 257, 8, False),  # ViT-L/14 extra-token path, 320 items on 148 SMs: stage reuse across items
     (37, 197, 12, False), # ViT-B/16, three items per CTA (stage / TMEM parity wrap-around)
+    (7, 16, 8, True),     # length-bucketed text passes: causal at every bucket top
+    (5, 32, 8, True),
+    (4, 48, 12, True),
+    (3, 64, 8, True),
+    (300, 16, 8, True),   # many short captions: 2400 items
 ])
 def test_attention(cuda_device, batch, tokens, heads, causal):
     D = heads * 64

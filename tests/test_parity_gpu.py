@@ -167,6 +167,40 @@ def test_host_inputs_are_streamed_in_chunks(cuda_device):
     assert torch.equal(ref, got2)
 
 
+def test_length_bucketed_text_batches_match_the_padded_pass(cuda_device):
+    """Host ids (or host lengths) make encode_texts run every caption on the first multiple-of-16 positions
+    that hold it; the embeddings are those of the padded 77-position pass (and of the oracle) because the
+    causal tower never looks right of the pooled EOS row."""
+    model = O.build_model("tiny-test", seed=0)
+    weights = O.synthetic_lora(model, 8, 16, ["q_proj", "v_proj"], seed=1)
+    gpu = _b200_model("tiny-test", model, weights, 8, 16, ("q_proj", "v_proj"), cuda_device)
+    ids, mask = O.synth_captions(200, seed=3)
+    ref = O.encode_texts(model, ids, mask)
+    padded = gpu.encode_texts(ids.to(cuda_device)).cpu()              # device ids, no lengths: one 77-wide pass
+    lib = gpu._lib
+    n0 = lib.clm_launch_count()
+    one_pass = gpu.encode_texts(ids).cpu()                             # 200 short rows: merged into one pass
+    per_pass = lib.clm_launch_count() - n0
+    gpu.BUCKET_MIN_TOKENS = 1024                                       # force real buckets on this small batch
+    tops = gpu._bucket_tops(mask.sum(dim=1), 77)
+    assert len(set(tops.tolist())) >= 4 and bool((tops >= mask.sum(dim=1)).all())
+    n0 = lib.clm_launch_count()
+    bucketed = gpu.encode_texts(ids).cpu()                             # host ids: lengths derived, bucketed
+    assert lib.clm_launch_count() - n0 == per_pass * len(set(tops.tolist()))
+    assert torch.allclose(one_pass, padded, atol=2e-3)
+    with_len = gpu.encode_texts(ids.to(cuda_device), lengths=mask.sum(dim=1)).cpu()
+    small = gpu.encode_texts(ids[:9]).cpu()                            # below BUCKET_MIN_BATCH: one pass at the longest
+    via_mask = gpu.get_text_features(ids, attention_mask=mask).cpu()
+    _assert_parity("bucketed text", bucketed, ref)
+    for name, got in (("bucketed", bucketed), ("with lengths", with_len)):
+        assert torch.allclose(got, padded, atol=2e-3), f"{name}: max diff {float((got - padded).abs().max())}"
+        m = O.parity_metrics(got, padded)
+        assert m["cos_min"] >= 0.99999, (name, m)
+    assert torch.allclose(small, padded[:9], atol=2e-3)
+    raw = gpu.encode_texts(ids.to(cuda_device), normalize=False).cpu()
+    assert O.parity_metrics(via_mask, raw)["cos_min"] >= 0.99999
+
+
 def test_graph_replay_is_bit_identical_and_counts_its_launches(cuda_device):
     """A small-batch tower pass runs eagerly once, is then captured into a CUDA graph and replayed: every
     call returns the eager result bit for bit (also for new input content and new input tensors), the

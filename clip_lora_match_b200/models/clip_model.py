@@ -463,7 +463,8 @@ class B200ClipModel:
                 raise ValueError(f"lengths must have one entry per caption ({b}), got {lens.numel()}")
             lens = lens.clamp(1, l)
             if b < self.BUCKET_MIN_BATCH:
-                top = int(lens.max())
+                step = self.BUCKET_STEP  # multiples of 16 only: few distinct shapes (and CUDA graphs) per batch size
+                top = min(l, (int(lens.max()) + step - 1) // step * step)
                 self._run_tower("text", ids[:, :top].contiguous(), out, normalize)
                 return out
             tops = self._bucket_tops(lens, l)

@@ -464,8 +464,11 @@ class B200ClipModel:
             lens = lens.clamp(1, l)
             if b < self.BUCKET_MIN_BATCH:
                 step = self.BUCKET_STEP  # multiples of 16 only: few distinct shapes (and CUDA graphs) per batch size
-                top = min(l, (int(lens.max()) + step - 1) // step * step)
-                self._run_tower("text", ids[:, :top].contiguous(), out, normalize)
+                top = min(a.context, (int(lens.max()) + step - 1) // step * step)
+                sub = ids[:, :min(top, l)]
+                if top > l:  # ids narrower than the pass (tokenizer padded to the longest caption): pad with EOS
+                    sub = torch.cat([sub, torch.full((b, top - l), a.eos_id, dtype=torch.int32, device=self.device)], dim=1)
+                self._run_tower("text", sub.contiguous(), out, normalize)
                 return out
             tops = self._bucket_tops(lens, l)
             for top in sorted(set(tops.tolist())):

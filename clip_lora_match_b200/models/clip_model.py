@@ -306,6 +306,7 @@ class B200ClipModel:
         return self._workspace
 
     H2D_CHUNK = 256  # images per host->device chunk when the input lives in host memory
+    H2D_FIRST_CHUNK = 64  # ... except the first, whose copy is exposed
     MAX_GRAPHS = 16
     GRAPH_MAX_BATCH = 32
 
@@ -391,9 +392,14 @@ class B200ClipModel:
         cur = torch.cuda.current_stream(self.device)
         for k in range(2):
             self._ev_free[k].record(cur)  # both staging buffers are free as of now on this stream
-        for i, b0 in enumerate(range(0, b, cs)):
+        # the first chunk's copy cannot hide behind compute, so it is a small one
+        bounds, b0 = [], 0
+        while b0 < b:
+            n = min(min(self.H2D_FIRST_CHUNK, cs) if b0 == 0 else cs, b - b0)
+            bounds.append((b0, n))
+            b0 += n
+        for i, (b0, n) in enumerate(bounds):
             k = i & 1
-            n = min(cs, b - b0)
             self._copy_stream.wait_event(self._ev_free[k])
             with torch.cuda.stream(self._copy_stream):
                 self._stage[k][:n].copy_(src[b0:b0 + n], non_blocking=True)

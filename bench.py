@@ -396,7 +396,16 @@ def main():
                "kernel_ms_per_step": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                                           "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1)}
                                       for k, v in prof_l.items()}}
-        del model_l, pv_l
+        # configs[4] (seeker -> finder): the query side encodes 4096-caption batches with the ViT-L/14 text tower
+        ids_q = O.synth_captions(QUERY_BATCH, seed=7)[0].to(dev, torch.int32)  # the same batch on every rank
+        for _ in range(2):
+            model_l.encode_texts(ids_q)
+        ms_q = timed(lambda: model_l.encode_texts(ids_q), args.steps)
+        l14["text_queries_per_s_per_gpu"] = QUERY_BATCH * args.steps / (ms_q / 1e3)
+        l14["text_query_batch"] = QUERY_BATCH
+        del pv_l
+        if args.no_search:
+            del model_l, ids_q
         torch.cuda.empty_cache()
 
     # ---- search: top-10 over the row-sharded 10M x 768 index ----------------------------
@@ -466,6 +475,35 @@ def main():
                              "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "scan_ms": p64["ms"] / n64,
                              "bytes_per_scan": p64["bytes"] / n64, "queries": 64},
         }
+        # configs[4]: top-50 over the same index (the seeker path's k) ...
+        for _ in range(2):
+            idx.search_batch(q, top_k=50)
+        ms_50 = timed(lambda: idx.search_batch(q, top_k=50), args.steps)
+        search["top50"] = {"value": QUERY_BATCH * args.steps / (ms_50 / 1e3), "unit": "queries/s", "k": 50,
+                           "ms_per_batch": ms_50 / args.steps}
+        # ... and the whole seeker -> finder step, timed as one: every rank encodes ITS block of the 4096-caption
+        # query batch with the ViT-L/14+LoRA text tower (data parallel), one all_gather rebuilds the [Q, 768]
+        # query matrix, then the row-sharded top-50 search (local scan + all_gather of Q x 50 pairs + merge)
+        if l14 is not None:
+            from clip_lora_match_b200.src.embedding.search import allgather_rows
+
+            qlo, qhi = shard_bounds(QUERY_BATCH, rank, world)
+            ids_mine = ids_q[qlo:qhi].contiguous()
+
+            def seeker_step():
+                emb = model_l.encode_texts(ids_mine)
+                if world > 1:
+                    emb = allgather_rows(emb, QUERY_BATCH)
+                res["s50"], res["i50"] = idx.search_batch(emb, top_k=50)
+
+            for _ in range(2):
+                seeker_step()
+            ms_sk = timed(seeker_step, args.steps)
+            search["seeker_config5"] = {
+                "value": QUERY_BATCH * args.steps / (ms_sk / 1e3), "unit": "queries/s", "ms_per_batch": ms_sk / args.steps,
+                "what": "configs[4]: ViT-L/14+LoRA text encode of a 4096-query batch (split over the ranks, one "
+                        "all_gather of the embeddings) + top-50 over the row-sharded 10M x 768 index, one timed step"}
+            del model_l, ids_q
         del idx
         torch.cuda.empty_cache()
 

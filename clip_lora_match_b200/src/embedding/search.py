@@ -71,6 +71,31 @@ def gather_shard_topk(scores: Optional[torch.Tensor], ids: Optional[torch.Tensor
     return torch.stack(all_s, dim=1).contiguous(), torch.stack(all_i, dim=1).contiguous()
 
 
+def allgather_rows(local: torch.Tensor, total_rows: int, group=None) -> torch.Tensor:
+    """Query-side data parallelism of the seeker path (BASELINE configs[4]): rank r encodes queries
+    shard_bounds(Q, r, world) of a batch and this gathers the [Q, d] embedding matrix on every rank, so the
+    encoder work of a query batch is split over the GPUs instead of being replicated.  One all_gather of
+    ceil(Q / world) * d floats per rank (1.6 MB at Q = 4096, d = 768 on 8 GPUs); blocks are padded to equal
+    size for the collective and trimmed afterwards."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = shard_bounds(total_rows, rank, world)
+    if local.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} must hold rows {lo}..{hi} ({hi - lo}), got {local.shape[0]}")
+    per = (total_rows + world - 1) // world
+    buf = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[: hi - lo] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    rows = []
+    for r, part in enumerate(parts):
+        rlo, rhi = shard_bounds(total_rows, r, world)
+        rows.append(part[: rhi - rlo])
+    return torch.cat(rows, dim=0)
+
+
 class TextSearchIndex:
     def __init__(self, index_path: Optional[Union[str, Path]] = None, *,
                  embeddings: Optional[torch.Tensor] = None, image_paths: Optional[list] = None,

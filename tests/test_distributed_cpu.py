@@ -62,3 +62,33 @@ def test_sharded_search_two_ranks_matches_unsharded():
 def test_sharded_search_shard_smaller_than_k():
     # 5 rows over 2 ranks: shards of 2 and 3 rows, k=4 > shard size -> padded payload
     _run(n=5, d=32, nq=3, k=4)
+
+
+def _gather_worker(rank, world, port, total, d, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from clip_lora_match_b200.src.embedding.search import allgather_rows, shard_bounds
+
+        full = O.synth_unit_rows(total, d, 11)
+        lo, hi = shard_bounds(total, rank, world)
+        got = allgather_rows(full[lo:hi].clone(), total)
+        bad = False
+        try:
+            allgather_rows(full[lo:hi + 1].clone(), total) if hi < total else allgather_rows(full[lo:hi - 1].clone(), total)
+        except ValueError:
+            bad = True
+        ret[rank] = bool(torch.equal(got, full)) and bad
+    finally:
+        dist.destroy_process_group()
+
+
+def test_query_rows_are_split_over_ranks_and_gathered_back():
+    """Seeker path, query side: each rank encodes its block of the query batch; allgather_rows rebuilds the
+    [Q, d] matrix on every rank (uneven split: 7 rows over 2 ranks), and rejects a block of the wrong size."""
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gather_worker, args=(2, port, 7, 16, ret), nprocs=2, join=True)
+    assert all(ret.get(r) for r in range(2)), dict(ret)

@@ -422,17 +422,14 @@ class B200ClipModel:
         levels = sorted(set(tops.tolist()))
         counts = {t: int((tops == t).sum()) for t in levels}
         remap, pending, pending_rows = {}, [], 0
-        rows_left = int(tops.numel())
         for i, t in enumerate(levels):
             pending.append(t)
             pending_rows += counts[t]
-            rows_after = rows_left - pending_rows
-            last = i == len(levels) - 1
-            # close the group at t if it is big enough and what remains can still form a big-enough pass
-            if last or (pending_rows * t >= self.BUCKET_MIN_TOKENS and rows_after * levels[-1] >= self.BUCKET_MIN_TOKENS):
+            # close the group at t once it is big enough; smaller groups ride along with the next longer one
+            # (the last group is served as it is: a short launch-bound pass costs less than lengthening the rest)
+            if i == len(levels) - 1 or pending_rows * t >= self.BUCKET_MIN_TOKENS:
                 for p_ in pending:
                     remap[p_] = t
-                rows_left -= pending_rows
                 pending, pending_rows = [], 0
         return torch.tensor([remap[t] for t in tops.tolist()], dtype=torch.int64)
 

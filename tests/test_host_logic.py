@@ -203,3 +203,24 @@ def test_shard_bounds_partition_rows():
         sizes = [hi - lo for lo, hi in spans]
         assert max(sizes) - min(sizes) <= 1
     assert shard_bounds(10_000_000, 3, 8) == (3_750_000, 5_000_000)
+
+
+def test_text_length_buckets_cover_every_caption_and_merge_small_groups():
+    """encode_texts' bucket policy (host logic, no GPU): every caption's pass is at least as long as the caption,
+    a multiple of 16 positions (or the full width), and groups too small to leave the launch-bound regime are
+    merged upwards."""
+    import torch
+
+    from clip_lora_match_b200.models.clip_model import B200ClipModel as M
+
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(3, 78, (1024,), generator=g)
+    tops = M._bucket_tops(M, lens, 77)
+    assert bool((tops >= lens).all()) and set(tops.tolist()) <= {16, 32, 48, 64, 77}
+    for t in sorted(set(tops.tolist()))[:-1]:  # every pass but the last is out of the launch-bound regime
+        assert int((tops == t).sum()) * t >= M.BUCKET_MIN_TOKENS
+    assert set(M._bucket_tops(M, torch.full((4096,), 12), 77).tolist()) == {16}          # uniformly short: one short pass
+    assert set(M._bucket_tops(M, torch.randint(3, 78, (100,), generator=g), 77).tolist()) == {77}  # too few rows to split
+    ragged = torch.tensor([5] * 3000 + [77] * 2)   # a tiny tail group is still served (at the full width)
+    tr = M._bucket_tops(M, ragged, 77)
+    assert bool((tr >= ragged).all()) and set(tr[:3000].tolist()) == {16} and set(tr[3000:].tolist()) == {77}

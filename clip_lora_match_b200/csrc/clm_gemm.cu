@@ -551,10 +551,26 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
     force_1cta = (e && e[0] == '1') ? 1 : 0;
   }
   // CTA-pair kernel for the big GEMMs; single-CTA kernel for narrow / ragged N and tiny M
-  const bool pair = !force_1cta && (N % 256 == 0) && (M > 128);
-  const int BN = pair ? 256
-                      : ((N >= 256 && N % 256 == 0) ? 256
-                         : ((N >= 128 && N % 128 == 0) ? 128 : (N > 128 ? 256 : (N > 64 ? 128 : 64))));
+  bool pair = !force_1cta && (N % 256 == 0) && (M > 128);
+  int BN = pair ? 256
+                : ((N >= 256 && N % 256 == 0) ? 256
+                   : ((N >= 128 && N % 128 == 0) ? 128 : (N > 128 ? 256 : (N > 64 ? 128 : 64))));
+  // Small M (the reference's one-item-at-a-time calls: 197 or 77 rows): a grid of 256-wide tiles would leave
+  // most SMs idle and every tile walks the whole K loop, so take the narrowest tile that divides N until at
+  // least half of the SMs have one.  Launch-bound regime: what counts is the latency of one tile.
+  {
+    const long long sms = clm_num_sms();
+    const long long tiles_now = pair ? static_cast<long long>((M + 255) / 256) * (N / 256)
+                                     : static_cast<long long>((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    if (tiles_now * (pair ? 2 : 1) * 2 <= sms) {
+      for (int bn : {256, 128, 64}) {
+        if (N % bn != 0) continue;
+        pair = false;
+        BN = bn;
+        if (static_cast<long long>((M + BM - 1) / BM) * (N / bn) * 2 >= sms) break;
+      }
+    }
+  }
   const int b_box_rows = pair ? BN / 2 : BN;
   CUtensorMap ma, mb, ma2, mb2;
   int rc;

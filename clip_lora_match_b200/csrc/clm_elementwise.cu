@@ -235,20 +235,34 @@ im2col_kernel(const float* __restrict__ pix, __nv_bfloat16* __restrict__ out, in
   const int gx = static_cast<int>(prow % grid_w);
   const int gy = static_cast<int>((prow / grid_w) % grid_w);
   const int b = static_cast<int>(prow / (grid_w * grid_w));
+  // one division per thread, not per element: (channel, patch row, patch column) of the chunk's first column,
+  // then walk; a patch width that is a multiple of 8 never wraps inside a chunk and loads two aligned float4
   float f[8];
+  const int pp = patch * patch;
+  int col = chunk * 8;
+  int c = col / pp;
+  const int rem = col - c * pp;
+  int py = rem / patch;
+  int px = rem - py * patch;
+  auto row_ptr = [&](int cc, int yy) {
+    return pix + ((static_cast<size_t>(b) * 3 + cc) * image + (gy * patch + yy)) * image + gx * patch;
+  };
+  if ((patch & 7) == 0 && (image & 3) == 0 && (reinterpret_cast<uintptr_t>(pix) & 15) == 0 && col + 8 <= k) {
+    const float4* src = reinterpret_cast<const float4*>(row_ptr(c, py) + px);
+    const float4 lo = __ldg(src), hi = __ldg(src + 1);
+    f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w;
+    f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+  } else {
+    const float* base = (col < k) ? row_ptr(c, py) : pix;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int col = chunk * 8 + i;
-    float val = 0.f;
-    if (col < k) {
-      const int c = col / (patch * patch);
-      const int rem = col - c * patch * patch;
-      const int py = rem / patch;
-      const int px = rem - py * patch;
-      val = pix[((static_cast<size_t>(b) * 3 + c) * image + (gy * patch + py)) * image +
-                (gx * patch + px)];
+    for (int i = 0; i < 8; ++i) {
+      f[i] = (col + i < k) ? __ldg(base + px) : 0.f;
+      if (++px == patch) {
+        px = 0;
+        if (++py == patch) { py = 0; ++c; }
+        if (col + i + 1 < k) base = row_ptr(c, py);
+      }
     }
-    f[i] = val;
   }
   uint4 o;
   o.x = pack_bf16x2(f[0], f[1]);

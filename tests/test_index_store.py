@@ -121,3 +121,68 @@ def test_two_rank_data_parallel_build(tmp_path):
     assert [tuple(s["order"]) for s in man["shards"]] == [(0, 0), (0, 1), (1, 0), (1, 1)]
     e, _, _ = IS.load_rows(tmp_path / "idx", 0, 1001)
     assert torch.equal(e, _rows(1001, 24, 7))
+
+
+# ------------------------------------------------------------------------------------------
+# the other two index writers of the reference (host logic; the encoder is a stub here)
+# ------------------------------------------------------------------------------------------
+def _stub_encode(texts):
+    g = torch.Generator().manual_seed(len(texts))
+    return torch.randn((len(texts), 8), generator=g) * 3.0   # not unit length on purpose
+
+
+def test_build_custom_index_keeps_the_reference_column_quirk(tmp_path):
+    """scripts/build_custom_index.py: header `image_path,text` over three-field rows read with index_col=0 ->
+    index = image path, 'image_path' = description, 'text' = location; caption = "<description>, <location>";
+    singular metadata keys; unit rows; the reference's errors."""
+    from clip_lora_match_b200.scripts.build_custom_index import build_custom_index, read_custom_csv
+    from clip_lora_match_b200.src.embedding.search import TextSearchIndex  # noqa: F401  (import check only)
+
+    csv = tmp_path / "my_items.csv"
+    csv.write_text("image_path,text\n"
+                   "data/custom/images/a.jpg,Kaca mata pink, ditemukan di gk 1.\n"
+                   "data/custom/images/b.jpg,Tas ransel hitam, ditemukan di aula gedung f.\n")
+    paths, texts = read_custom_csv(csv)
+    assert paths == ["data/custom/images/a.jpg", "data/custom/images/b.jpg"]
+    assert texts == ["Kaca mata pink,  ditemukan di gk 1.", "Tas ransel hitam,  ditemukan di aula gedung f."]
+    out = tmp_path / "idx" / "custom_items_index.pt"
+    emb = build_custom_index(csv, out, _stub_encode, log=lambda m: None)
+    obj = torch.load(out)
+    assert set(obj) == {"embeddings", "image_path", "text"}
+    assert obj["image_path"] == paths and obj["text"] == texts
+    assert torch.allclose(obj["embeddings"].norm(dim=-1), torch.ones(2), atol=1e-6) and torch.equal(obj["embeddings"], emb)
+    with pytest.raises(FileNotFoundError):
+        read_custom_csv(tmp_path / "nope.csv")
+    bad = tmp_path / "bad.csv"
+    bad.write_text("path,caption\nx,y,z\n")
+    with pytest.raises(ValueError):
+        read_custom_csv(bad)
+    empty = tmp_path / "empty.csv"
+    empty.write_text("image_path,text\n")
+    with pytest.raises(ValueError):
+        read_custom_csv(empty)
+
+
+def test_rebuild_index_orders_by_id_and_writes_plural_keys(tmp_path):
+    """scripts/rebuild_index.py: items in id order, plural metadata keys (the spelling FinderService reads),
+    nothing written for an empty table, records may be dicts or attribute objects."""
+    from types import SimpleNamespace
+
+    from clip_lora_match_b200.scripts.rebuild_index import read_items_jsonl, rebuild_index
+
+    items = [SimpleNamespace(id=3, description="tas pink", image_path="c.jpg"),
+             {"id": 1, "description": "kaca mata", "image_path": "a.jpg"},
+             SimpleNamespace(id=2, description="sepatu", image_path="b.jpg")]
+    out = tmp_path / "index.pt"
+    emb = rebuild_index(items, out, _stub_encode, log=lambda m: None)
+    obj = torch.load(out)
+    assert set(obj) == {"embeddings", "image_paths", "texts"}
+    assert obj["image_paths"] == ["a.jpg", "b.jpg", "c.jpg"] and obj["texts"] == ["kaca mata", "sepatu", "tas pink"]
+    assert torch.allclose(obj["embeddings"].norm(dim=-1), torch.ones(3), atol=1e-6) and emb.shape == (3, 8)
+    none_out = tmp_path / "none.pt"
+    assert rebuild_index([], none_out, _stub_encode, log=lambda m: None) is None and not none_out.exists()
+    dump = tmp_path / "items.jsonl"
+    dump.write_text('{"id": 2, "description": "b", "image_path": "b.png"}\n\n{"id": 1, "description": "a", "image_path": "a.png"}\n')
+    assert [r["id"] for r in read_items_jsonl(dump)] == [2, 1]
+    with pytest.raises(FileNotFoundError):
+        read_items_jsonl(tmp_path / "missing.jsonl")

@@ -186,3 +186,51 @@ def test_rebuild_index_orders_by_id_and_writes_plural_keys(tmp_path):
     assert [r["id"] for r in read_items_jsonl(dump)] == [2, 1]
     with pytest.raises(FileNotFoundError):
         read_items_jsonl(tmp_path / "missing.jsonl")
+
+
+def test_finder_service_report_item_appends_like_the_reference(tmp_path):
+    """src/embedding/finder_service.py mirror (host logic; stub text encoder): the image is copied into
+    upload_dir, only the caption "<description>, ditemukan di <location>" is embedded, the one-file index
+    grows by load-cat-save with the plural keys, a directory index grows by one shard per report, both stay
+    readable row for row; errors as the reference."""
+    from datetime import datetime
+
+    from clip_lora_match_b200.src.embedding.finder_service import FinderConfig, FinderService
+
+    root = tmp_path / "svc"
+    (root / "incoming").mkdir(parents=True)
+    img = root / "incoming" / "tas-pink.jpg"
+    img.write_bytes(b"\xff\xd8not-a-real-jpeg")
+    seen = []
+
+    def enc(text):
+        seen.append(text)
+        g = torch.Generator().manual_seed(len(seen))
+        return torch.randn((8,), generator=g) * 2.0
+
+    ids = iter([41, 42])
+    for index_path in (root / "data" / "index" / "custom_items_index.pt", root / "data" / "index" / "sharded"):
+        seen.clear()
+        cfg = FinderConfig(root_dir=root, clip_config_path=root / "none.yaml", lora_dir=root / "none",
+                           index_path=index_path, upload_dir=root / "data" / "reported" / "images")
+        svc = FinderService(cfg, encode_fn=enc, on_item=(lambda rec: next(ids)) if index_path.suffix else None)
+        r1 = svc.report_item(img, "tas pink kanken", location="lab iot", reporter="ani",
+                             found_at=datetime(2025, 1, 2, 3, 4, 5))
+        r2 = svc.report_item(img, "kaca mata pink")
+        assert (cfg.upload_dir / "tas-pink.jpg").read_bytes() == img.read_bytes()
+        assert r1["image_path"] == "data/reported/images/tas-pink.jpg" and r1["location"] == "lab iot"
+        assert r1["description"] == "tas pink kanken, ditemukan di lab iot" and r2["description"] == "kaca mata pink"
+        assert r1["found_at"] == "2025-01-02T03:04:05" and r1["reporter"] == "ani" and r2["found_at"] is not None
+        assert (r1["id"], r2["id"]) == ((41, 42) if index_path.suffix else (1, 2))
+        assert seen == ["tas pink kanken, ditemukan di lab iot", "kaca mata pink"]   # the TEXT is what is embedded
+        if index_path.suffix:
+            obj = torch.load(index_path)
+            assert set(obj) == {"embeddings", "image_paths", "texts"}
+            emb, paths, texts = obj["embeddings"], obj["image_paths"], obj["texts"]
+        else:
+            assert IS.read_manifest(index_path)["rows"] == 2 and len(IS.scan_shards(index_path)) == 2
+            emb, paths, texts = IS.load_rows(index_path, 0, 2)
+        assert emb.shape == (2, 8) and torch.allclose(emb.norm(dim=-1), torch.ones(2), atol=1e-6)
+        assert paths == ["data/reported/images/tas-pink.jpg"] * 2 and texts == seen
+        with pytest.raises(FileNotFoundError):
+            svc.report_item(root / "incoming" / "missing.png", "x")

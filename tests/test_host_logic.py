@@ -224,3 +224,16 @@ def test_text_length_buckets_cover_every_caption_and_merge_small_groups():
     ragged = torch.tensor([5] * 3000 + [77] * 2)   # a tiny tail group is still served (at the full width)
     tr = M._bucket_tops(M, ragged, 77)
     assert bool((tr >= ragged).all()) and set(tr[:3000].tolist()) == {16} and set(tr[3000:].tolist()) == {77}
+
+
+@pytest.mark.parametrize("name", ["build_text_index", "build_custom_index", "rebuild_index", "build_image_index",
+                                  "demo_search_text", "demo_search_image", "demo_seeker", "demo_finder_report"])
+def test_every_script_mirror_imports_and_parses_its_arguments(name):
+    """The reference's scripts have hard-coded paths; the mirrors take them as arguments.  Importing a script
+    must not need a GPU, and --help must describe it."""
+    import importlib
+
+    mod = importlib.import_module(f"clip_lora_match_b200.scripts.{name}")
+    with pytest.raises(SystemExit) as e:
+        mod.main(["--help"])
+    assert e.value.code == 0

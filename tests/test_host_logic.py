@@ -237,3 +237,25 @@ def test_every_script_mirror_imports_and_parses_its_arguments(name):
     with pytest.raises(SystemExit) as e:
         mod.main(["--help"])
     assert e.value.code == 0
+
+
+def test_built_library_contains_tcgen05_and_tma_sass():
+    """The hot kernels are tcgen05/TMEM + TMA code, not mma.sync recompiled: the built sm_100a library must
+    carry the SASS mnemonics of /opt/skills/guides/B200_PROFILING.md (tcgen05.mma -> UTC*MMA incl. the
+    cta_group::2 form, tcgen05.ld/st -> LDTM/STTM, TMA loads / stores / reduce-add -> UTMALDG / UTMASTG /
+    UTMAREDG) and no legacy tensor-core instruction."""
+    import shutil
+    import subprocess
+
+    from clip_lora_match_b200 import _lib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    _lib.load()
+    sass = subprocess.run([cuobjdump, "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG.2D", "UTMALDG.2D.2CTA", "UTMASTG.2D",
+                     "UTMAREDG.2D.ADD", "UTCBAR"):
+        assert mnemonic in sass, f"{mnemonic} missing from the built library"
+    assert not re.search(r"\bHMMA\.", sass) and "WGMMA" not in sass

@@ -259,3 +259,30 @@ def test_built_library_contains_tcgen05_and_tma_sass():
                      "UTMAREDG.2D.ADD", "UTCBAR"):
         assert mnemonic in sass, f"{mnemonic} missing from the built library"
     assert not re.search(r"\bHMMA\.", sass) and "WGMMA" not in sass
+
+
+def test_extra_token_attention_decomposition_is_exact_softmax_attention():
+    """The ViT-L/14 attention plan (csrc/clm_attention.cu, T = 128k + 1) restated in torch: tensor cores take the
+    256 x 256 block (P rounded to bf16), the class token's key enters each row through one dot product (row max,
+    row sum, rank-1 update of O in fp32) and its query row is a separate fp32 row.  Same result as plain softmax
+    attention to bf16-P accuracy: the decomposition itself loses nothing."""
+    g = torch.Generator().manual_seed(0)
+    T, d = 257, 64
+    q, k, v = (torch.randn((T, d), generator=g).bfloat16().float() * 1.5 for _ in range(3))
+    ref = torch.softmax((q @ k.T) * 0.125, dim=-1) @ v
+    Tk = T - 1
+    c = 0.125 * 1.4426950408889634
+    s_main = q[:Tk] @ k[:Tk].T                       # S = Q K^T on the tensor cores
+    s_x = q[:Tk] @ k[Tk]                             # the extra key: one dot product per row
+    m = torch.maximum(s_main.max(dim=-1).values, s_x)
+    p_main = torch.exp2((s_main - m[:, None]) * c)
+    p_x = torch.exp2((s_x - m) * c)
+    denom = p_main.sum(dim=-1) + p_x                 # the row sum is taken in fp32, before P is rounded
+    o = p_main.bfloat16().float() @ v[:Tk] + p_x[:, None] * v[Tk][None, :]   # P V (bf16 P) + rank-1 update
+    out_main = o / denom[:, None]
+    s_t = q[Tk] @ k.T                                # the extra query row, fp32 throughout
+    p_t = torch.exp2((s_t - s_t.max()) * c)
+    out_tail = (p_t @ v) / p_t.sum()
+    out = torch.cat([out_main, out_tail[None, :]], dim=0)
+    assert torch.allclose(out, ref, atol=6e-3, rtol=0)
+    assert torch.allclose(out[Tk], ref[Tk], atol=1e-5)   # the tail row has no bf16 rounding at all

@@ -6,6 +6,7 @@ caller gets an exception.  torch is used only to hold device memory and streams.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional
 
@@ -103,11 +104,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    lib_path = Path(os.environ["CLM_LIB_PATH"]) if os.environ.get("CLM_LIB_PATH") else LIB_PATH  # A/B runs of two builds
+    if not lib_path.exists():
         raise ClmError(
-            f"{LIB_PATH} is missing: build it with `python -m clip_lora_match_b200.build` "
+            f"{lib_path} is missing: build it with `python -m clip_lora_match_b200.build` "
             "(there is no CPU or PyTorch fallback for this path)")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(lib_path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -44,6 +44,21 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
 
 
+def synth_captions(batch, seed=3, context=77, bos=49406, eos=49407):
+    """SURVEY.md §8(d) captions: ids [B,77] = [BOS, tok..., EOS, EOS...], tok ~ U[0,49405], length ~ U{3..77};
+    mask = pos < length.  (Same generator as the oracle's, restated here so the B200 arm imports nothing
+    from oracle/.)"""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    lengths = torch.randint(3, context + 1, (batch,), generator=g)
+    ids = torch.randint(0, bos, (batch, context), generator=g)
+    pos = torch.arange(context).unsqueeze(0)
+    ids[:, 0] = bos
+    ids = torch.where(pos >= (lengths - 1).unsqueeze(1), torch.full_like(ids, eos), ids)
+    return ids, (pos < lengths.unsqueeze(1)).long()
+
+
 def flops_per_item(T, D, L, M, P, r, n_lora, patch_k=0, np_=0):
     """L(8TD^2 + 4TDM + 4T^2D + n_lora 4TDr) + 2 Np 3P^2 D + 2DP."""
     return L * (8 * T * D * D + 4 * T * D * M + 4 * T * T * D + n_lora * 4 * T * D * r) + \
@@ -254,9 +269,7 @@ def main():
     model.set_lora(lora)
     g = torch.Generator(device=dev).manual_seed(2 + rank)
     pv = torch.randn((BATCH, 3, 224, 224), generator=g, device=dev)
-    from oracle import clip_oracle as O  # synthetic caption generator only (§8d), not timed
-
-    ids_cpu, mask_cpu = O.synth_captions(BATCH, seed=3 + rank)
+    ids_cpu, mask_cpu = synth_captions(BATCH, seed=3 + rank)
     ids = ids_cpu.to(dev, torch.int32)
     # Every caption is encoded on all 77 positions (SURVEY.md §8d counts a caption as a 77-token problem), so
     # no position is skipped in the timed region.  CLM_BENCH_BUCKETED_TEXT=1 runs the length-bucketed passes
@@ -397,7 +410,7 @@ def main():
                                           "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1)}
                                       for k, v in prof_l.items()}}
         # configs[4] (seeker -> finder): the query side encodes 4096-caption batches with the ViT-L/14 text tower
-        ids_q = O.synth_captions(QUERY_BATCH, seed=7)[0].to(dev, torch.int32)  # the same batch on every rank
+        ids_q = synth_captions(QUERY_BATCH, seed=7)[0].to(dev, torch.int32)  # the same batch on every rank
         for _ in range(2):
             model_l.encode_texts(ids_q)
         ms_q = timed(lambda: model_l.encode_texts(ids_q), args.steps)

@@ -73,6 +73,7 @@ SIGNATURES = {
     "clm_pool_ln": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "clm_gemm_epi": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _P, _P, _I,
                           _I, _P]),
+    "clm_last_gemm_variant": (_I, []),
     "clm_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "clm_tower_create": (_I, [C.POINTER(TowerConfig), C.POINTER(TowerWeights),
                               C.POINTER(LayerWeights), C.POINTER(_P)]),

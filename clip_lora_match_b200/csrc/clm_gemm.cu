@@ -510,10 +510,14 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   return CLM_OK;
 }
 
+// which kernel instantiation the last clm_gemm_epi call of this thread selected (tests assert it)
+thread_local int g_last_variant = 0;
+
 template <int kEpi>
 int launch_gemm_bn(bool pair, int BN, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2,
                    const CUtensorMap& mb2, const CUtensorMap& mo, int M, int N, int kb_main, int kb_ext,
                    const EpiParams& ep, cudaStream_t stream) {
+  g_last_variant = (pair ? 256 : BN) * 100 + (pair ? 2 : 1) * 10 + kEpi;
   if (pair) return launch_gemm<256, 2, kEpi>(ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
   switch (BN) {
     case 256: return launch_gemm<256, 1, kEpi>(ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
@@ -627,6 +631,8 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
       return launch_gemm_bn<kEpiLegacy>(pair, BN, ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
   }
 }
+
+extern "C" int clm_last_gemm_variant(void) { return g_last_variant; }
 
 extern "C" int clm_gemm_epi(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                             const void* A2, int lda2, const void* W2, int ldw2, int K2, void* out,

@@ -77,6 +77,19 @@ def arch_from_name(name: str) -> ClipArch:
     raise ValueError(f"unknown CLIP architecture {name!r}; known: {sorted(ARCHS)}")
 
 
+def pooling_eos_id(eos_token_id, vocab_size: int) -> int:
+    """The token id whose FIRST occurrence the text tower pools at.
+
+    transformers pools at `input_ids.argmax(-1)` when `text_config.eos_token_id == 2` (the legacy value
+    every openai/clip-vit-* checkpoint still carries; TF:575-590) -- i.e. at the highest id of the row,
+    which for CLIP's tokenizer is the end-of-text token `vocab_size - 1` (49407) -- and at the first
+    occurrence of `eos_token_id` otherwise.  Both rules are "first position of the EOS token" once the
+    legacy value (or a missing one) is mapped to `vocab_size - 1`."""
+    if eos_token_id is None or int(eos_token_id) == 2:
+        return int(vocab_size) - 1
+    return int(eos_token_id)
+
+
 def arch_from_hf_config(cfg, name: str = "custom") -> ClipArch:
     v, t = cfg.vision_config, cfg.text_config
     return ClipArch(
@@ -85,7 +98,7 @@ def arch_from_hf_config(cfg, name: str = "custom") -> ClipArch:
         text=TowerArch(t.hidden_size, t.num_hidden_layers, t.num_attention_heads, t.intermediate_size),
         patch=v.patch_size, proj_dim=cfg.projection_dim, image=v.image_size,
         context=t.max_position_embeddings, vocab=t.vocab_size,
-        eos_id=t.eos_token_id if t.eos_token_id is not None else EOS_ID,
+        eos_id=pooling_eos_id(t.eos_token_id, t.vocab_size),
         ln_eps=v.layer_norm_eps)
 
 
@@ -648,6 +661,23 @@ def random_init_state_dict(arch: ClipArch, seed: int = 0) -> Dict[str, torch.Ten
     return {k: v.detach().clone() for k, v in hf.state_dict().items()}
 
 
+def _find_local_checkpoint(model_name: str) -> Optional[str]:
+    """Path of a local copy of `model_name` (a directory holding config.json, or a cached hub snapshot);
+    None when nothing is on disk.  Only "nothing on disk" selects random init in load_clip_model."""
+    p = Path(model_name)
+    if p.is_dir() and (p / "config.json").exists():
+        return str(p)
+    try:
+        from huggingface_hub import try_to_load_from_cache
+
+        hit = try_to_load_from_cache(model_name, "config.json")
+        if isinstance(hit, str) and os.path.exists(hit):
+            return str(Path(hit).parent)
+    except ImportError:
+        pass
+    return None
+
+
 def load_clip_model(
     config_path: Union[str, Path] = "config/clip_config.yaml",
     use_lora: bool = False,
@@ -664,19 +694,25 @@ def load_clip_model(
     seed = int(model_cfg.get("seed", 0))
     print(f"[clip_model] Loading CLIP model '{model_name}' on device: {device} (dtype={dtype})")
 
-    state_dict = None
-    arch = None
-    try:
+    # Weights: a local checkpoint (directory or cached hub snapshot) is loaded and every failure while
+    # doing so is raised, as in the reference (models/clip_model.py:59-63) -- a corrupt or unsupported
+    # checkpoint must not turn into a model that serves garbage.  Random-init weights of the named
+    # architecture are used ONLY when no checkpoint exists on this machine (there is no network here;
+    # BASELINE.json measures exactly that) or when the config asks for them (`model.random_init: true`
+    # / CLM_RANDOM_INIT=1).
+    want_random = bool(model_cfg.get("random_init", False)) or os.environ.get("CLM_RANDOM_INIT") == "1"
+    ckpt = None if want_random else _find_local_checkpoint(model_name)
+    if ckpt is None:
+        arch = arch_from_name(model_name)
+        why = "random_init requested" if want_random else "no local checkpoint"
+        print(f"[clip_model] {why} for '{model_name}': random-init weights of that architecture (seed={seed})")
+        state_dict = random_init_state_dict(arch, seed)
+    else:
         from transformers import CLIPModel
 
-        hf = CLIPModel.from_pretrained(model_name, local_files_only=True)
+        hf = CLIPModel.from_pretrained(ckpt, local_files_only=True)
         arch = arch_from_hf_config(hf.config, model_name)
         state_dict = hf.state_dict()
-    except Exception:
-        arch = arch_from_name(model_name)
-        print(f"[clip_model] no local checkpoint for '{model_name}': random-init weights of that "
-              f"architecture (seed={seed})")
-        state_dict = random_init_state_dict(arch, seed)
 
     lora = None
     if use_lora:

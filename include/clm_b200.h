@@ -124,6 +124,12 @@ int clm_gemm_epi(const void* A, int lda, const void* W, int ldw, int M, int N, i
                  void* out, int ldo, int out_dtype, const float* bias,
                  const float* residual, int ldr, int epilogue, void* stream);
 
+/* Debug / test hook: the kernel instantiation the calling thread's last clm_gemm_epi selected, encoded as
+ * BN*100 + ctas*10 + epilogue (ctas: 1 = single CTA, 2 = cta_group::2 pair; epilogue: 0 = per-thread,
+ * 1 = TMA store bf16, 2 = TMA store fp32, 3 = TMA reduce-add fp32).  25621 = gemm_kernel<256,2,1>.
+ * 0 before the first call.  No reference counterpart (the reference calls ATen's matmul). */
+int clm_last_gemm_variant(void);
+
 /* ------------------------------------------------------------------------------------
  * Fused attention (tcgen05: S=QK^T in TMEM, fp32 softmax in registers, O=PV)
  * ---------------------------------------------------------------------------------- */

@@ -286,3 +286,20 @@ def test_extra_token_attention_decomposition_is_exact_softmax_attention():
     out = torch.cat([out_main, out_tail[None, :]], dim=0)
     assert torch.allclose(out, ref, atol=6e-3, rtol=0)
     assert torch.allclose(out[Tk], ref[Tk], atol=1e-5)   # the tail row has no bf16 rounding at all
+
+
+def test_pooling_eos_id_maps_the_legacy_value():
+    """text_config.eos_token_id == 2 (every openai/clip-vit-* checkpoint) makes transformers pool at
+    input_ids.argmax (TF:575-590), i.e. at the end-of-text token vocab-1; any other value pools at its first
+    occurrence.  The tower's eos_id must follow."""
+    from transformers import CLIPConfig
+
+    from clip_lora_match_b200.models import clip_model as CM
+
+    assert CM.pooling_eos_id(2, 49408) == 49407
+    assert CM.pooling_eos_id(None, 49408) == 49407
+    assert CM.pooling_eos_id(49407, 49408) == 49407
+    assert CM.pooling_eos_id(1234, 49408) == 1234
+    cfg = CLIPConfig(text_config={"eos_token_id": 2})  # what the published openai/clip-vit-* configs carry
+    assert cfg.text_config.eos_token_id == 2
+    assert CM.arch_from_hf_config(cfg).eos_id == cfg.text_config.vocab_size - 1

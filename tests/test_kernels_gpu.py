@@ -181,6 +181,98 @@ def test_gemm_lora_extension(cuda_device):
     assert (ref[:, D:2 * D] - base[:, D:2 * D]).abs().max() == 0
 
 
+# ---- the kernels the benchmark actually runs: cta_group::2 pair tiles (256 x 256), every epilogue --------------
+# A GEMM goes to the CTA-pair kernel when N % 256 == 0 and it has at least ~38 pair tiles (clm_gemm_launch);
+# every shape above is smaller, so these are the fp32 comparisons of gemm_kernel<256, 2, *>.  The reference is
+# torch fp32 on the GPU (TF32 off): the CPU would need minutes for these sizes.
+def _variant():
+    from clip_lora_match_b200 import _lib
+    return _lib.load().clm_last_gemm_variant()
+
+
+def _gemm_ref_gpu(a, w, bias=None, residual=None, act=0, a2=None, w2=None):
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        return _gemm_ref(a, w, bias, residual, act, a2, w2)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+PAIR = 25620  # BN 256, two CTAs; + epilogue id
+
+
+@pytest.mark.parametrize("M", [8192, 197 * 50])  # full pair tiles / ragged last pair tile (9850 = 38 * 256 + 122)
+def test_gemm_pair_bias_quickgelu_bf16(cuda_device, M):
+    """(8192, 3072, 768) bias + QuickGELU, bf16 store: the vision fc1 launch -> gemm_kernel<256,2,1>."""
+    d = cuda_device
+    a = _randn((M, 768), 40).bfloat16().to(d)
+    w = _randn((3072, 768), 41, 768 ** -0.5).bfloat16().to(d)
+    bias = _randn((3072,), 42).to(d)
+    out = K.gemm_epi(a, w, bias=bias, act=K.EPI_QUICKGELU)
+    assert _variant() == PAIR + 1, _variant()
+    _close(f"pair_gelu_{M}", out, _gemm_ref_gpu(a, w, bias, act=K.EPI_QUICKGELU), atol=2e-2, rtol=8e-3)
+
+
+def test_gemm_pair_reduce_add_residual(cuda_device):
+    """(16384, 768, 3072) h += g W2^T + b in place: the fc2 / out-proj launch -> gemm_kernel<256,2,3>
+    (TMA reduce-add of fp32 tiles into the residual stream)."""
+    d = cuda_device
+    M, N, Kd = 16384, 768, 3072
+    a = _randn((M, Kd), 43).bfloat16().to(d)
+    w = _randn((N, Kd), 44, Kd ** -0.5).bfloat16().to(d)
+    bias = _randn((N,), 45).to(d)
+    res = _randn((M, N), 46).to(d)
+    ref = _gemm_ref_gpu(a, w, bias, res)
+    h = res.clone()
+    out = K.gemm_epi(a, w, bias=bias, residual=h, out=h)
+    assert _variant() == PAIR + 3, _variant()
+    assert out.data_ptr() == h.data_ptr()
+    _close("pair_reduce_add", h, ref, atol=3e-3, rtol=1e-3)
+    # ragged M: rows past M of the last pair tile must not be touched (guard rows behind the buffer)
+    M2 = 16384 - 100
+    buf = res.clone()
+    h2 = buf[:M2]
+    K.gemm_epi(a[:M2], w, bias=bias, residual=h2, out=h2)
+    assert _variant() == PAIR + 3
+    _close("pair_reduce_add_ragged", h2, ref[:M2], atol=3e-3, rtol=1e-3)
+    assert torch.equal(buf[M2:], res[M2:])
+
+
+@pytest.mark.parametrize("cols", [64, 128])
+def test_gemm_pair_lora_extension(cuda_device, cols):
+    """(8192, 2304, 768) fused QKV with the LoRA K-extension (kb_ext = cols / 64 extra k-blocks read from a
+    second pair of tensor maps) on the pair kernel -> gemm_kernel<256,2,1>."""
+    d = cuda_device
+    M, D = 8192, 768
+    x = _randn((M, D), 50).bfloat16().to(d)
+    w = _randn((3 * D, D), 51, D ** -0.5).bfloat16().to(d)
+    bias = _randn((3 * D,), 52).to(d)
+    a_cat = _randn((cols, D), 53, D ** -0.5).bfloat16().to(d)
+    b_cat = (_randn((3 * D, cols), 54, 0.05) * 2.0)
+    b_cat[D:2 * D] = 0  # no adapter on k
+    b_cat = b_cat.bfloat16().to(d)
+    t = K.gemm_epi(x, a_cat)
+    _close(f"pair_lora_down_{cols}", t, _gemm_ref_gpu(x, a_cat), atol=2e-2, rtol=8e-3)
+    out = K.gemm_epi(x, w, bias=bias, a2=t, w2=b_cat)
+    assert _variant() == PAIR + 1, _variant()
+    ref = _gemm_ref_gpu(x, w, bias, a2=t, w2=b_cat)
+    _close(f"pair_lora_ext_{cols}", out, ref, atol=2e-2, rtol=8e-3)
+    base = _gemm_ref_gpu(x, w, bias)
+    assert (ref[:, :D] - base[:, :D]).abs().max() > 1e-2          # the extension is not a no-op on q ...
+    assert (ref[:, D:2 * D] - base[:, D:2 * D]).abs().max() == 0  # ... and leaves k alone
+
+
+def test_gemm_pair_store_f32(cuda_device):
+    """fp32 TMA tile store on the pair kernel (the search's threshold-sampling GEMM) -> gemm_kernel<256,2,2>."""
+    d = cuda_device
+    a = _randn((8192, 1024), 55).bfloat16().to(d)
+    w = _randn((2048, 1024), 56, 1024 ** -0.5).bfloat16().to(d)
+    out = K.gemm_epi(a, w, out_dtype=torch.float32)
+    assert _variant() == PAIR + 2, _variant()
+    _close("pair_store_f32", out, _gemm_ref_gpu(a, w), atol=2e-3, rtol=1e-3)
+
+
 # ------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------

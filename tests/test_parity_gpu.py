@@ -85,6 +85,39 @@ def test_encoder_parity_vs_oracle(cuda_device, arch, n_img, n_txt, r, alpha, tar
         assert (base - got_img).abs().max() > 1e-4
 
 
+@pytest.mark.parametrize("arch,batch", [("openai/clip-vit-base-patch16", 1024), ("openai/clip-vit-large-patch14", 512)])
+def test_encoder_parity_at_benchmark_batch(cuda_device, arch, batch):
+    """The batch sizes bench.py measures (configs[1]: 1024, configs[2]: 512): CTA-pair GEMMs, several items per
+    attention CTA, the 256-image host chunks.  16 sampled rows against the oracle, and batch invariance: the
+    same rows encoded at batch 4 give the same embeddings (different GEMM tile shapes and reduction orders, so
+    equality is up to bf16-operand rounding, far inside the parity bar)."""
+    torch.set_num_threads(os.cpu_count() or 8)
+    model = O.build_model(arch, seed=0)
+    weights = O.synthetic_lora(model, 16, 32, ("q_proj", "v_proj"), seed=1)
+    gpu = _b200_model(arch, model, weights, 16, 32, ("q_proj", "v_proj"), cuda_device)
+    g = torch.Generator().manual_seed(2)
+    pv = torch.randn((batch, 3, 224, 224), generator=g)
+    ids, mask = O.synth_captions(batch, seed=3)
+    got_img = gpu.encode_images(pv.pin_memory()).cpu()     # host input: chunked H2D path, as bench.py's e2e
+    got_img_dev = gpu.encode_images(pv.to(cuda_device)).cpu()
+    got_txt = gpu.encode_texts(ids.to(cuda_device)).cpu()  # device ids: one padded 77-position pass
+    assert torch.isfinite(got_img).all() and torch.isfinite(got_txt).all()
+    sel = torch.linspace(0, batch - 1, 16).long()
+    tag = arch.split("/")[-1] + f"_b{batch}"
+    _assert_parity(tag + "_image", got_img[sel], O.encode_images(model, pv[sel]))
+    _assert_parity(tag + "_text", got_txt[sel], O.encode_texts(model, ids[sel], mask[sel]))
+    # chunk boundaries of the streamed host path fall on other rows than micro-batches of the device path
+    assert O.parity_metrics(got_img, got_img_dev)["cos_min"] >= 0.99999
+    for j in range(0, 16, 4):
+        rows = sel[j:j + 4]
+        small_i = gpu.encode_images(pv[rows].to(cuda_device)).cpu()
+        small_t = gpu.encode_texts(ids[rows].to(cuda_device)).cpu()
+        mi, mt = O.parity_metrics(small_i, got_img[rows]), O.parity_metrics(small_t, got_txt[rows])
+        print(f"[batch-invariance] {tag} rows {rows.tolist()}: image {mi} text {mt}")
+        assert mi["cos_min"] >= 0.9999 and mi["rel_l2_max"] <= 0.01, mi
+        assert mt["cos_min"] >= 0.9999 and mt["rel_l2_max"] <= 0.01, mt
+
+
 def test_encoder_matches_reference_golden_vectors(cuda_device):
     """B/32 + LoRA r=8 q/v embeddings produced by the reference's own encode_image/encode_text
     (tests/golden/encoder_golden.npz, case 2) through the reference-shaped surface."""

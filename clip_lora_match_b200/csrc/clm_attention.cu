@@ -62,6 +62,10 @@ struct AttnParams {
   // update of O per row) and the extra QUERY row is computed by a dedicated warp, both from the staged
   // shared-memory tiles.  Otherwise Tk == Tp.
   int Tk, xt;
+  // serial != 0: the exponential pass (pass 2) of tile t starts only after P(t-1) has been published by the
+  // other softmax group, so the two groups take turns on the MUFU pipe instead of running in lockstep (both
+  // exponentiating, then both waiting for their P V and output phases with the pipe idle)
+  int serial;
   // TMEM column of the S / P region and of the O accumulator used by tiles of parity 0 / 1;
   // o_alias: O lives inside the same parity's S region (dead by then), so S(t+2) waits for the drain
   int s_col0, s_col1, o_col0, o_col1, o_alias0, o_alias1;
@@ -717,6 +721,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
         mx = fmaxf(mx, sx);
       }
       TRACE(t, 3);
+      if (p.serial && t >= 1) mbar_wait(&p_full[g ^ 1], static_cast<uint32_t>(((t - 1) >> 1) & 1));
       // ---- pass 2: p = 2^(s*c - max*c), partial row sum, P (bf16x2) written over S.  P(c) lands in the
       // columns of S chunk c/2, so the pair synchronises once per iteration: by then both threads hold
       // every chunk up to 2i+1 in registers and the columns of chunk i are dead.
@@ -858,6 +863,520 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+
+// =====================================================================================================
+// attention_kernel_v2 — one softmax thread per query row, software-pipelined TMEM loads.
+//
+// Same work decomposition, TMEM plans, TMA producer and MMA issuer as attention_kernel (single key block,
+// two S regions).  What changes is the softmax side, which was latency-bound on hand-offs between the
+// two threads that shared a row (one named barrier per chunk pair, max / sum / extra-key exchange through
+// shared memory) and on tcgen05.ld round trips nothing overlapped:
+//   * 8 softmax warps instead of 16: group g = tile parity, one warp per TMEM lane quarter, ONE thread per
+//     query row.  No pair barriers, no exchanges; the row max, row sum and the extra key's score are
+//     thread-private registers.
+//   * 448 threads per CTA -> 144 registers per thread: both passes keep the NEXT 32-column chunk in flight
+//     (tcgen05.ld issued before the arithmetic of the current chunk, two register buffers) so the TMEM
+//     latency hides behind the FFMA / MUFU work of the same warp.
+//   * pass 1 uses three-input FMNMX3; a configurable share of the exponentials runs on the FMA pipe
+//     (Cody-Waite split + cubic minimax polynomial, rel. error 7.5e-5 << the bf16 rounding of P) because
+//     MUFU.EX2 (16 / clk / SM) is the pipe that bounds head_dim 64 attention.
+//   * four extra-token warps (one per SM sub-partition) instead of two on shared sub-partitions.
+// Warp roles: 0 TMA producer, 1 MMA issuer, 4..11 softmax, {2, 3, 12, 13} extra-token rows (T = 128k + 1).
+// =====================================================================================================
+constexpr int kThreadsV2 = 448;
+constexpr int kSoftWarp0 = 4;
+#ifndef CLM_ATTN_POLY
+#define CLM_ATTN_POLY 0  // of every 4 exponentials, how many run on the FMA pipe (0..4)
+#endif
+
+__device__ __forceinline__ int tail_index_v2(int warp) {
+  return warp == 2 ? 0 : (warp == 3 ? 1 : (warp == 12 ? 2 : (warp == 13 ? 3 : -1)));
+}
+
+// tcgen05.wait::ld that also "produces" the registers of the load it completes: nothing that reads them can
+// be scheduled above it, although another load (into the other buffer) may already be in flight
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),
+                 "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]),
+                 "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]),
+                 "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// max of 32 scores: FMNMX3, four chains
+__device__ __forceinline__ float chunk_max3(const uint32_t (&v)[32], float m) {
+  float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+    m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+    m2 = fmax3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+    m3 = fmax3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// 2^x for x <= 0 on the FMA / ALU pipes: x = j + f, j = round(x), f in [-0.5, 0.5]; 2^f by a cubic (minimax in
+// relative error, 7.5e-5); the integer part goes straight into the exponent field.  The magic constant
+// 1.5 * 2^23 leaves j in the low mantissa bits of r, so (bits(r) << 23) is j << 23 (mod 2^32).
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -125.0f);
+  const float r = x + 12582912.0f;
+  const float f = x - (r - 12582912.0f);
+  float p = fmaf(0.0551716648f, f, 0.2426111251f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
+// p = 2^(s*c - max*c) for 32 scores -> 16 packed bf16x2 words; returns the chunk's sum of p.  Of every four
+// elements the last kPoly use exp2_fma, the others MUFU.EX2.
+template <bool kMasked, int kPoly>
+__device__ __forceinline__ float chunk_exp_v2(const uint32_t (&v)[32], uint32_t (&pk)[16], float scale,
+                                              float neg_mx, int base, int valid) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float x0 = fmaf(__uint_as_float(v[i]), scale, neg_mx);
+    const float x1 = fmaf(__uint_as_float(v[i + 1]), scale, neg_mx);
+    const float x2 = fmaf(__uint_as_float(v[i + 2]), scale, neg_mx);
+    const float x3 = fmaf(__uint_as_float(v[i + 3]), scale, neg_mx);
+    float e0 = (kPoly >= 4) ? exp2_fma(x0) : fast_exp2(x0);
+    float e1 = (kPoly >= 3) ? exp2_fma(x1) : fast_exp2(x1);
+    float e2 = (kPoly >= 2) ? exp2_fma(x2) : fast_exp2(x2);
+    float e3 = (kPoly >= 1) ? exp2_fma(x3) : fast_exp2(x3);
+    if (kMasked) {
+      e0 = (base + i < valid) ? e0 : 0.f;
+      e1 = (base + i + 1 < valid) ? e1 : 0.f;
+      e2 = (base + i + 2 < valid) ? e2 : 0.f;
+      e3 = (base + i + 3 < valid) ? e3 : 0.f;
+    }
+    s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+    pk[i / 2] = pack_bf16x2(e0, e1);
+    pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+template <bool kCausal>
+__global__ void __launch_bounds__(kThreadsV2, 1)
+attention_kernel_v2(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CUtensorMap map16,
+                    const __grid_constant__ CUtensorMap map_out, __nv_bfloat16* __restrict__ out, AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* ostage = smem + p.stages * p.stage_bytes;  // 1024-byte aligned (stage_bytes is a multiple of 6144)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + (p.stage_out == 1 ? kOutStageBytes : 0));
+  uint64_t* stage_full = bars;                     // [kMaxStages]
+  uint64_t* stage_empty = bars + kMaxStages;       // [kMaxStages]
+  uint64_t* s_full = bars + 2 * kMaxStages;        // [2] S ready (MMA commit), by tile parity
+  uint64_t* p_full = s_full + 2;                   // [2] P written (128 softmax threads)
+  uint64_t* o_full = s_full + 4;                   // [2] O ready (MMA commit)
+  uint64_t* slot_free = s_full + 6;                // [2] O drained (128 softmax threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
+  // [4] "an item owned by extra-token warp j has landed": the MMA thread, which sees every stage fill in order,
+  // arrives.  The extra-token warps cannot wait on stage_full themselves: each takes every fourth item, so it
+  // would skip phases of a stage's barrier and a parity wait cannot tell phase k from phase k - 2.
+  uint64_t* tail_go = s_full + 9;
+  // extra-token scratch (only when p.xt): per softmax warp a copy of the extra V row (64 bf16), then one
+  // fp32 probability row per extra-token warp
+  uint8_t* vxs = reinterpret_cast<uint8_t*>(bars) + 256;      // [8 warps][128 B]
+  float* prow = reinterpret_cast<float*>(vxs + 8 * 128);      // [4 warps][288]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int T = p.T, H = p.H, Tp = p.Tp, Tk = p.Tk, D = p.H * kHeadDim;
+  const int kv_bytes = Tp * 128;  // one of Q / K / V in a stage (Tp rows are loaded; the MMAs see Tk keys)
+  const int n_local = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                      static_cast<int>(gridDim.x);
+  const int n_tiles = n_local * p.mtiles;
+  const int tail_w = tail_index_v2(warp);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map64);
+    tma_prefetch_desc(&map16);
+    if (p.stage_out) tma_prefetch_desc(&map_out);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&stage_full[s], 1);
+      // last PV's commit (+ the extra-token warp that owns the item) (+ the 4 softmax warps of each of the
+      // item's tiles once their output slab, staged in the tile's dead Q rows, has been read by the TMA unit)
+      mbar_init(&stage_empty[s], 1 + p.xt + (p.stage_out == 2 ? 4 * p.mtiles : 0));
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&o_full[s], 1);
+      mbar_init(&slot_free[s], 128);
+    }
+    for (int s = 0; s < 4; ++s) mbar_init(&tail_go[s], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int n64 = Tp / 64, n16 = (Tp % 64) / 16;
+      int st = 0;
+      uint32_t ph = 0;
+#ifdef CLM_ATTN_TRACE
+      int tl = 0;
+#endif
+      for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+        const int b = it / H, h = it % H;
+        const int row_base = b * T;
+        TRACE(tl, 0);
+        mbar_wait(&stage_empty[st], ph ^ 1);
+        TRACE(tl, 1);
+#ifdef CLM_ATTN_TRACE
+        ++tl;
+#endif
+        uint8_t* base = smem + st * p.stage_bytes;
+        mbar_arrive_expect_tx(&stage_full[st], static_cast<uint32_t>(3 * kv_bytes));
+        for (int part = 0; part < 3; ++part) {  // 0 = Q, 1 = K, 2 = V
+          uint8_t* dst = base + part * kv_bytes;
+          const int col = part * D + h * kHeadDim;
+          for (int i = 0; i < n64; ++i)
+            tma_load_2d(dst + i * 8192, &map64, &stage_full[st], col, row_base + i * 64);
+          for (int i = 0; i < n16; ++i)
+            tma_load_2d(dst + n64 * 8192 + i * 2048, &map16, &stage_full[st], col,
+                        row_base + n64 * 64 + i * 16);
+        }
+        if (++st == p.stages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (two independent streams, one per tile parity) =================
+    const uint32_t idesc_pv = umma_idesc_bf16(128, kHeadDim, 0, 1);
+    struct Cursor {  // position of a stream inside the CTA's tile list
+      int t, mt, st, li;  // tile, tile inside its item, stage, item (CTA-local sequence number)
+      uint32_t ph;
+      __device__ void init(int t0, const AttnParams& p) {
+        t = t0; mt = t0; st = 0; ph = 0; li = 0;
+        while (mt >= p.mtiles) { mt -= p.mtiles; bump(p); }
+      }
+      __device__ void bump(const AttnParams& p) {
+        ++li;
+        if (++st == p.stages) { st = 0; ph ^= 1; }
+      }
+      __device__ void advance(int step, const AttnParams& p) {
+        t += step; mt += step;
+        while (mt >= p.mtiles) { mt -= p.mtiles; bump(p); }
+      }
+    };
+    auto do_s = [&](const Cursor& c) {
+      if (lane == 0) {
+        const uint32_t q_addr = smem_u32(smem + c.st * p.stage_bytes);
+        const uint32_t k_addr = q_addr + kv_bytes;
+        const uint32_t sbase = tmem + static_cast<uint32_t>(p.s_col(c.t & 1));
+        for (int n0 = 0; n0 < Tk; n0 += 256) {
+          const int nn = (Tk - n0) < 256 ? (Tk - n0) : 256;
+          const uint32_t idesc = umma_idesc_bf16(128, nn, 0, 0);
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k)
+            umma_bf16_ss(sbase + n0, umma_desc_sw128(q_addr + c.mt * 16384 + k * 32, 1024),
+                         umma_desc_sw128(k_addr + n0 * 128 + k * 32, 1024), idesc, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[c.t & 1]);
+        if (p.xt && c.mt == 0) mbar_arrive(&tail_go[c.li & 3]);  // the item's Q / K / V are in shared memory
+      }
+      __syncwarp();
+    };
+    int pv_cnt[kMaxStages];  // PVs issued per stage: the last one of an item releases its stage
+#pragma unroll
+    for (int i = 0; i < kMaxStages; ++i) pv_cnt[i] = 0;
+    auto do_pv = [&](const Cursor& c) {
+      // O(t) = P(t) V : P from TMEM (written by the softmax group), V MN-major from smem.  p_full(t)
+      // also implies that the same group has drained O(t-2), whose columns this overwrites.
+      const int b = c.t & 1;
+      const bool last = (++pv_cnt[c.st] == p.mtiles);
+      if (last) pv_cnt[c.st] = 0;
+      if (lane == 0) {
+        const uint32_t v_addr = smem_u32(smem + c.st * p.stage_bytes) + 2 * kv_bytes;
+        const uint32_t pbase = tmem + static_cast<uint32_t>(p.s_col(b));
+        const uint32_t obase = tmem + static_cast<uint32_t>(p.o_col(b));
+        const int ksteps = Tk / 16;
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_bf16_ts(obase, pbase + ks * 8, umma_desc_sw128_mn(v_addr + ks * 2048), idesc_pv,
+                       ks != 0 ? 1u : 0u);
+        umma_commit(&o_full[b]);
+        if (last) umma_commit(&stage_empty[c.st]);  // stage reusable once these MMAs retire
+      }
+      __syncwarp();
+    };
+    Cursor sc[2], pc[2];  // next S / next PV of each stream
+    sc[0].init(0, p); sc[1].init(1, p); pc[0].init(0, p); pc[1].init(1, p);
+    while (pc[0].t < n_tiles || pc[1].t < n_tiles) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        // PV(t): S(t) has been issued and the group has published P(t)
+        // (test_wait, not try_wait: try_wait may put the thread to sleep on one stream's barrier while the
+        // other stream's becomes ready)
+        if (pc[b].t < sc[b].t && mbar_test_wait(&p_full[b], static_cast<uint32_t>((pc[b].t >> 1) & 1))) {
+          tc_fence_after();
+          TRACE(pc[b].t, 1);
+          do_pv(pc[b]);
+          pc[b].advance(2, p);
+        }
+        // S(t): PV(t-2) has been issued (in-order pipe: its P columns are safe); an aliased O(t-2)
+        // has been drained; the item's Q/K/V have landed
+        if (sc[b].t < n_tiles && sc[b].t - 2 < pc[b].t) {
+          bool ok = true;
+          if (p.o_alias(b) && sc[b].t >= 2)
+            ok = mbar_test_wait(&slot_free[b], static_cast<uint32_t>(((sc[b].t - 2) >> 1) & 1));
+          if (ok) ok = mbar_test_wait(&stage_full[sc[b].st], sc[b].ph);
+          if (ok) {
+            tc_fence_after();
+            TRACE(sc[b].t, 0);
+            do_s(sc[b]);
+            sc[b].advance(2, p);
+          }
+        }
+      }
+    }
+  } else if (warp >= kSoftWarp0 && warp < kSoftWarp0 + 8) {
+    // ================= softmax: one thread per query row =================
+    const int g = (warp - kSoftWarp0) >> 2;  // group = parity of the tiles it owns
+    const int q = warp & 3;                  // TMEM lane quarter of this warp (warp % 4)
+    const int r = q * 32 + lane;             // row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const int nchunks = (Tk + 31) / 32;
+    constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const uint32_t srow = tmem + lane_off + static_cast<uint32_t>(p.s_col(g));
+    const uint32_t orow = tmem + lane_off + static_cast<uint32_t>(p.o_col(g));
+    const bool xt = !kCausal && p.xt != 0;
+    const uint32_t vx_w = smem_u32(vxs + (warp - kSoftWarp0) * 128);  // this warp's copy of the extra V row
+    int t = 0;
+    int li = 0;  // items seen by this CTA: item li sits in stage li % stages
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, ++li)
+    for (int mt = 0; mt < p.mtiles; ++mt, ++t) {
+      if ((t & 1) != g) continue;
+      const int b = it / H, h = it - b * H;
+      const uint32_t par = static_cast<uint32_t>((t >> 1) & 1);
+      const int qi = mt * 128 + r;                     // query position in the sequence
+      const bool warp_live = mt * 128 + q * 32 < T;    // does this warp own any real row?
+      int valid = T < Tk ? T : Tk;
+      if (kCausal) valid = (qi + 1 < T) ? qi + 1 : T;
+      const int st_cur = li % p.stages;
+      // ---- extra key (row Tk of K / V): q_row . k_x on the CUDA cores, and a private copy of v_x (the
+      // stage may be refilled before the output phase of the item's last tile)
+      float sx = 0.f, px = 0.f;
+      if (xt) {
+        mbar_wait(&stage_full[st_cur], static_cast<uint32_t>((li / p.stages) & 1));
+        TRACE(t, 7);
+        const uint32_t sb = smem_u32(smem + st_cur * p.stage_bytes);
+        const uint32_t qa = sb + static_cast<uint32_t>(qi) * 128u;
+        const uint32_t ka = sb + static_cast<uint32_t>(kv_bytes + Tk * 128);
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 a = ld_shared_v4(qa + ((static_cast<uint32_t>(c) ^ static_cast<uint32_t>(r & 7)) << 4));
+          const uint4 kx = ld_shared_v4(ka + (static_cast<uint32_t>(c) << 4));
+          dot8(a, kx, d0, d1);
+        }
+        sx = d0 + d1;
+        if (lane < 8) {
+          const uint4 w = ld_shared_v4(sb + static_cast<uint32_t>(2 * kv_bytes + Tk * 128 + (lane << 4)));
+          st_shared_v4(vx_w + (lane << 4), w.x, w.y, w.z, w.w);
+        }
+        __syncwarp();
+      }
+      // chunks this warp has to look at: under the causal mask nothing right of its last row counts
+      int nch = nchunks;
+      if (kCausal) {
+        const int wv = (mt * 128 + q * 32 + 32 < T) ? mt * 128 + q * 32 + 32 : T;
+        nch = (wv + 31) / 32;
+      }
+
+      TRACE(t, 0);
+      mbar_wait(&s_full[g], par);
+      tc_fence_after();
+      TRACE(t, 1);
+      uint32_t va[32], vb[32];
+      // ---- pass 1: row max; the load of chunk c+1 is in flight while chunk c is reduced
+      float mx = -INFINITY;
+      if (warp_live) {
+        tmem_ld_32x32b_x32(srow, va);
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait_dep(va);
+          if (c + 1 < nch) tmem_ld_32x32b_x32(srow + (c + 1) * 32, vb);
+          mx = (c * 32 + 32 <= valid) ? chunk_max3(va, mx) : chunk_max_masked(va, mx, c * 32, valid);
+          if (c + 1 < nch) {
+            tmem_ld_wait_dep(vb);
+            if (c + 2 < nch) tmem_ld_32x32b_x32(srow + (c + 2) * 32, va);
+            mx = (c * 32 + 64 <= valid) ? chunk_max3(vb, mx) : chunk_max_masked(vb, mx, c * 32 + 32, valid);
+          }
+        }
+      }
+      if (xt) mx = fmaxf(mx, sx);
+      TRACE(t, 2);
+      if (p.serial && t >= 1) mbar_wait(&p_full[g ^ 1], static_cast<uint32_t>(((t - 1) >> 1) & 1));
+      TRACE(t, 3);
+      // ---- pass 2: p = 2^(s*c - max*c), row sum, P (bf16x2) written over S.  P(c) lands in the columns
+      // [16c, 16c + 16) of S, i.e. inside chunk c / 2, which this thread has already consumed; the chunk in
+      // flight (c + 1) lies further right.
+      float sum = 0.f;
+      if (warp_live) {
+        const float neg_mx = -mx * kScaleLog2e;
+        if (xt) {
+          px = fast_exp2(fmaf(sx, kScaleLog2e, neg_mx));  // fp32 weight of the extra key (not rounded to bf16)
+          sum = px;
+        }
+        uint32_t pk[16];
+        tmem_ld_32x32b_x32(srow, va);
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait_dep(va);
+          if (c + 1 < nch) tmem_ld_32x32b_x32(srow + (c + 1) * 32, vb);
+          sum += (c * 32 + 32 <= valid)
+                     ? chunk_exp_v2<false, CLM_ATTN_POLY>(va, pk, kScaleLog2e, neg_mx, c * 32, valid)
+                     : chunk_exp_v2<true, 0>(va, pk, kScaleLog2e, neg_mx, c * 32, valid);
+          tmem_st_32x32b_x16(srow + c * 16, pk);
+          if (c + 1 < nch) {
+            tmem_ld_wait_dep(vb);
+            if (c + 2 < nch) tmem_ld_32x32b_x32(srow + (c + 2) * 32, va);
+            sum += (c * 32 + 64 <= valid)
+                       ? chunk_exp_v2<false, CLM_ATTN_POLY>(vb, pk, kScaleLog2e, neg_mx, c * 32 + 32, valid)
+                       : chunk_exp_v2<true, 0>(vb, pk, kScaleLog2e, neg_mx, c * 32 + 32, valid);
+            tmem_st_32x32b_x16(srow + (c + 1) * 16, pk);
+          }
+        }
+        if (kCausal && nch < nchunks) {  // P right of the causal frontier is zero (PV reads it)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          for (int c = nch; c < nchunks; ++c) tmem_st_32x32b_x16(srow + c * 16, pk);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      TRACE(t, 4);
+      mbar_arrive(&p_full[g]);
+
+      // ---- O(t): out of TMEM, + p_x v_x, / row sum, bf16, out through shared memory and a TMA tile store
+      mbar_wait(&o_full[g], par);
+      tc_fence_after();
+      TRACE(t, 5);
+      if (warp_live) {
+        tmem_ld_32x32b_x32(orow, va);
+        tmem_ld_32x32b_x32(orow + 32, vb);
+        tmem_ld_wait_dep(va);
+        tmem_ld_wait_dep(vb);
+      }
+      tc_fence_before();
+      TRACE(t, 6);
+      mbar_arrive(&slot_free[g]);  // O(t) is in registers: its columns may be overwritten
+      if (xt && warp_live) {       // O += p_x * v_x
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint4 w = ld_shared_v4(vx_w + (jj << 4));
+          uint32_t* o = (jj < 4) ? &va[8 * jj] : &vb[8 * (jj - 4)];
+          o[0] = __float_as_uint(fmaf(px, bf16_lo(w.x), __uint_as_float(o[0])));
+          o[1] = __float_as_uint(fmaf(px, bf16_hi(w.x), __uint_as_float(o[1])));
+          o[2] = __float_as_uint(fmaf(px, bf16_lo(w.y), __uint_as_float(o[2])));
+          o[3] = __float_as_uint(fmaf(px, bf16_hi(w.y), __uint_as_float(o[3])));
+          o[4] = __float_as_uint(fmaf(px, bf16_lo(w.z), __uint_as_float(o[4])));
+          o[5] = __float_as_uint(fmaf(px, bf16_hi(w.z), __uint_as_float(o[5])));
+          o[6] = __float_as_uint(fmaf(px, bf16_lo(w.w), __uint_as_float(o[6])));
+          o[7] = __float_as_uint(fmaf(px, bf16_hi(w.w), __uint_as_float(o[7])));
+        }
+      }
+      const float inv = 1.0f / sum;
+      if (p.stage_out) {
+        // One lane owns one 128-byte output row.  The warp assembles its 32-row slab in shared memory in the
+        // SWIZZLE_128B pattern of the output map and one lane hands it to the TMA unit; rows >= T are clipped.
+        // stage_out == 2: no room for a staging buffer; the slab goes into this warp's 32 rows of the tile's
+        // own Q block, which nothing reads after S has been computed (same swizzled row layout).
+        const uint32_t ost = (p.stage_out == 2)
+                                 ? smem_u32(smem + st_cur * p.stage_bytes) + static_cast<uint32_t>(mt * 128 + q * 32) * 128u
+                                 : smem_u32(ostage + (g * 4 + q) * 4096);
+        if (warp_live) {
+          if (p.stage_out == 1) {  // the previous tile's slab has left the staging buffer
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const uint32_t* o = (jj < 4) ? &va[8 * jj] : &vb[8 * (jj - 4)];
+            st_shared_v4(ost + static_cast<uint32_t>(lane) * 128u + ((static_cast<uint32_t>(jj) ^ (lane & 7)) << 4),
+                         pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv),
+                         pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv),
+                         pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv),
+                         pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_out, ost, h * kHeadDim, mt * 128 + q * 32, b);
+            bulk_commit();
+          }
+        }
+        if (p.stage_out == 2 && lane == 0) {
+          // release this warp's share of the stage as soon as the TMA unit has read the slab: the refill of
+          // the stage (two stages only) is on the critical path of the tile after next
+          bulk_wait_read<0>();
+          mbar_arrive(&stage_empty[st_cur]);
+        }
+        __syncwarp();
+      } else if (warp_live && qi < T) {
+        uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(b * T + qi) * D + h * kHeadDim);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint32_t* o = (jj < 4) ? &va[8 * jj] : &vb[8 * (jj - 4)];
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+          o4[jj] = w;
+        }
+      }
+    }
+    if (p.stage_out && lane == 0) bulk_wait<0>();  // every slab of this warp has reached memory
+  } else if (tail_w >= 0 && !kCausal && p.xt) {
+    // ================= extra-token warps: the query row Tk of every item, on the CUDA cores =================
+    // (one row per (batch, head): a third 128-row tensor-core tile would be 1/128 used).  The four warps take
+    // every fourth item; see tail_row.
+    float* my_prow = prow + tail_w * 288;
+    int st = 0, tl = 0;
+    uint32_t own_ph = 0;
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, ++tl) {
+      if ((tl & 3) == tail_w) {
+        const int b = it / H, h = it - b * H;
+        TRACE(tl, 0);
+        mbar_wait(&tail_go[tail_w], own_ph);
+        own_ph ^= 1;
+        TRACE(tl, 1);
+        const uint32_t sb = smem_u32(smem + st * p.stage_bytes);
+        uint32_t* orow = reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * T + Tk) * D + h * kHeadDim);
+        if (Tk == 256) tail_row<8>(sb, kv_bytes, my_prow, lane, orow);
+        else tail_row<4>(sb, kv_bytes, my_prow, lane, orow);
+        __syncwarp();  // every lane is done with the stage and with its p row
+        TRACE(tl, 3);
+        if (lane == 0) mbar_arrive(&stage_empty[st]);
+      }
+      if (++st == p.stages) st = 0;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 
 int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int heads, int causal,
@@ -880,6 +1399,12 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
     xt_off = (e && e[0] == '0') ? 1 : 0;
   }
   p.xt = (!xt_off && !causal && T > 128 && T % 128 == 1 && T <= 257) ? 1 : 0;
+  static int serial = -1;  // CLM_ATTN_SERIAL=0: the two softmax groups run unsynchronised (A/B measurements)
+  if (serial < 0) {
+    const char* e = getenv("CLM_ATTN_SERIAL");
+    serial = (e && e[0] == '0') ? 0 : 1;
+  }
+  p.serial = serial;
   p.Tk = p.xt ? T - 1 : p.Tp;
   if (p.xt) p.mtiles = p.Tk / 128;
   const long long items = static_cast<long long>(batch) * heads;
@@ -898,6 +1423,9 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   if (stages > kMaxStages) stages = kMaxStages;
   CLM_REQUIRE(stages >= 1, "clm_attention: tokens=%d needs %d bytes of shared memory per stage", T,
               stage_bytes);
+  // one tile per item: each stream (tile parity) visits every other item, so with an odd ring it would skip
+  // phases of a stage's barrier and a parity wait cannot tell phase k from phase k - 2
+  if (p.mtiles == 1 && stages > 2 && (stages & 1)) stages -= 1;
   p.stages = stages;
   // TMEM plan (512 columns).  S needs round_up(Tp,32) fp32 columns (the softmax reads 32-column
   // chunks); P (bf16x2) reuses its first Tp/2; O needs 64.  Tiles alternate between two parities:
@@ -972,6 +1500,28 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   // algorithmic work: QK^T and PV at the true T (causal not discounted)
   ProfScope prof(CLM_K_ATTENTION, 4.0 * batch * heads * static_cast<double>(T) * T * kHeadDim,
                  2.0 * batch * T * 4.0 * D, stream);
+  // one-thread-per-row kernel for every plan with a single key block and two S regions (all CLIP shapes);
+  // the older two-threads-per-row kernel keeps the two-block / one-region plans.  CLM_ATTN_V1=1 forces it.
+  static int force_v1 = -1;
+  if (force_v1 < 0) {
+    const char* e = getenv("CLM_ATTN_V1");
+    force_v1 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!force_v1 && p.blocks == 1 && p.nslots == 2) {
+    if (causal) {
+      CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel_v2<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      attention_kernel_v2<true><<<grid, kThreadsV2, smem_bytes, stream>>>(
+          map64, map16, map_out, static_cast<__nv_bfloat16*>(out), p);
+    } else {
+      CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel_v2<false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      attention_kernel_v2<false><<<grid, kThreadsV2, smem_bytes, stream>>>(
+          map64, map16, map_out, static_cast<__nv_bfloat16*>(out), p);
+    }
+    CLM_CUDA_CHECK(cudaGetLastError());
+    return CLM_OK;
+  }
   if (causal) {
     CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

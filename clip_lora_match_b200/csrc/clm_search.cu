@@ -42,6 +42,7 @@ struct SearchParams {
   int nq, n, kblocks, q_tiles, splits, tiles_n, kc, stages;  // q_tiles: tiles of BM * kCtas queries
   int a_bytes;  // bytes of the query tile actually loaded per k-block (64-row box when nq <= 64)
   float* thr_io;  // per-query running lower bound of the kc-th best score, shared by all units (or null)
+  float margin;   // scores above (shared bound - margin) are kept: see clm_search_topk in include/clm_b200.h
   float* cand_score;
   int32_t* cand_id;
 };
@@ -109,7 +110,10 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
 // State of one thread's candidate list (the list itself is in shared memory, element j at sc[j * BM]).
 struct ListState {
   int cnt, minpos;
-  float thr, published;
+  float thr;        // a score must exceed this to enter the list: max(own, gbound - margin)
+  float own;        // minimum of this list once it is full (-inf before)
+  float gbound;     // the shared per-query bound as last seen / published by this thread
+  float margin;
 };
 
 // Insert (s, id) into a thread's list of the kc best; once the list is full, track its minimum (the thread's
@@ -129,13 +133,14 @@ __device__ __noinline__ ListState list_insert(ListState st, float s, int id, flo
       const float x = my_sc[j * BM];
       if (x < m) { m = x; mp = j; }
     }
-    st.thr = fmaxf(st.thr, m);
+    st.own = m;
     st.minpos = mp;
-    if (gthr && m > st.published) {  // publish: float max through the integer atomics
-      st.published = m;
+    if (gthr && m > st.gbound) {  // publish: float max through the integer atomics
+      st.gbound = m;
       if (m >= 0.f) atomicMax(reinterpret_cast<int*>(gthr), __float_as_int(m));
       else atomicMin(reinterpret_cast<unsigned int*>(gthr), __float_as_uint(m));
     }
+    st.thr = fmaxf(st.own, st.gbound - st.margin);
   }
   return st;
 }
@@ -286,18 +291,21 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       ListState ls;
       ls.cnt = 0;
       ls.minpos = 0;
-      // thr is a lower bound of this query's kc-th best score over the WHOLE index: the k-th best of
+      // gbound is a lower bound of this query's kc-th best score over the WHOLE index: the kc-th best of
       // any subset of rows qualifies, so every unit publishes its own list minimum (atomic max in
       // global memory) and re-reads the shared bound once per tile.  Units that start after the
-      // first wave inherit a nearly final bound and almost never enter the insert path.
+      // first wave inherit a nearly final bound and almost never enter the insert path.  Scores within
+      // `margin` below the bound are still kept (the bf16 score of a true top-k row may sit that far below
+      // the bf16 score of the k-th best row; see include/clm_b200.h).
       float* gthr = (p.thr_io != nullptr && q0 + r < p.nq) ? p.thr_io + q0 + r : nullptr;
       ls.thr = -INFINITY;
-      ls.published = -INFINITY;
+      ls.own = -INFINITY;
+      ls.gbound = -INFINITY;
+      ls.margin = p.margin;
       for (int t = t0; t < t1; ++t) {
         if (gthr) {
-          const float g = __ldcg(gthr);
-          ls.published = fmaxf(ls.published, g);
-          ls.thr = fmaxf(ls.thr, g);
+          ls.gbound = fmaxf(ls.gbound, __ldcg(gthr));
+          ls.thr = fmaxf(ls.own, ls.gbound - ls.margin);
         }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -377,81 +385,179 @@ int launch_search(const CUtensorMap& mq, const CUtensorMap& me, const SearchPara
 }
 
 // -----------------------------------------------------------------------------------------
-// merge / re-score
+// selection helpers: k-th largest by radix select, bitonic sort of (score, id) pairs
 // -----------------------------------------------------------------------------------------
-constexpr int kMergeThreads = 128;
-constexpr int kMaxKc = 64;
+constexpr int kSelThreads = 256;
+constexpr int kMaxSel = 2048;  // candidates a query may carry into the exact re-score / final sort
+
+// order-preserving map float -> uint32 (ascending); -inf is the smallest key that occurs
+__device__ __forceinline__ uint32_t key_of(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_of(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// k-th largest (kth >= 1) of v[0..n) -- v in shared OR global memory -- by an 8-bit-per-pass radix select over
+// the order-preserving keys: 4 passes, each a block-wide histogram of the values that still match the prefix.
+// hist: 256 ints of shared memory; ctl: 2 uint32 of shared memory.  Every thread of the block must call it;
+// returns the same value to all.  n >= kth is required.
+__device__ float block_kth_largest(const float* v, int n, int kth, int* hist, uint32_t* ctl) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  uint32_t prefix = 0, mask = 0;
+  int remaining = kth;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += nt) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+      const uint32_t k = key_of(v[i]);
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // lane l owns bins [8l, 8l+8); suffix sums from the top bin down locate the bin holding the kth largest
+      int c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[tid * 8 + j]; sum += c[j]; }
+      int incl = sum;  // inclusive suffix sum over lanes >= this one (Hillis-Steele with shfl_down)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_down_sync(0xffffffffu, incl, o);
+        if (tid + o < 32) incl += x;
+      }
+      const int above = incl - sum;  // values in bins owned by higher lanes
+      if (above < remaining && above + sum >= remaining) {
+        int need = remaining - above;
+        int digit = 0;
+        for (int j = 7; j >= 0; --j) {
+          if (c[j] >= need) { digit = j; break; }
+          need -= c[j];
+        }
+        ctl[0] = prefix | (static_cast<uint32_t>(tid * 8 + digit) << shift);
+        ctl[1] = static_cast<uint32_t>(need);
+      }
+    }
+    __syncthreads();
+    prefix = ctl[0];
+    remaining = static_cast<int>(ctl[1]);
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  return float_of(prefix);
+}
 
 // (score, id) ordering of torch.topk(largest=True) with a deterministic tie rule: lower id wins
 __device__ __forceinline__ bool better(float sa, long long ia, float sb, long long ib) {
   return sa > sb || (sa == sb && ia < ib);
 }
 
-// One block per query.  in: [lists*kc] candidates (id < 0 = empty).  Picks the `keep` best by
-// input score (block arg-max, repeated), optionally re-scores them in fp32, ranks, writes top k.
+// in-place bitonic sort of n2 (a power of two) pairs in shared memory, best first
+__device__ void block_sort_pairs(float* sc, long long* id, int n2) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = tid; i < (n2 >> 1); i += nt) {
+        const int lo = ((i / stride) * (stride << 1)) + (i % stride);
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);  // this sub-sequence is sorted best-first
+        const float sa = sc[lo], sb = sc[hi];
+        const long long ia = id[lo], ib = id[hi];
+        const bool swap = desc ? better(sb, ib, sa, ia) : better(sa, ia, sb, ib);
+        if (swap) { sc[lo] = sb; sc[hi] = sa; id[lo] = ib; id[hi] = ia; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// -----------------------------------------------------------------------------------------
+// merge / re-score
+// -----------------------------------------------------------------------------------------
+// One block per query.  in: [lists][kc] candidates (id < 0 = empty slot).
+//   t   = k-th largest candidate score (all candidates if there are fewer than k)
+//   cut = t - margin;  selected = every candidate with score >= cut  (at most kMaxSel)
+//   optional exact fp32 re-score of the selected rows, sort by (score desc, id asc), emit the top k.
+// overflow[q] (optional) is set when the selection may be incomplete: a list that is full (kc entries) whose
+// minimum is >= cut may have dropped rows the selection should contain, or more than kMaxSel were selected.
 template <typename IdT>
-__global__ void __launch_bounds__(kMergeThreads)
-merge_kernel(const float* __restrict__ in_score, const IdT* __restrict__ in_id, int total, int keep,
+__global__ void __launch_bounds__(kSelThreads)
+merge_kernel(const float* __restrict__ in_score, const IdT* __restrict__ in_id, int lists, int kc,
+             long long q_stride, long long l_stride_s, long long l_stride_i, float margin,
              const float* __restrict__ q_f32, const float* __restrict__ index_f32, int dim, int k,
-             long long id_offset, float* __restrict__ out_score, long long* __restrict__ out_id) {
+             long long id_offset, float* __restrict__ out_score, long long* __restrict__ out_id,
+             int* __restrict__ overflow) {
   extern __shared__ __align__(16) uint8_t msm[];
-  float* sc = reinterpret_cast<float*>(msm);                 // [total]
-  long long* sel_id = reinterpret_cast<long long*>(sc + ((total + 1) & ~1));  // [kMaxKc]
-  float* sel_sc = reinterpret_cast<float*>(sel_id + kMaxKc);  // [kMaxKc]
-  __shared__ float red_s[kMergeThreads / 32];
-  __shared__ int red_i[kMergeThreads / 32];
-  __shared__ int winner;
+  const int total = lists * kc;
+  long long* sel_id = reinterpret_cast<long long*>(msm);                 // [kMaxSel]
+  float* sel_sc = reinterpret_cast<float*>(sel_id + kMaxSel);            // [kMaxSel]
+  float* sc = sel_sc + kMaxSel;                                          // [total]
+  __shared__ int hist[256];
+  __shared__ uint32_t ctl[2];
+  __shared__ int n_valid, n_sel, ovf;
 
   const int qi = blockIdx.x;
   const int tid = threadIdx.x;
-  const float* qs = in_score + static_cast<size_t>(qi) * total;
-  const IdT* qid = in_id + static_cast<size_t>(qi) * total;
-  for (int i = tid; i < total; i += kMergeThreads) sc[i] = (qid[i] < 0) ? -INFINITY : qs[i];
+  // candidate (list l, slot j) of this query sits at [qi * q_stride + l * l_stride + j]; scores and ids may
+  // have different list strides (the gathered per-rank chunks hold 8-byte ids and 4-byte scores)
+  const float* qs = in_score + static_cast<size_t>(qi) * q_stride;
+  const IdT* qid = in_id + static_cast<size_t>(qi) * q_stride;
+  auto at_s = [&](int i) { return static_cast<size_t>(i / kc) * l_stride_s + (i % kc); };
+  auto at_i = [&](int i) { return static_cast<size_t>(i / kc) * l_stride_i + (i % kc); };
+  if (tid == 0) { n_valid = 0; n_sel = 0; ovf = 0; }
   __syncthreads();
+  int mine = 0;
+  for (int i = tid; i < total; i += kSelThreads) {
+    const bool ok = qid[at_i(i)] >= 0;
+    sc[i] = ok ? qs[at_s(i)] : -INFINITY;
+    mine += ok ? 1 : 0;
+  }
+  mine = static_cast<int>(warp_sum(static_cast<float>(mine)));  // exact: counts < 2^24
+  if ((tid & 31) == 0 && mine) atomicAdd(&n_valid, mine);
+  __syncthreads();
+  const int nv = n_valid;
+  float cut = -INFINITY;
+  if (nv > k) cut = block_kth_largest(sc, total, k, hist, ctl) - margin;  // uniform branch
 
-  int nsel = 0;
-  for (int round = 0; round < keep; ++round) {
-    float bs = -INFINITY;
-    int bi = -1;
-    for (int i = tid; i < total; i += kMergeThreads) {
-      const float s = sc[i];
-      if (s == -INFINITY) continue;  // empty slot or already selected
-      if (bi < 0 || s > bs || (s == bs && qid[i] < qid[bi])) { bs = s; bi = i; }
-    }
+  // a full list whose minimum is still inside the cut may have dropped rows that belong to the selection
+  if (overflow != nullptr) {
+    for (int l = (tid >> 5); l < lists; l += kSelThreads / 32) {
+      float mn = INFINITY;
+      int cnt = 0;
+      for (int j = (tid & 31); j < kc; j += 32) {
+        const float x = sc[l * kc + j];
+        if (x != -INFINITY) { ++cnt; mn = fminf(mn, x); }
+      }
+      cnt = static_cast<int>(warp_sum(static_cast<float>(cnt)));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (oi >= 0 && (bi < 0 || os > bs || (os == bs && qid[oi] < qid[bi]))) { bs = os; bi = oi; }
+      for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      if ((tid & 31) == 0 && cnt == kc && mn >= cut) ovf = 1;
     }
-    if ((tid & 31) == 0) { red_s[tid >> 5] = bs; red_i[tid >> 5] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-      float ws = red_s[0];
-      int wi = red_i[0];
-      for (int w = 1; w < kMergeThreads / 32; ++w) {
-        const float os = red_s[w];
-        const int oi = red_i[w];
-        if (oi >= 0 && (wi < 0 || os > ws || (os == ws && qid[oi] < qid[wi]))) { ws = os; wi = oi; }
-      }
-      winner = wi;
-      if (wi >= 0) {
-        sel_id[round] = static_cast<long long>(qid[wi]);
-        sel_sc[round] = ws;
-        sc[wi] = -INFINITY;
+  }
+  // selection (order irrelevant: everything selected is re-scored / sorted below)
+  for (int i = tid; i < total; i += kSelThreads) {
+    const float x = sc[i];
+    if (x != -INFINITY && x >= cut) {
+      const int slot = atomicAdd(&n_sel, 1);
+      if (slot < kMaxSel) {
+        sel_sc[slot] = x;
+        sel_id[slot] = static_cast<long long>(qid[at_i(i)]);
       }
     }
-    __syncthreads();
-    if (winner < 0) break;
-    nsel = round + 1;
   }
   __syncthreads();
+  int nsel = n_sel;
+  if (nsel > kMaxSel) {
+    nsel = kMaxSel;
+    if (tid == 0) ovf = 1;
+  }
 
   // exact fp32 re-score: one warp per candidate
   if (index_f32 != nullptr) {
     const float4* q4 = reinterpret_cast<const float4*>(q_f32 + static_cast<size_t>(qi) * dim);
     const int n4 = dim >> 2;
-    for (int cnd = (tid >> 5); cnd < nsel; cnd += kMergeThreads / 32) {
+    for (int cnd = (tid >> 5); cnd < nsel; cnd += kSelThreads / 32) {
       const float4* e4 =
           reinterpret_cast<const float4*>(index_f32 + static_cast<size_t>(sel_id[cnd]) * dim);
       float s = 0.f;
@@ -463,40 +569,32 @@ merge_kernel(const float* __restrict__ in_score, const IdT* __restrict__ in_id, 
       s = warp_sum(s);
       if ((tid & 31) == 0) sel_sc[cnd] = s;
     }
-    __syncthreads();
   }
-
-  // rank by (score desc, id asc); nsel <= 64 so a counting rank is cheapest
-  if (tid < nsel) {
-    const float s = sel_sc[tid];
-    const long long id = sel_id[tid];
-    int rank = 0;
-    for (int j = 0; j < nsel; ++j)
-      if (j != tid && better(sel_sc[j], sel_id[j], s, id)) ++rank;
-    if (rank < k) {
-      out_score[static_cast<size_t>(qi) * k + rank] = s;
-      out_id[static_cast<size_t>(qi) * k + rank] = id + id_offset;
-    }
+  int n2 = 1;
+  while (n2 < nsel) n2 <<= 1;
+  for (int i = nsel + tid; i < n2; i += kSelThreads) { sel_sc[i] = -INFINITY; sel_id[i] = 0x7fffffffffffffffLL; }
+  block_sort_pairs(sel_sc, sel_id, n2);  // starts with a __syncthreads()
+  for (int j = tid; j < k; j += kSelThreads) {
+    const bool ok = j < nsel;
+    out_score[static_cast<size_t>(qi) * k + j] = ok ? sel_sc[j] : -INFINITY;
+    out_id[static_cast<size_t>(qi) * k + j] = ok ? sel_id[j] + id_offset : -1;  // fewer than k candidates: pad
   }
-  // fewer than k candidates (tiny index): pad
-  for (int j = nsel + tid; j < k; j += kMergeThreads) {
-    out_score[static_cast<size_t>(qi) * k + j] = -INFINITY;
-    out_id[static_cast<size_t>(qi) * k + j] = -1;
-  }
+  if (overflow != nullptr && tid == 0) overflow[qi] = ovf;
 }
 
 template <typename IdT>
-int launch_merge(const float* in_score, const IdT* in_id, int nq, int total, int keep,
-                 const float* q_f32, const float* index_f32, int dim, int k, long long id_offset,
-                 float* out_score, long long* out_id, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>((total + 1) & ~1) * 4 + kMaxKc * 8 + kMaxKc * 4;
+int launch_merge(const float* in_score, const IdT* in_id, int nq, int lists, int kc, long long q_stride,
+                 long long l_stride_s, long long l_stride_i, float margin, const float* q_f32, const float* index_f32, int dim, int k, long long id_offset,
+                 float* out_score, long long* out_id, int* overflow, cudaStream_t s) {
+  const int total = lists * kc;
+  const size_t smem = static_cast<size_t>(kMaxSel) * 12 + static_cast<size_t>(total) * 4;
   CLM_REQUIRE(smem <= 200 * 1024, "topk merge: %d candidates per query exceed shared memory", total);
   if (smem > 48 * 1024)
     CLM_CUDA_CHECK(cudaFuncSetAttribute(merge_kernel<IdT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
-  ProfScope prof(CLM_K_MERGE, 0.0, 8.0 * nq * total + (index_f32 ? 4.0 * nq * keep * dim : 0.0), s);
-  merge_kernel<IdT><<<nq, kMergeThreads, smem, s>>>(in_score, in_id, total, keep, q_f32, index_f32,
-                                                    dim, k, id_offset, out_score, out_id);
+  ProfScope prof(CLM_K_MERGE, 0.0, 8.0 * nq * total + (index_f32 ? 4.0 * nq * k * dim : 0.0), s);
+  merge_kernel<IdT><<<nq, kSelThreads, smem, s>>>(in_score, in_id, lists, kc, q_stride, l_stride_s, l_stride_i, margin, q_f32,
+                                                  index_f32, dim, k, id_offset, out_score, out_id, overflow);
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
 }
@@ -520,52 +618,63 @@ gemv_kernel(const float* __restrict__ q, const float* __restrict__ e, int n, int
   if ((threadIdx.x & 31) == 0) out[row] = s;
 }
 
-// kth largest value of each row of a [rows, n] fp32 matrix (n <= 16384): one block per row, the row
-// is staged in shared memory and the block arg-max is removed kth-1 times.  Used to seed the scan's
-// per-query threshold from the scores of a small sample of index rows.
-constexpr int kSelThreads = 256;
+// kth largest value of each row of a [rows, n] fp32 matrix (n <= 16384): one block per row, the row is staged
+// in shared memory and radix-selected (four histogram passes instead of kth arg-max rounds).  Used to seed the scan's per-query threshold from the
+// scores of a small sample of index rows.
 __global__ void __launch_bounds__(kSelThreads)
 kth_largest_kernel(const float* __restrict__ x, int n, int kth, float guard, float* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t ksm[];
-  float* v = reinterpret_cast<float*>(ksm);
-  __shared__ float red_v[kSelThreads / 32];
-  __shared__ int red_i[kSelThreads / 32];
-  __shared__ int win;
-  const int tid = threadIdx.x;
+  float* stage = reinterpret_cast<float*>(ksm);
+  __shared__ int hist[256];
+  __shared__ uint32_t ctl[2];
   const float* row = x + static_cast<size_t>(blockIdx.x) * n;
-  for (int i = tid; i < n; i += kSelThreads) v[i] = row[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) stage[i] = row[i];
   __syncthreads();
-  float best = -INFINITY;
-  for (int round = 0; round < kth; ++round) {
-    float bv = -INFINITY;
-    int bi = -1;
-    for (int i = tid; i < n; i += kSelThreads) {
-      const float a = v[i];
-      if (a > bv) { bv = a; bi = i; }
+  const float v = block_kth_largest(stage, n, kth, hist, ctl);
+  if (threadIdx.x == 0) out[blockIdx.x] = v - guard;
+}
+
+// Exact top-k of ONE row of n fp32 scores (the reference's torch.topk(sims, k), src/embedding/search.py:99),
+// for the cases the fused scan hands back (an overflowed candidate list, k larger than the lists hold).
+// One block: radix select of the k-th largest value tau, gather of everything above tau plus enough entries
+// equal to tau (ties are interchangeable), bitonic sort.  k <= kMaxSel.
+__global__ void __launch_bounds__(1024)
+topk_row_kernel(const float* __restrict__ x, int n, int k, long long id_offset, float* __restrict__ out_score,
+                long long* __restrict__ out_id) {
+  extern __shared__ __align__(16) uint8_t tsm[];
+  long long* sel_id = reinterpret_cast<long long*>(tsm);        // [n2]
+  float* sel_sc = reinterpret_cast<float*>(sel_id + kMaxSel);   // [n2]
+  __shared__ int hist[256];
+  __shared__ uint32_t ctl[2];
+  __shared__ int n_gt, n_eq;
+  const int tid = threadIdx.x;
+  if (tid == 0) { n_gt = 0; n_eq = 0; }
+  const float tau = block_kth_largest(x, n, k, hist, ctl);  // syncs inside
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float v = x[i];
+    if (v > tau) {
+      const int slot = atomicAdd(&n_gt, 1);  // fewer than k values exceed the k-th largest
+      sel_sc[slot] = v;
+      sel_id[slot] = i;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv) { bv = ov; bi = oi; }
-    }
-    if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-      float wv = red_v[0];
-      int wi = red_i[0];
-      for (int w = 1; w < kSelThreads / 32; ++w)
-        if (red_v[w] > wv) { wv = red_v[w]; wi = red_i[w]; }
-      win = wi;
-      if (wi >= 0) v[wi] = -INFINITY;
-      red_v[0] = wv;
-    }
-    __syncthreads();
-    best = red_v[0];
-    if (win < 0) { best = -INFINITY; break; }
-    __syncthreads();
   }
-  if (tid == 0) out[blockIdx.x] = best - guard;
+  __syncthreads();
+  const int ngt = n_gt;
+  for (int i = tid; i < n; i += blockDim.x) {
+    if (x[i] == tau) {
+      const int slot = ngt + atomicAdd(&n_eq, 1);
+      if (slot < k) { sel_sc[slot] = tau; sel_id[slot] = i; }
+    }
+  }
+  __syncthreads();
+  int n2 = 1;
+  while (n2 < k) n2 <<= 1;
+  for (int i = k + tid; i < n2; i += blockDim.x) { sel_sc[i] = -INFINITY; sel_id[i] = 0x7fffffffffffffffLL; }
+  block_sort_pairs(sel_sc, sel_id, n2);
+  for (int j = tid; j < k; j += blockDim.x) {
+    out_score[j] = sel_sc[j];
+    out_id[j] = sel_id[j] + id_offset;
+  }
 }
 
 int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
@@ -595,13 +704,17 @@ extern "C" int clm_search_num_splits(int num_queries, int num_rows) {
   return splits;
 }
 
+constexpr int kMaxKc = 64;       // capacity of one (query, split) candidate list of the scan
+constexpr int kMaxMergeK = 1024;  // largest k the merge emits (half of kMaxSel: room for the margin's extras)
+
 extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int nq, int n, int dim,
-                               int kc, int splits, float* thr_io, float* cand_score,
+                               int kc, int splits, float* thr_io, float margin, float* cand_score,
                                int32_t* cand_id, void* stream) {
   CLM_REQUIRE(q_bf16 && index_bf16 && cand_score && cand_id, "clm_search_topk: null argument");
   CLM_REQUIRE(nq > 0 && n > 0 && dim > 0 && dim % 8 == 0, "clm_search_topk: bad shape nq=%d n=%d dim=%d",
               nq, n, dim);
   CLM_REQUIRE(kc >= 1 && kc <= kMaxKc, "clm_search_topk: kc=%d must be in [1,%d]", kc, kMaxKc);
+  CLM_REQUIRE(margin >= 0.f, "clm_search_topk: margin must be >= 0");
   const int ctas = search_ctas(nq);
   const int q_tiles = (nq + BM * ctas - 1) / (BM * ctas);
   const int tiles_n = (n + BN - 1) / BN;
@@ -629,6 +742,7 @@ extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int n
   p.kc = kc;
   p.a_bytes = q_box_rows * BK * 2;
   p.thr_io = thr_io;
+  p.margin = margin;
   p.cand_score = cand_score;
   p.cand_id = cand_id;
   const int stage_bytes = ctas == 2 ? SCfg<2>::kStageBytes : SCfg<1>::kStageBytes;
@@ -650,25 +764,62 @@ extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int n
 }
 
 extern "C" int clm_topk_merge(const float* cand_score, const int32_t* cand_id, int nq, int lists, int kc,
-                              const float* q_f32, const float* index_f32, int dim, int k,
-                              int64_t id_offset, float* out_score, int64_t* out_id, void* stream) {
+                              float margin, const float* q_f32, const float* index_f32, int dim, int k,
+                              int64_t id_offset, float* out_score, int64_t* out_id, int32_t* overflow,
+                              void* stream) {
   CLM_REQUIRE(cand_score && cand_id && out_score && out_id, "clm_topk_merge: null argument");
-  CLM_REQUIRE(nq > 0 && lists > 0 && kc >= 1 && kc <= kMaxKc && k >= 1 && k <= kc,
-              "clm_topk_merge: bad sizes nq=%d lists=%d kc=%d k=%d", nq, lists, kc, k);
+  CLM_REQUIRE(nq > 0 && lists > 0 && kc >= 1 && k >= 1 && k <= kMaxMergeK && margin >= 0.f,
+              "clm_topk_merge: bad sizes nq=%d lists=%d kc=%d k=%d (k <= %d)", nq, lists, kc, k, kMaxMergeK);
   CLM_REQUIRE(index_f32 == nullptr || (q_f32 != nullptr && dim % 4 == 0),
               "clm_topk_merge: re-scoring needs fp32 queries and dim %% 4 == 0");
-  return launch_merge<int32_t>(cand_score, cand_id, nq, lists * kc, kc, q_f32, index_f32, dim, k,
+  return launch_merge<int32_t>(cand_score, cand_id, nq, lists, kc, static_cast<long long>(lists) * kc, kc, kc, margin,
+                               q_f32, index_f32, dim, k,
                                static_cast<long long>(id_offset), out_score,
-                               reinterpret_cast<long long*>(out_id), static_cast<cudaStream_t>(stream));
+                               reinterpret_cast<long long*>(out_id), overflow, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int clm_topk_merge_sorted(const float* in_score, const int64_t* in_id, int nq, int lists,
                                      int k, float* out_score, int64_t* out_id, void* stream) {
   CLM_REQUIRE(in_score && in_id && out_score && out_id, "clm_topk_merge_sorted: null argument");
-  CLM_REQUIRE(nq > 0 && lists > 0 && k >= 1 && k <= kMaxKc, "clm_topk_merge_sorted: bad sizes");
-  return launch_merge<long long>(in_score, reinterpret_cast<const long long*>(in_id), nq, lists * k, k,
-                                 nullptr, nullptr, 0, k, 0, out_score,
-                                 reinterpret_cast<long long*>(out_id), static_cast<cudaStream_t>(stream));
+  CLM_REQUIRE(nq > 0 && lists > 0 && k >= 1 && k <= kMaxMergeK, "clm_topk_merge_sorted: bad sizes (k <= %d)",
+              kMaxMergeK);
+  return launch_merge<long long>(in_score, reinterpret_cast<const long long*>(in_id), nq, lists, k,
+                                 static_cast<long long>(lists) * k, k, k, 0.f, nullptr, nullptr, 0, k, 0, out_score,
+                                 reinterpret_cast<long long*>(out_id), nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t clm_topk_gather_chunk_bytes(int nq, int k) {
+  if (nq <= 0 || k <= 0) return 0;
+  const size_t pairs = (static_cast<size_t>(nq) * k + 1) / 2 * 2;  // even: the next rank's ids stay 8-byte aligned
+  return pairs * 12;
+}
+
+extern "C" int clm_topk_merge_gathered(const void* gathered, int world, int nq, int k, float* out_score,
+                                       int64_t* out_id, void* stream) {
+  CLM_REQUIRE(gathered && out_score && out_id, "clm_topk_merge_gathered: null argument");
+  CLM_REQUIRE(world > 0 && nq > 0 && k >= 1 && k <= kMaxMergeK, "clm_topk_merge_gathered: bad sizes (k <= %d)",
+              kMaxMergeK);
+  CLM_REQUIRE((reinterpret_cast<uintptr_t>(gathered) & 7) == 0, "clm_topk_merge_gathered: buffer not 8-byte aligned");
+  const size_t chunk = clm_topk_gather_chunk_bytes(nq, k);
+  const size_t pairs = chunk / 12;
+  const long long* ids = reinterpret_cast<const long long*>(gathered);
+  const float* scores = reinterpret_cast<const float*>(static_cast<const uint8_t*>(gathered) + pairs * 8);
+  // rank l's chunk starts l * chunk bytes further: chunk / 8 id elements, chunk / 4 score elements (both exact:
+  // chunk = 12 * pairs with pairs even); inside a chunk query qi's k entries start at qi * k
+  return launch_merge<long long>(scores, ids, nq, world, k, k, static_cast<long long>(chunk / 4),
+                                 static_cast<long long>(chunk / 8), 0.f, nullptr, nullptr, 0, k, 0, out_score,
+                                 reinterpret_cast<long long*>(out_id), nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int clm_topk_row(const float* scores, int n, int k, int64_t id_offset, float* out_score,
+                            int64_t* out_id, void* stream) {
+  CLM_REQUIRE(scores && out_score && out_id && n >= 1 && k >= 1 && k <= n && k <= kMaxSel,
+              "clm_topk_row: bad argument (n=%d k=%d; k <= min(n, %d))", n, k, kMaxSel);
+  ProfScope prof(CLM_K_MERGE, 0.0, 6.0 * 4.0 * n, static_cast<cudaStream_t>(stream));
+  topk_row_kernel<<<1, 1024, kMaxSel * 12, static_cast<cudaStream_t>(stream)>>>(
+      scores, n, k, static_cast<long long>(id_offset), out_score, reinterpret_cast<long long*>(out_id));
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
 }
 
 extern "C" int clm_cosine_gemv(const float* q_f32, const float* index_f32, int n, int dim, float* out,

@@ -131,49 +131,104 @@ def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, causal: bo
 
 
 SAMPLE_ROWS = 16384  # rows whose exact scores seed the scan thresholds (multiple of 256)
+# |bf16 score - fp32 score| for L2-normalised rows rounded to bf16: each factor carries a relative error of at
+# most 2^-9, so a product is off by at most ~2^-8 |q_i e_i| and the dot product by 2^-8 sum|q_i e_i| <= 2^-8
+# (Cauchy-Schwarz, unit norms); fp32 accumulation adds ~1e-5.
+EPS_BF16 = 2.0 ** -8 + 1e-5
+FUSED_MAX_K = 1024   # largest k of the fused scan + merge (clm_topk_merge)
+EXACT_MAX_K = 2048   # largest k of the exact one-query path (clm_topk_row)
+LIST_CAP = 64        # capacity of one (query, split) candidate list of the scan
+
+
+def exact_topk_row(q_f32_row: torch.Tensor, index_f32: torch.Tensor, k: int, id_offset: int = 0,
+                   out_s: Optional[torch.Tensor] = None, out_i: Optional[torch.Tensor] = None):
+    """The reference's batch-1 search, exactly: fp32 scores of one normalised query against every row
+    (clm_cosine_gemv) and their top-k (clm_topk_row).  k <= min(n, 2048)."""
+    n = index_f32.shape[0]
+    if not (1 <= k <= min(n, EXACT_MAX_K)):
+        raise ValueError(f"k must be in [1, min(rows, {EXACT_MAX_K})], got {k}")
+    scores = cosine_gemv(q_f32_row, index_f32)
+    if out_s is None:
+        out_s = torch.empty((k,), dtype=torch.float32, device=index_f32.device)
+        out_i = torch.empty((k,), dtype=torch.int64, device=index_f32.device)
+    check(_lib.load().clm_topk_row(ptr(scores), n, k, id_offset, ptr(out_s), ptr(out_i), cur_stream()),
+          "clm_topk_row")
+    return out_s, out_i
 
 
 def search_topk(q_f32: torch.Tensor, q_bf16: torch.Tensor, index_bf16: torch.Tensor,
                 index_f32: Optional[torch.Tensor], k: int, id_offset: int = 0,
-                margin: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Top-k of q @ index.T: bf16 tensor-core scan + fused per-tile top-kc, then fp32 re-score.
+                margin: Optional[float] = None, list_cap: Optional[int] = None,
+                stats: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Top-k of q @ index.T: bf16 tensor-core scan with fused per-(query, split) candidate lists, then an exact
+    fp32 re-score of every candidate the bf16 scores cannot rule out.
 
-    Returns (scores fp32 [Q,k], ids int64 [Q,k]) sorted descending; ids are global
-    (id_offset added).  k must be <= rows of the index shard (the caller clamps, as the
-    reference does at src/embedding/search.py:98)."""
+    Exactness: bf16 scores only nominate.  With |bf16 - fp32| <= eps per row, every row of the fp32 top-k has
+    a bf16 score >= t_k - 2 eps (t_k = k-th best bf16 score), so the scan keeps everything above its running
+    lower bound of t_k minus `margin` = 2 eps and the merge re-scores ALL candidates >= t_k - margin (a
+    data-dependent number, not k + a constant).  A candidate list that fills up with rows inside that window may
+    have dropped one; the merge flags such queries and they are redone with the exact fp32 scan
+    (exact_topk_row), so the returned ids equal torch.topk of the fp32 scores up to exact ties.
+
+    Returns (scores fp32 [Q,k], ids int64 [Q,k]) sorted descending; ids are global (id_offset added).
+    1 <= k <= rows of the shard (the caller clamps, as the reference does at src/embedding/search.py:98);
+    k <= 1024 on the fused path, <= 2048 overall (larger k runs the exact path per query).
+    `stats`, if given, receives {"overflow_queries": int, "lists": splits, "list_cap": kc}."""
     _req(q_f32, torch.float32, "q_f32"); _req(q_bf16, torch.bfloat16, "q_bf16")
     _req(index_bf16, torch.bfloat16, "index_bf16")
     if index_f32 is not None:
         _req(index_f32, torch.float32, "index_f32")
     nq, dim = q_bf16.shape
     n = index_bf16.shape[0]
-    if not (1 <= k <= 64):
-        raise ValueError("k must be in [1, 64]")
-    if margin is None:
-        margin = 6 if index_f32 is not None else 0
-    kc = max(k, min(64, max(k + margin, 16)))  # candidates kept per (query, split)
+    if not (1 <= k <= n):
+        raise ValueError(f"k must be in [1, rows={n}], got {k}")
     lib = _lib.load()
     dev = q_bf16.device
-    # Per-query running threshold shared by all work units of the scan (see clm_search_topk).
-    # It is seeded from a sample: scores of the queries against the first SAMPLE_ROWS index rows
-    # (plain tcgen05 GEMM, same bf16 operands as the scan) -> exact kc-th largest per query.
-    if n >= 4 * SAMPLE_ROWS:
-        sample_scores = gemm_epi(q_bf16, index_bf16[:SAMPLE_ROWS], out_dtype=torch.float32)
-        thr = torch.empty((nq,), dtype=torch.float32, device=dev)
-        check(lib.clm_kth_largest(ptr(sample_scores), nq, SAMPLE_ROWS, kc, 1e-6, ptr(thr), cur_stream()),
-              "clm_kth_largest")
-        del sample_scores
-    else:
-        thr = torch.full((nq,), float("-inf"), dtype=torch.float32, device=dev)
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    if k > FUSED_MAX_K:
+        if index_f32 is None or k > EXACT_MAX_K:
+            raise ValueError(f"top_k={k} is not supported: the fused search handles k <= {FUSED_MAX_K}, the exact "
+                             f"fp32 path k <= {EXACT_MAX_K}")
+        for qi in range(nq):
+            exact_topk_row(q_f32[qi], index_f32, k, id_offset, out_s[qi], out_i[qi])
+        if stats is not None:
+            stats.update(overflow_queries=nq, lists=0, list_cap=0)
+        return out_s, out_i
+    if margin is None:
+        margin = 2.0 * EPS_BF16 if index_f32 is not None else 0.0
+    kc = list_cap if list_cap is not None else min(LIST_CAP, max(32, 2 * k))  # candidates kept per (query, split)
+    # Per-query running lower bound of t_k shared by all work units of the scan (see clm_search_topk): a
+    # unit's full list proves kc rows above its minimum, which bounds t_k only if kc >= k.  It is seeded from
+    # a sample: scores of the queries against the first SAMPLE_ROWS index rows (plain tcgen05 GEMM, same bf16
+    # operands as the scan) -> exact k-th largest per query.
+    thr = None
+    if kc >= k:
+        if n >= 4 * SAMPLE_ROWS:
+            sample_scores = gemm_epi(q_bf16, index_bf16[:SAMPLE_ROWS], out_dtype=torch.float32)
+            thr = torch.empty((nq,), dtype=torch.float32, device=dev)
+            check(lib.clm_kth_largest(ptr(sample_scores), nq, SAMPLE_ROWS, k, 1e-5, ptr(thr), cur_stream()),
+                  "clm_kth_largest")
+            del sample_scores
+        else:
+            thr = torch.full((nq,), float("-inf"), dtype=torch.float32, device=dev)
     splits = lib.clm_search_num_splits(nq, n)
     cand_s = torch.empty((nq, splits, kc), dtype=torch.float32, device=dev)
     cand_i = torch.empty((nq, splits, kc), dtype=torch.int32, device=dev)
-    check(lib.clm_search_topk(ptr(q_bf16), ptr(index_bf16), nq, n, dim, kc, splits, ptr(thr),
+    check(lib.clm_search_topk(ptr(q_bf16), ptr(index_bf16), nq, n, dim, kc, splits, ptr(thr), float(margin),
                               ptr(cand_s), ptr(cand_i), cur_stream()), "clm_search_topk")
-    out_s = torch.empty((nq, k), dtype=torch.float32, device=q_bf16.device)
-    out_i = torch.empty((nq, k), dtype=torch.int64, device=q_bf16.device)
-    check(lib.clm_topk_merge(ptr(cand_s), ptr(cand_i), nq, splits, kc, ptr(q_f32), ptr(index_f32), dim,
-                             k, id_offset, ptr(out_s), ptr(out_i), cur_stream()), "clm_topk_merge")
+    overflow = torch.empty((nq,), dtype=torch.int32, device=dev) if index_f32 is not None else None
+    check(lib.clm_topk_merge(ptr(cand_s), ptr(cand_i), nq, splits, kc, float(margin), ptr(q_f32), ptr(index_f32),
+                             dim, k, id_offset, ptr(out_s), ptr(out_i), ptr(overflow), cur_stream()),
+          "clm_topk_merge")
+    n_over = 0
+    if overflow is not None:
+        bad = torch.nonzero(overflow).reshape(-1).tolist()  # one host sync per call; empty on ordinary data
+        n_over = len(bad)
+        for qi in bad:
+            exact_topk_row(q_f32[qi], index_f32, k, id_offset, out_s[qi], out_i[qi])
+    if stats is not None:
+        stats.update(overflow_queries=n_over, lists=splits, list_cap=kc)
     return out_s, out_i
 
 
@@ -190,6 +245,41 @@ def topk_merge_sorted(scores: torch.Tensor, ids: torch.Tensor, k: int) -> Tuple[
     return out_s, out_i
 
 
+def topk_gather_chunk_bytes(nq: int, k: int) -> int:
+    return int(_lib.load().clm_topk_gather_chunk_bytes(nq, k))
+
+
+def pack_topk_chunk(scores: Optional[torch.Tensor], ids: Optional[torch.Tensor], nq: int, k: int,
+                    device: torch.device) -> torch.Tensor:
+    """One rank's contribution to the exchange step: uint8 [chunk_bytes] holding int64 ids [nq*k] (padded to an
+    even count) then fp32 scores [nq*k]; rows shorter than k (a shard with fewer than k rows) are padded with
+    (id -1, score -inf).  Layout of clm_topk_merge_gathered (include/clm_b200.h)."""
+    nbytes = topk_gather_chunk_bytes(nq, k)
+    pairs = nbytes // 12
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    ids_v = buf[: pairs * 8].view(torch.int64)
+    sc_v = buf[pairs * 8:].view(torch.float32)
+    ids_v.fill_(-1)
+    sc_v.fill_(float("-inf"))
+    if scores is not None and scores.shape[1] > 0:
+        kl = scores.shape[1]
+        ids_v[: nq * k].view(nq, k)[:, :kl] = ids
+        sc_v[: nq * k].view(nq, k)[:, :kl] = scores
+    return buf
+
+
+def topk_merge_gathered(gathered: torch.Tensor, world: int, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Global top-k from the all-gathered per-rank chunks (rank-major, pack_topk_chunk layout), read in place."""
+    _req(gathered, torch.uint8, "gathered")
+    if gathered.numel() != world * topk_gather_chunk_bytes(nq, k):
+        raise ValueError("gathered buffer has the wrong size")
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=gathered.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=gathered.device)
+    check(_lib.load().clm_topk_merge_gathered(ptr(gathered), world, nq, k, ptr(out_s), ptr(out_i), cur_stream()),
+          "clm_topk_merge_gathered")
+    return out_s, out_i
+
+
 def rescore(cand_score: torch.Tensor, cand_id: torch.Tensor, q_f32: torch.Tensor,
             index_f32: torch.Tensor, k: int, id_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """Exact fp32 scores of nominated rows: cand_* [Q, lists, kc] -> top-k (score desc, id asc)."""
@@ -198,9 +288,9 @@ def rescore(cand_score: torch.Tensor, cand_id: torch.Tensor, q_f32: torch.Tensor
     nq, lists, kc = cand_score.shape
     out_s = torch.empty((nq, k), dtype=torch.float32, device=q_f32.device)
     out_i = torch.empty((nq, k), dtype=torch.int64, device=q_f32.device)
-    check(_lib.load().clm_topk_merge(ptr(cand_score), ptr(cand_id), nq, lists, kc, ptr(q_f32),
+    check(_lib.load().clm_topk_merge(ptr(cand_score), ptr(cand_id), nq, lists, kc, 0.0, ptr(q_f32),
                                      ptr(index_f32), q_f32.shape[1], k, id_offset, ptr(out_s), ptr(out_i),
-                                     cur_stream()), "clm_topk_merge")
+                                     None, cur_stream()), "clm_topk_merge")
     return out_s, out_i
 
 

@@ -9,7 +9,7 @@ Reference surface kept (names, argument order, exceptions, result type):
 Extensions:
   .search_batch(queries [Q,d], top_k) -> (scores [Q,k], ids [Q,k]) device tensors
   row sharding over torch.distributed ranks (each GPU holds a contiguous block of rows, local
-  fused top-k, ONE all_gather of Q*k (score,id) pairs, merge) — SURVEY.md §8(e).
+  fused top-k, ONE all_gather_into_tensor of the packed Q*k (id, score) pairs, merge in place) — SURVEY.md §8(e).
 
 The index lives on the GPU as an fp32 master (exact re-scoring) plus a bf16 shadow (the copy
 the tensor-core scan streams).  Loading accepts both metadata key spellings of the
@@ -52,23 +52,30 @@ def shard_bounds(num_rows: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def gather_shard_topk(scores: Optional[torch.Tensor], ids: Optional[torch.Tensor], nq: int, k: int,
-                      device: torch.device, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """The one exchange step of the sharded search: every rank contributes its local top-k
-    (padded to k with (-inf, -1)); returns [Q, world, k] scores / global ids on every rank.
-    Payload per rank is Q*k*12 bytes (328 KB..2.4 MB at Q=4096), i.e. latency-bound on NVLink."""
+                      device: torch.device, group=None) -> torch.Tensor:
+    """The one exchange step of the sharded search: every rank packs its local top-k (padded to k with
+    (id -1, score -inf)) into one chunk -- int64 ids, then fp32 scores (kernels.pack_topk_chunk) -- and ONE
+    all_gather_into_tensor collects the chunks rank-major.  Returns the gathered uint8 buffer
+    [world * chunk_bytes], which clm_topk_merge_gathered reads in place (no re-layout).  Payload per rank is
+    Q*k*12 bytes (0.5 MB at Q=4096, k=10; 2.4 MB at k=50), i.e. latency-bound on NVLink."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    pad_s = torch.full((nq, k), float("-inf"), dtype=torch.float32, device=device)
-    pad_i = torch.full((nq, k), -1, dtype=torch.int64, device=device)
-    if scores is not None and scores.shape[1] > 0:
-        kl = scores.shape[1]
-        pad_s[:, :kl], pad_i[:, :kl] = scores, ids
-    all_s = [torch.empty_like(pad_s) for _ in range(world)]
-    all_i = [torch.empty_like(pad_i) for _ in range(world)]
-    dist.all_gather(all_s, pad_s, group=group)
-    dist.all_gather(all_i, pad_i, group=group)
-    return torch.stack(all_s, dim=1).contiguous(), torch.stack(all_i, dim=1).contiguous()
+    mine = K.pack_topk_chunk(scores, ids, nq, k, device)
+    out = torch.empty(world * mine.numel(), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out
+
+
+def unpack_gathered_topk(gathered: torch.Tensor, world: int, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[Q, world, k] scores / ids views of a gathered buffer (host-side checks and tests; the GPU merge reads
+    the buffer in place)."""
+    chunk = K.topk_gather_chunk_bytes(nq, k)
+    pairs = chunk // 12
+    per_rank = gathered.view(world, chunk)
+    ids = per_rank[:, : pairs * 8].contiguous().view(torch.int64).view(world, pairs)[:, : nq * k].reshape(world, nq, k)
+    sc = per_rank[:, pairs * 8:].contiguous().view(torch.float32).view(world, pairs)[:, : nq * k].reshape(world, nq, k)
+    return sc.permute(1, 0, 2).contiguous(), ids.permute(1, 0, 2).contiguous()
 
 
 def allgather_rows(local: torch.Tensor, total_rows: int, group=None) -> torch.Tensor:
@@ -163,6 +170,7 @@ class TextSearchIndex:
         else:
             self.embeddings, self.embeddings_bf16 = local, local.to(torch.bfloat16)
         self.local_rows = self.embeddings.shape[0]
+        self.last_search_stats: dict = {}  # filled by search_batch: overflow_queries, lists, list_cap
 
     @classmethod
     def from_directory(cls, directory: Union[str, Path], device: Union[str, torch.device] = "cuda",
@@ -186,31 +194,35 @@ class TextSearchIndex:
     # ---- batched search (extension) ------------------------------------------------------
     def search_batch(self, queries: torch.Tensor, top_k: int = 5) -> Tuple[torch.Tensor, torch.Tensor]:
         """queries [Q, d] (any device) -> (scores fp32 [Q,k], global ids int64 [Q,k]) on the GPU,
-        sorted descending, k = min(top_k, N).  On a sharded index every rank passes the same
-        queries and gets the same merged result."""
+        sorted descending, k = min(top_k, N) as the reference (:98) -- any top_k: k <= 0 gives empty [Q, 0]
+        results (torch.topk with k = 0), k up to 1024 runs the fused scan, larger k (<= 2048, one GPU) the
+        exact per-query path.  On a sharded index every rank passes the same queries and gets the same
+        merged result."""
         if queries.dim() != 2:
             raise ValueError(f"queries must be [Q, d], got {tuple(queries.shape)}")
         if queries.shape[-1] != self.dim:
             raise ValueError(f"query_emb dim {queries.shape[-1]} != index dim {self.dim}")
-        k = min(top_k, self.num_items)
-        if k < 1:
-            raise ValueError("top_k must be >= 1 and the index non-empty")
-        if k > 64:
-            raise ValueError("top_k > 64 is not supported by the fused top-k kernel")
+        k = min(int(top_k), self.num_items)
+        nq = queries.shape[0]
+        if k <= 0 or nq == 0:
+            k = max(k, 0)
+            return (torch.empty((nq, k), dtype=torch.float32, device=self.device),
+                    torch.empty((nq, k), dtype=torch.int64, device=self.device))
+        sharded = self.distributed and self.world > 1
+        if k > (K.FUSED_MAX_K if sharded else K.EXACT_MAX_K):
+            raise ValueError(f"top_k={top_k} (k={k}) exceeds what the search kernels support: "
+                             f"{K.FUSED_MAX_K} on a sharded index, {K.EXACT_MAX_K} on one GPU")
         q = queries.to(device=self.device, dtype=torch.float32).contiguous()
         qn, qb = K.l2norm(q, want_bf16=True)  # reference :93
-        nq = qn.shape[0]
         k_local = min(k, self.local_rows)
+        s = i = None
         if k_local > 0:
             s, i = K.search_topk(qn, qb, self.embeddings_bf16, self.embeddings, k_local,
-                                 id_offset=self.row_offset)
-        if not self.distributed or self.world == 1:
+                                 id_offset=self.row_offset, stats=self.last_search_stats)
+        if not sharded:
             return s, i
-        if k_local > 0:
-            gs, gi = gather_shard_topk(s, i, nq, k, self.device)
-        else:
-            gs, gi = gather_shard_topk(None, None, nq, k, self.device)
-        return K.topk_merge_sorted(gs, gi, k)
+        gathered = gather_shard_topk(s, i, nq, k, self.device)
+        return K.topk_merge_gathered(gathered, self.world, nq, k)
 
     # ---- reference API -------------------------------------------------------------------
     def search_with_embedding(self, query_emb: torch.Tensor, top_k: int = 5) -> List[SearchResult]:

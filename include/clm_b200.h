@@ -222,13 +222,19 @@ int clm_search_num_splits(int num_queries, int num_rows);
  * from the bf16 shadow of the index; the score matrix stays in TMEM; every (query,
  * split) keeps its kc best candidates.  q_bf16 [nq, dim], index_bf16 [n, dim],
  * cand_score fp32 / cand_id int32 [nq, splits, kc].  dim multiple of 64, kc <= 64.
- * thr_io (fp32 [nq], may be NULL): per-query lower bound of the kc-th best score, shared by all
- * work units of the scan through atomic max.  The caller initialises it (-inf, or any valid lower
- * bound such as the result of a previous scan of other rows of the same index); on return it holds
- * the tightest bound the scan established.  Scores <= bound are never kept, so per-split lists may
- * hold fewer than kc entries; empty slots are (-inf, -1). */
+ * thr_io (fp32 [nq], may be NULL): per-query lower bound L of the kc-th best bf16 score over the whole
+ * index, shared by all work units of the scan through atomic max.  The caller initialises it (-inf, or any
+ * valid lower bound such as the kc-th best score of a sample of rows); on return it holds the tightest bound
+ * the scan established.  Scores <= L - margin are never kept, so per-split lists may hold fewer than kc
+ * entries; empty slots are (-inf, -1).
+ * margin: bf16 scores only NOMINATE rows for the exact fp32 re-score of clm_topk_merge.  With |bf16 score -
+ * fp32 score| <= eps for every row (unit-norm rows rounded to bf16: eps <= 2^-8), every row of the fp32
+ * top-k has a bf16 score >= t_k - 2 eps, t_k the k-th best bf16 score; since L <= t_kc <= t_k for kc >= k,
+ * margin = 2 eps keeps all of them.  Pass NULL for thr_io when kc < k (the list minimum of a unit is then no
+ * bound of t_k). */
 int clm_search_topk(const void* q_bf16, const void* index_bf16, int nq, int n, int dim, int kc,
-                    int splits, float* thr_io, float* cand_score, int32_t* cand_id, void* stream);
+                    int splits, float* thr_io, float margin, float* cand_score, int32_t* cand_id,
+                    void* stream);
 
 /* out[r] = (kth largest of x[r, 0..n)) - guard, for each of `rows` rows of a row-major fp32 matrix
  * (n <= 16384).  Seeds clm_search_topk's thr_io from the exact scores of a sample of index rows
@@ -236,18 +242,38 @@ int clm_search_topk(const void* q_bf16, const void* index_bf16, int nq, int n, i
  * whole index, so it is a valid bound; `guard` keeps ties with the bound alive. */
 int clm_kth_largest(const float* x, int rows, int n, int kth, float guard, float* out, void* stream);
 
-/* Second pass: per query merge splits*kc candidates to the kc best by first-pass score,
- * re-score those exactly in fp32 against the fp32 master rows (q_f32·E_f32[id]), sort
- * descending (ties: lower id first) and emit the top k with id_offset added (the shard's
- * first global row).  Reproduces torch.topk(largest=True, sorted=True) of search.py:99. */
-int clm_topk_merge(const float* cand_score, const int32_t* cand_id, int nq, int lists, int kc,
+/* Second pass, per query over its lists*kc candidates: t = k-th best first-pass score, select EVERY candidate
+ * with score >= t - margin (not a fixed number), re-score the selected rows exactly in fp32 against the fp32
+ * master rows (q_f32·E_f32[id]; skipped when index_f32 is NULL), sort descending (ties: lower id first) and
+ * emit the top k with id_offset added (the shard's first global row); fewer than k candidates pad with
+ * (-inf, -1).  Reproduces torch.topk(largest=True, sorted=True) of search.py:99.  k <= 1024.
+ * overflow (int32 [nq] or NULL): set to 1 for a query whose selection may be incomplete -- a list that is
+ * full and whose minimum is still >= t - margin may have dropped qualifying rows, or more than 2048 rows
+ * qualified -- so the caller can redo that query exactly (clm_cosine_gemv + clm_topk_row); 0 otherwise. */
+int clm_topk_merge(const float* cand_score, const int32_t* cand_id, int nq, int lists, int kc, float margin,
                    const float* q_f32, const float* index_f32, int dim, int k, int64_t id_offset,
-                   float* out_score, int64_t* out_id, void* stream);
+                   float* out_score, int64_t* out_id, int32_t* overflow, void* stream);
 
 /* Cross-shard merge after the allgather: in [nq, lists, k] (score, global id) ->
- * top k sorted.  No re-scoring (scores are already exact). */
+ * top k sorted.  No re-scoring (scores are already exact).  k <= 1024. */
 int clm_topk_merge_sorted(const float* in_score, const int64_t* in_id, int nq, int lists, int k,
                           float* out_score, int64_t* out_id, void* stream);
+
+/* The exchange step of the row-sharded search in ONE collective: every rank packs its local
+ * top-k into a chunk of clm_topk_gather_chunk_bytes(nq, k) bytes -- int64 global ids [nq*k] (padded to an even
+ * count), then fp32 scores [nq*k] -- and all-gathers the chunks rank-major into one buffer;
+ * clm_topk_merge_gathered reads that buffer in place ([world] chunks) and emits the global top k, sorted.
+ * Unused slots are (id -1, score -inf).  k <= 1024. */
+size_t clm_topk_gather_chunk_bytes(int nq, int k);
+int clm_topk_merge_gathered(const void* gathered, int world, int nq, int k, float* out_score,
+                            int64_t* out_id, void* stream);
+
+/* Exact top-k of one row of n fp32 scores, sorted descending (ties: lower id first among the rows kept;
+ * which of several rows EQUAL to the k-th score are kept is unspecified, as for torch.topk): the reference's
+ * torch.topk(sims, k) of src/embedding/search.py:99 / similarity.py:57 for the queries the fused scan hands
+ * back and for k beyond the fused path.  k <= min(n, 2048). */
+int clm_topk_row(const float* scores, int n, int k, int64_t id_offset, float* out_score, int64_t* out_id,
+                 void* stream);
 
 /* out[i] = q · E[i] in exact fp32 for ONE query: the reference's batch-1 scoring
  * (src/embedding/search.py:96, src/embedding/similarity.py:32).  Rows are expected to be

@@ -1,6 +1,6 @@
 """CPU test of the N>1 host path: world_size-2 gloo process group, row-sharded index, local
 top-k per rank (the oracle stands in for the CUDA scan here), the ONE exchange step
-(gather_shard_topk = all_gather of Q*k pairs) and the merge == unsharded oracle search.
+(gather_shard_topk = one all_gather_into_tensor of the packed Q*k pairs) and the merge == unsharded oracle search.
 """
 import os
 import socket
@@ -23,7 +23,7 @@ def _worker(rank, world, port, n, d, nq, k, ret):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from clip_lora_match_b200.src.embedding.search import gather_shard_topk, shard_bounds
+        from clip_lora_match_b200.src.embedding.search import gather_shard_topk, shard_bounds, unpack_gathered_topk
 
         index = O.synth_unit_rows(n, d, 4)
         queries = O.synth_unit_rows(nq, d, 5)
@@ -34,7 +34,9 @@ def _worker(rank, world, port, n, d, nq, k, ret):
             i = i + lo
         else:
             s = i = None
-        gs, gi = gather_shard_topk(s, i, nq, k, torch.device("cpu"))
+        buf = gather_shard_topk(s, i, nq, k, torch.device("cpu"))  # ONE all_gather_into_tensor of packed chunks
+        assert buf.dtype == torch.uint8 and buf.numel() == world * (((nq * k + 1) // 2 * 2) * 12)
+        gs, gi = unpack_gathered_topk(buf, world, nq, k)
         assert gs.shape == (nq, world, k) and gi.shape == (nq, world, k)
         # every rank merges the same candidates; checker merge = torch.topk over the gathered lists
         flat_s, flat_i = gs.reshape(nq, -1), gi.reshape(nq, -1)

@@ -354,7 +354,10 @@ def _check_topk(name, got_s, got_i, q, e, k):
     (16, 10000, 512, 10),    # config 1
     (1000, 10000, 512, 10),  # config 1, full query set
     (130, 70000, 768, 10),   # two query tiles, many splits, ragged last tile
-    (64, 40000, 768, 50),    # k = 50 (config 5): kc = 56, 3-stage ring
+    (64, 40000, 768, 50),    # k = 50 (config 5): 64-entry lists
+    (300, 50000, 512, 100),  # top_k beyond one list: kc = 64 < k, no shared bound, CTA-pair scan
+    (3, 9000, 512, 700),     # large k on the fused path (k <= 1024)
+    (2, 3000, 256, 1500),    # beyond the fused path: exact per-query scan (clm_cosine_gemv + clm_topk_row)
 ])
 def test_search_topk(cuda_device, nq, n, d, k):
     e = _unit_rows(n, d, 50)
@@ -381,3 +384,64 @@ def test_search_id_offset_and_merge(cuda_device):
     ids = torch.stack([p[1] for p in parts], dim=1).contiguous()
     s, i = K.topk_merge_sorted(scores, ids, k)
     _check_topk("search_sharded_merge", s, i, q, e, k)
+
+
+def test_kth_largest_and_topk_row_match_torch(cuda_device):
+    """The two selection primitives against torch on adversarial value sets: heavy ties, negatives, -inf padding."""
+    from clip_lora_match_b200 import _lib
+    from clip_lora_match_b200._lib import check, cur_stream, ptr
+
+    lib = _lib.load()
+    dv = cuda_device
+    g = _gen(70)
+    rows, n = 37, 16384
+    x = torch.randn((rows, n), generator=g)
+    x[:, ::7] = x[:, 3:4]                    # every 7th value of a row is the same number: massive ties
+    x[5] = torch.round(x[5] * 2) / 2          # a row with ~10 distinct values
+    x[6, 100:] = float("-inf")                # mostly empty
+    xd = x.to(dv)
+    for kth in (1, 2, 10, 50, 99, 1000, n):
+        out = torch.empty(rows, dtype=torch.float32, device=dv)
+        check(lib.clm_kth_largest(ptr(xd), rows, n, kth, 0.0, ptr(out), cur_stream()), "clm_kth_largest")
+        ref = torch.topk(x, kth, dim=-1).values[:, -1]
+        assert torch.equal(out.cpu(), ref), f"kth={kth}"
+    n2 = 300_000
+    y = torch.randn(n2, generator=g)
+    y[1000:1400] = y[999]                    # 401 equal values straddling the cut for some k
+    yd = y.to(dv)
+    order = torch.argsort(y, descending=True, stable=True)
+    for k in (1, 10, 64, 65, 1024, 2048):
+        os_ = torch.empty(k, dtype=torch.float32, device=dv)
+        oi = torch.empty(k, dtype=torch.int64, device=dv)
+        check(lib.clm_topk_row(ptr(yd), n2, k, 7, ptr(os_), ptr(oi), cur_stream()), "clm_topk_row")
+        ref_s = y[order[:k]]
+        assert torch.equal(os_.cpu(), ref_s), f"k={k}: scores"
+        got = oi.cpu() - 7
+        assert torch.equal(y[got], ref_s) and len(set(got.tolist())) == k, f"k={k}: ids"
+        # sorted by (score desc, id asc)
+        same = os_.cpu()[1:] == os_.cpu()[:-1]
+        assert bool((got[1:][same] > got[:-1][same]).all())
+
+
+def test_topk_merge_gathered_reads_the_packed_chunks_in_place(cuda_device):
+    """The exchange layout (pack_topk_chunk -> rank-major buffer -> clm_topk_merge_gathered) against the plain
+    [Q, lists, k] merge, including a rank that holds fewer than k rows and an odd Q*k (padding to an even count)."""
+    dv = cuda_device
+    g = _gen(71)
+    world, nq, k = 3, 7, 5   # nq * k = 35: odd
+    scores = torch.sort(torch.randn((world, nq, k), generator=g), dim=-1, descending=True).values
+    ids = torch.randint(0, 1_000_000, (world, nq, k), generator=g)
+    chunks = []
+    for r in range(world):
+        kl = 2 if r == 1 else k  # rank 1's shard has only 2 rows
+        chunks.append(K.pack_topk_chunk(scores[r, :, :kl].to(dv), ids[r, :, :kl].to(dv), nq, k, dv))
+    scores[1, :, 2:] = float("-inf"); ids[1, :, 2:] = -1
+    buf = torch.cat(chunks)
+    s, i = K.topk_merge_gathered(buf, world, nq, k)
+    flat_s = scores.permute(1, 0, 2).reshape(nq, -1)
+    flat_i = ids.permute(1, 0, 2).reshape(nq, -1)
+    ref_s, pos = torch.topk(flat_s, k, dim=-1)
+    assert torch.equal(s.cpu(), ref_s)
+    assert torch.equal(i.cpu(), torch.gather(flat_i, 1, pos))
+    s2, i2 = K.topk_merge_sorted(scores.permute(1, 0, 2).contiguous().to(dv), ids.permute(1, 0, 2).contiguous().to(dv), k)
+    assert torch.equal(s2, s) and torch.equal(i2, i)

@@ -406,6 +406,95 @@ def test_search_at_scale_properties(cuda_device, n, nq, k):
     assert O.ids_match_with_ties(ref_s.cpu(), ref_i.cpu(), i[sample].cpu(), sims.cpu()), "(d) ids differ"
 
 
+
+def _cluster_index(n, d, nq, k, span, spacing, contiguous, seed):
+    """Unit-norm index in which, for each of nq queries, a cluster of `span` rows has fp32 scores spaced
+    `spacing` apart, straddling rank k of that query.  Rows are q * c + sqrt(1 - c^2) * u with u a unit vector
+    orthogonal to q, so the planted score is c up to fp32 rounding."""
+    g = torch.Generator().manual_seed(seed)
+    e = torch.randn((n, d), generator=g)
+    e = e / e.norm(dim=-1, keepdim=True)
+    q = torch.randn((nq, d), generator=g)
+    q = q / q.norm(dim=-1, keepdim=True)
+    top = 0.35  # far above the ~5 sigma = 0.19 maximum of the random background
+    planted = []
+    for qi in range(nq):
+        # k - span/2 rows clearly above the cluster, then the cluster around rank k
+        n_above = max(k - span // 2, 0)
+        cs = [top + 0.05 + 0.002 * j for j in range(n_above)] + [top - spacing * j for j in range(span)]
+        if contiguous:
+            start = 1000 + qi * (len(cs) + 50)
+            rows = torch.arange(start, start + len(cs))
+        else:
+            rows = torch.randperm(n - 2000, generator=g)[: len(cs)] + 1000
+        planted.append(rows)
+        for r, c in zip(rows.tolist(), cs):
+            u = torch.randn(d, generator=g)
+            u = u - (u @ q[qi]) * q[qi]
+            u = u / u.norm()
+            e[r] = q[qi] * c + u * (1 - c * c) ** 0.5
+    return e, q, planted
+
+
+@pytest.mark.parametrize("k,contiguous", [(10, False), (50, False), (10, True), (50, True)])
+def test_search_exact_under_adversarial_near_ties(cuda_device, k, contiguous):
+    """Clusters of 40 rows whose fp32 scores are 1.5e-4 apart around rank k (near-duplicate descriptions: the
+    reference's use case) in a 2M x 768 index: the bf16 score error (~2e-4 typical, 2^-8 worst case) exceeds the
+    spacing, so a fixed k + 6 nomination margin can drop a true top-k row.  The selection keeps every candidate
+    the bf16 scores cannot rule out; with the cluster inside ONE split of the scan its list may overflow and the
+    query is redone exactly.  Required: north_star's rule against the fp32 scan."""
+    from clip_lora_match_b200.src.embedding.search import TextSearchIndex
+
+    n, d, nq = 2_000_000, 768, 64
+    e, q, planted = _cluster_index(n, d, nq, k, span=40, spacing=1.5e-4, contiguous=contiguous, seed=17 + k)
+    idx = TextSearchIndex(embeddings=e, device=cuda_device, verbose=False)
+    s, i = idx.search_batch(q, top_k=k)
+    stats = dict(idx.last_search_stats)
+    print(f"[adversarial] k={k} contiguous={contiguous}: {stats}")
+    en = idx.embeddings  # the normalised fp32 master the scores are defined on
+    qn = (q / q.norm(dim=-1, keepdim=True)).to(cuda_device)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sims = qn @ en.T  # fp32 checker scan on the GPU (a 64 x 2M matrix)
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    ref_s, ref_i = torch.topk(sims, k, dim=-1)
+    assert torch.allclose(s, ref_s, atol=3e-6), float((s - ref_s).abs().max())
+    mism = i != ref_i
+    if mism.any():
+        gap = (torch.gather(sims, 1, i) - ref_s).abs()[mism]
+        assert bool((gap <= 1e-4).all()), f"{int(mism.sum())} ids differ beyond the 1e-4 tie window"
+    # the planted cluster really straddles rank k: some of its members are in the result, and not all of them
+    for qi in (0, nq - 1):
+        hits = len(set(i[qi].tolist()) & set(planted[qi][-40:].tolist()))
+        assert 0 < hits < 40
+
+
+def test_search_top_k_is_unbounded_like_the_reference(cuda_device):
+    """search_with_embedding(q, top_k) = torch.topk(sims, min(top_k, N)) for ANY top_k (reference
+    src/embedding/search.py:98-99): 0, 1, 64, 65, 100, 1000, beyond N."""
+    from clip_lora_match_b200.src.embedding.search import TextSearchIndex
+
+    e = O.synth_unit_rows(5000, 512, 4)
+    q = O.synth_unit_rows(3, 512, 5)
+    idx = TextSearchIndex(embeddings=e, device=cuda_device, verbose=False)
+    sims = q @ e.T
+    for top_k in (0, -3, 1, 64, 65, 100, 1000, 1500):
+        s, i = idx.search_batch(q, top_k=top_k)
+        k = max(min(top_k, 5000), 0)
+        assert s.shape == (3, k) and i.shape == (3, k)
+        if k:
+            ref_s, ref_i = torch.topk(sims, k, dim=-1)
+            assert torch.allclose(s.cpu(), ref_s, atol=2e-6)
+            assert O.ids_match_with_ties(ref_s, ref_i, i.cpu(), sims)
+    assert idx.search_with_embedding(q[0], top_k=0) == []
+    res = idx.search_with_embedding(q[0], top_k=100)
+    assert len(res) == 100 and [r.index for r in res[:5]] == torch.topk(sims[0], 5).indices.tolist()
+    small = TextSearchIndex(embeddings=e[:7], device=cuda_device, verbose=False)
+    assert len(small.search_with_embedding(q[0], top_k=100)) == 7  # k = min(top_k, N)
+    with pytest.raises(ValueError):
+        idx.search_batch(q, top_k=3000)  # beyond clm_topk_row's 2048: said loudly, never truncated silently
+
+
 # ------------------------------------------------------------------------------------------
 # next rows (SURVEY.md §8f): seeker query fusion, sharded index build + resident service
 # ------------------------------------------------------------------------------------------

@@ -44,14 +44,18 @@ def main():
         print(f"tile {t}: MMA S_issue={int(tr[1,t,0])-t0 if tr[1,t,0] else None} PV_issue={int(tr[1,t,1])-t0 if tr[1,t,1] else None} other={[int(x)-t0 if x else None for x in tr[1,t,2:].tolist()]}")
         if tr[0, t, 1]:
             print(f"   TMA warp, item {t}: wants_stage={int(tr[0,t,0])-t0} stage_free={int(tr[0,t,1])-t0}")
-        for w in (18, 19):
+        v1 = os.environ.get("CLM_ATTN_V1") == "1"
+        tails = (18, 19) if v1 else (2, 3, 12, 13)
+        softs = range(2, 18) if v1 else range(4, 12)
+        for w in tails:
             ev = [int(x) - t0 if x else None for x in tr[w, t].tolist()]
             if any(e is not None for e in ev):
                 print(f"   extra-token warp {w}, item {t}: wait_stage={ev[0]} got_stage={ev[1]} scores_done={ev[2]} row_done={ev[3]}")
-        for w in range(2, 18):
+        for w in softs:
             ev = [int(x) - t0 if x else None for x in tr[w, t].tolist()]
             if any(e is not None for e in ev):
-                print(f"   warp {w:2d} (grp {((w-2)>>2)&1} half {(w-2)>>3} q {w&3}): " + " ".join(f"{n}={e}" for n, e in zip(names, ev)))
+                role = f"grp {((w-2)>>2)&1} half {(w-2)>>3} q {w&3}" if v1 else f"grp {(w-4)>>2} q {w&3}"
+                print(f"   warp {w:2d} ({role}): " + " ".join(f"{n}={e}" for n, e in zip(names, ev)))
 
 if __name__ == "__main__":
     main()

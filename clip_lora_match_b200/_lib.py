@@ -27,13 +27,15 @@ class TowerConfig(C.Structure):
         ("kind", C.c_int32), ("width", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32),
         ("mlp", C.c_int32), ("proj_dim", C.c_int32), ("tokens", C.c_int32), ("image", C.c_int32),
         ("patch", C.c_int32), ("vocab", C.c_int32), ("eos_id", C.c_int32),
-        ("lora_cols_qkv", C.c_int32), ("lora_cols_out", C.c_int32), ("ln_eps", C.c_float),
+        ("lora_cols_qkv", C.c_int32), ("lora_cols_out", C.c_int32), ("lora_cols_fc1", C.c_int32),
+        ("lora_cols_fc2", C.c_int32), ("ln_eps", C.c_float),
     ]
 
 
 _LAYER_FIELDS = [
     "ln1_g", "ln1_b", "w_qkv", "b_qkv", "lora_a_qkv", "lora_b_qkv", "w_o", "b_o", "lora_a_o",
-    "lora_b_o", "ln2_g", "ln2_b", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
+    "lora_b_o", "ln2_g", "ln2_b", "w_fc1", "b_fc1", "w_fc2", "b_fc2", "lora_a_fc1", "lora_b_fc1", "lora_a_fc2",
+    "lora_b_fc2",
 ]
 _TOWER_FIELDS = [
     "patch_w", "class_emb", "pre_ln_g", "pre_ln_b", "tok_emb", "pos_emb", "final_ln_g",

@@ -1399,10 +1399,10 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
     xt_off = (e && e[0] == '0') ? 1 : 0;
   }
   p.xt = (!xt_off && !causal && T > 128 && T % 128 == 1 && T <= 257) ? 1 : 0;
-  static int serial = -1;  // CLM_ATTN_SERIAL=0: the two softmax groups run unsynchronised (A/B measurements)
+  static int serial = -1;  // CLM_ATTN_SERIAL=1: the two softmax groups take turns on pass 2 (measured: no gain)
   if (serial < 0) {
     const char* e = getenv("CLM_ATTN_SERIAL");
-    serial = (e && e[0] == '0') ? 0 : 1;
+    serial = (e && e[0] == '1') ? 1 : 0;
   }
   p.serial = serial;
   p.Tk = p.xt ? T - 1 : p.Tp;
@@ -1500,14 +1500,17 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   // algorithmic work: QK^T and PV at the true T (causal not discounted)
   ProfScope prof(CLM_K_ATTENTION, 4.0 * batch * heads * static_cast<double>(T) * T * kHeadDim,
                  2.0 * batch * T * 4.0 * D, stream);
-  // one-thread-per-row kernel for every plan with a single key block and two S regions (all CLIP shapes);
-  // the older two-threads-per-row kernel keeps the two-block / one-region plans.  CLM_ATTN_V1=1 forces it.
-  static int force_v1 = -1;
-  if (force_v1 < 0) {
-    const char* e = getenv("CLM_ATTN_V1");
-    force_v1 = (e && e[0] == '1') ? 1 : 0;
+  // CLM_ATTN_V2=1 selects the one-thread-per-row kernel (attention_kernel_v2) for the plans with a single key
+  // block and two S regions.  Measured (profiles/r2_attention_notes.md) it is 5-25 % SLOWER than the
+  // two-threads-per-row kernel: each stream is a serial chain S -> max -> exp -> P V -> drain -> store, and
+  // halving the threads per tile lengthens the chain more than the removed pair barriers shorten it.  Kept for
+  // A/B measurements only.
+  static int use_v2 = -1;
+  if (use_v2 < 0) {
+    const char* e = getenv("CLM_ATTN_V2");
+    use_v2 = (e && e[0] == '1') ? 1 : 0;
   }
-  if (!force_v1 && p.blocks == 1 && p.nslots == 2) {
+  if (use_v2 && p.blocks == 1 && p.nslots == 2) {
     if (causal) {
       CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel_v2<true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

@@ -35,7 +35,15 @@ struct clm_tower {
 
 namespace {
 
-constexpr int kLoraCols = 64;
+constexpr int kLoraBlock = 64;  // LoRA column counts are multiples of one K block of the GEMM
+
+inline int max_lora_cols(const clm_tower_config& c) {
+  int m = c.lora_cols_qkv;
+  if (c.lora_cols_out > m) m = c.lora_cols_out;
+  if (c.lora_cols_fc1 > m) m = c.lora_cols_fc1;
+  if (c.lora_cols_fc2 > m) m = c.lora_cols_fc2;
+  return m > 0 ? m : kLoraBlock;
+}
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -77,7 +85,7 @@ Workspace carve(const clm_tower* tw, int batch, uint8_t* base, int tokens = 0) {
   }
   ws.qkv = reinterpret_cast<__nv_bfloat16*>(take(qkv_bytes));
   ws.g = reinterpret_cast<__nv_bfloat16*>(take(g_bytes));
-  ws.t = reinterpret_cast<__nv_bfloat16*>(take(rows * kLoraCols * 2));
+  ws.t = reinterpret_cast<__nv_bfloat16*>(take(rows * max_lora_cols(c) * 2));
   ws.pooled = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(batch) * c.width * 2));
   ws.emb = reinterpret_cast<float*>(take(static_cast<size_t>(batch) * c.proj_dim * 4));
   ws.eos = reinterpret_cast<int32_t*>(take(static_cast<size_t>(batch) * 4));
@@ -113,26 +121,37 @@ int run_layers(clm_tower* tw, const Workspace& ws, int batch, const int32_t* poo
   for (int l = 0; l < c.layers; ++l) {
     const clm_layer_weights& L = tw->layers[l];
     CLM_TRY(clm_layernorm(ws.h, L.ln1_g, L.ln1_b, ws.x, rows, D, c.ln_eps, sv));
-    const bool lq = c.lora_cols_qkv > 0 && L.lora_a_qkv && L.lora_b_qkv;
-    if (lq)
-      CLM_TRY(clm_gemm_launch(ws.x, D, L.lora_a_qkv, D, rows, kLoraCols, D, nullptr, 0, nullptr, 0, 0,
-                              ws.t, kLoraCols, CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s));
-    CLM_TRY(clm_gemm_launch(ws.x, D, L.w_qkv, D, rows, 3 * D, D, lq ? ws.t : nullptr, kLoraCols,
-                            lq ? L.lora_b_qkv : nullptr, kLoraCols, lq ? kLoraCols : 0, ws.qkv, 3 * D,
+    // LoRA (unmerged): t = x A_cat^T is a skinny GEMM, then (t, (s B)_cat) ride along as extra K blocks
+    const int cq = (c.lora_cols_qkv > 0 && L.lora_a_qkv && L.lora_b_qkv) ? c.lora_cols_qkv : 0;
+    if (cq)
+      CLM_TRY(clm_gemm_launch(ws.x, D, L.lora_a_qkv, D, rows, cq, D, nullptr, 0, nullptr, 0, 0,
+                              ws.t, cq, CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s));
+    CLM_TRY(clm_gemm_launch(ws.x, D, L.w_qkv, D, rows, 3 * D, D, cq ? ws.t : nullptr, cq,
+                            cq ? L.lora_b_qkv : nullptr, cq, cq, ws.qkv, 3 * D,
                             CLM_OUT_BF16, L.b_qkv, nullptr, 0, CLM_EPI_NONE, s));
     CLM_TRY(clm_attention_launch(ws.qkv, ws.ao, batch, tokens, c.heads, c.kind == 1, s));
-    const bool lo = c.lora_cols_out > 0 && L.lora_a_o && L.lora_b_o;
-    if (lo)
-      CLM_TRY(clm_gemm_launch(ws.ao, D, L.lora_a_o, D, rows, kLoraCols, D, nullptr, 0, nullptr, 0, 0,
-                              ws.t, kLoraCols, CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s));
-    CLM_TRY(clm_gemm_launch(ws.ao, D, L.w_o, D, rows, D, D, lo ? ws.t : nullptr, kLoraCols,
-                            lo ? L.lora_b_o : nullptr, kLoraCols, lo ? kLoraCols : 0, ws.h, D,
+    const int co = (c.lora_cols_out > 0 && L.lora_a_o && L.lora_b_o) ? c.lora_cols_out : 0;
+    if (co)
+      CLM_TRY(clm_gemm_launch(ws.ao, D, L.lora_a_o, D, rows, co, D, nullptr, 0, nullptr, 0, 0,
+                              ws.t, co, CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s));
+    CLM_TRY(clm_gemm_launch(ws.ao, D, L.w_o, D, rows, D, D, co ? ws.t : nullptr, co,
+                            co ? L.lora_b_o : nullptr, co, co, ws.h, D,
                             CLM_OUT_F32, L.b_o, ws.h, D, CLM_EPI_NONE, s));
     CLM_TRY(clm_layernorm(ws.h, L.ln2_g, L.ln2_b, ws.x, rows, D, c.ln_eps, sv));
-    CLM_TRY(clm_gemm_launch(ws.x, D, L.w_fc1, D, rows, c.mlp, D, nullptr, 0, nullptr, 0, 0, ws.g,
+    const int c1 = (c.lora_cols_fc1 > 0 && L.lora_a_fc1 && L.lora_b_fc1) ? c.lora_cols_fc1 : 0;
+    if (c1)
+      CLM_TRY(clm_gemm_launch(ws.x, D, L.lora_a_fc1, D, rows, c1, D, nullptr, 0, nullptr, 0, 0,
+                              ws.t, c1, CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s));
+    CLM_TRY(clm_gemm_launch(ws.x, D, L.w_fc1, D, rows, c.mlp, D, c1 ? ws.t : nullptr, c1,
+                            c1 ? L.lora_b_fc1 : nullptr, c1, c1, ws.g,
                             c.mlp, CLM_OUT_BF16, L.b_fc1, nullptr, 0, CLM_EPI_QUICKGELU, s));
-    CLM_TRY(clm_gemm_launch(ws.g, c.mlp, L.w_fc2, c.mlp, rows, D, c.mlp, nullptr, 0, nullptr, 0, 0,
-                            ws.h, D, CLM_OUT_F32, L.b_fc2, ws.h, D, CLM_EPI_NONE, s));
+    const int c2 = (c.lora_cols_fc2 > 0 && L.lora_a_fc2 && L.lora_b_fc2) ? c.lora_cols_fc2 : 0;
+    if (c2)
+      CLM_TRY(clm_gemm_launch(ws.g, c.mlp, L.lora_a_fc2, c.mlp, rows, c2, c.mlp, nullptr, 0, nullptr, 0, 0,
+                              ws.t, c2, CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s));
+    CLM_TRY(clm_gemm_launch(ws.g, c.mlp, L.w_fc2, c.mlp, rows, D, c.mlp, c2 ? ws.t : nullptr, c2,
+                            c2 ? L.lora_b_fc2 : nullptr, c2, c2, ws.h, D, CLM_OUT_F32, L.b_fc2, ws.h, D,
+                            CLM_EPI_NONE, s));
   }
   CLM_TRY(clm_pool_ln(ws.h, pool_idx, tw->w.final_ln_g, tw->w.final_ln_b, ws.pooled, batch, tokens,
                       D, c.ln_eps, sv));
@@ -154,10 +173,13 @@ extern "C" int clm_tower_create(const clm_tower_config* cfg, const clm_tower_wei
   CLM_REQUIRE(cfg->width % 128 == 0 && cfg->mlp % 64 == 0 && cfg->proj_dim % 8 == 0,
               "clm_tower_create: unsupported dims width=%d mlp=%d proj=%d", cfg->width, cfg->mlp,
               cfg->proj_dim);
-  CLM_REQUIRE(cfg->layers > 0 && cfg->tokens > 0 && cfg->tokens <= 512, "clm_tower_create: bad layers/tokens");
-  CLM_REQUIRE((cfg->lora_cols_qkv == 0 || cfg->lora_cols_qkv == kLoraCols) &&
-                  (cfg->lora_cols_out == 0 || cfg->lora_cols_out == kLoraCols),
-              "clm_tower_create: lora_cols must be 0 or %d", kLoraCols);
+  CLM_REQUIRE(cfg->layers > 0 && cfg->tokens > 0 && cfg->tokens <= 384,
+              "clm_tower_create: bad layers/tokens (tokens <= 384: the attention kernel's limit)");
+  CLM_REQUIRE(cfg->lora_cols_qkv >= 0 && cfg->lora_cols_qkv % kLoraBlock == 0 && cfg->lora_cols_out >= 0 &&
+                  cfg->lora_cols_out % kLoraBlock == 0 && cfg->lora_cols_fc1 >= 0 &&
+                  cfg->lora_cols_fc1 % kLoraBlock == 0 && cfg->lora_cols_fc2 >= 0 &&
+                  cfg->lora_cols_fc2 % kLoraBlock == 0,
+              "clm_tower_create: lora_cols must be 0 or multiples of %d", kLoraBlock);
   clm_tower* t = new (std::nothrow) clm_tower();
   CLM_REQUIRE(t != nullptr, "clm_tower_create: out of host memory");
   t->cfg = *cfg;

@@ -28,7 +28,7 @@ import yaml
 from .. import _lib
 from .lora_adapter import LoraAdapter, linear_module_paths, load_lora_adapter
 
-LORA_COLS = 64  # padded total LoRA rank folded into one extra K block of the fused GEMMs
+LORA_COLS = 64  # LoRA ranks are padded to multiples of this: one extra K block of the fused GEMMs each
 BOS_ID, EOS_ID = 49406, 49407
 
 
@@ -198,28 +198,31 @@ class B200ClipModel:
     def _dev(self, t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
         return t.to(device=self.device, dtype=dtype).contiguous()
 
-    def _lora_operands(self, prefix: str, width: int, group: List[str]):
-        """Pack the adapters of `group` (module leaves sharing one fused GEMM) into
-        A_cat [64, D] and (s·B)_cat [len(group)*D, 64]; None if no member has LoRA."""
+    def _lora_operands(self, prefix: str, in_dim: int, group: List[Tuple[str, int]]):
+        """Pack the adapters of `group` -- (module leaf, out features) of the Linears that share one fused
+        GEMM and one input -- into A_cat [cols, in_dim] and (s*B)_cat [sum(out), cols], cols = the total
+        rank padded to a multiple of LORA_COLS (one K block of the GEMM).  (None, None, 0) if no member has
+        LoRA.  Any rank and any subset of the group is accepted (reference models/lora_adapter.py:33-41)."""
         if self.lora is None:
-            return None, None
-        present = [(i, m) for i, m in enumerate(group) if f"{prefix}.{m}" in self.lora.weights]
+            return None, None, 0
+        present = [(i, m) for i, (m, _) in enumerate(group) if f"{prefix}.{m}" in self.lora.weights]
         if not present:
-            return None, None
+            return None, None, 0
         r = self.lora.config.r
-        if r * len(present) > LORA_COLS:
-            raise NotImplementedError(
-                f"total LoRA rank {r}x{len(present)} on {prefix} exceeds {LORA_COLS} columns")
-        a_cat = torch.zeros((LORA_COLS, width), dtype=torch.float32)
-        b_cat = torch.zeros((len(group) * width, LORA_COLS), dtype=torch.float32)
+        cols = (r * len(present) + LORA_COLS - 1) // LORA_COLS * LORA_COLS
+        outs = [o for _, o in group]
+        a_cat = torch.zeros((cols, in_dim), dtype=torch.float32)
+        b_cat = torch.zeros((sum(outs), cols), dtype=torch.float32)
         s = self.lora.scaling
         for slot, (i, m) in enumerate(present):
             a, b = self.lora.weights[f"{prefix}.{m}"]
-            if tuple(a.shape) != (r, width) or tuple(b.shape) != (width, r):
-                raise ValueError(f"LoRA shape mismatch on {prefix}.{m}: A {tuple(a.shape)} B {tuple(b.shape)}")
+            if tuple(a.shape) != (r, in_dim) or tuple(b.shape) != (outs[i], r):
+                raise ValueError(f"LoRA shape mismatch on {prefix}.{m}: A {tuple(a.shape)} B {tuple(b.shape)} "
+                                 f"(expected A [{r}, {in_dim}], B [{outs[i]}, {r}])")
+            row0 = sum(outs[:i])
             a_cat[slot * r:(slot + 1) * r] = a
-            b_cat[i * width:(i + 1) * width, slot * r:(slot + 1) * r] = b * s
-        return self._dev(a_cat, torch.bfloat16), self._dev(b_cat, torch.bfloat16)
+            b_cat[row0:row0 + outs[i], slot * r:(slot + 1) * r] = b * s
+        return self._dev(a_cat, torch.bfloat16), self._dev(b_cat, torch.bfloat16), cols
 
     def _build_tower(self, kind: str) -> None:
         arch = self.arch
@@ -239,7 +242,19 @@ class B200ClipModel:
             return t.data_ptr()
 
         layers = (_lib.LayerWeights * ta.layers)()
-        any_qkv = any_out = False
+        cols = {"qkv": 0, "out": 0, "fc1": 0, "fc2": 0}  # every layer of a tower carries the same adapter shape
+
+        def lora(L, name, prefix, in_dim, group):
+            a_cat, b_cat, c = self._lora_operands(prefix, in_dim, group)
+            if a_cat is None:
+                return
+            if cols[name] not in (0, c):
+                raise ValueError(f"LoRA targets differ between layers of the {kind} tower ({name}: {cols[name]} vs {c})")
+            cols[name] = c
+            keep.extend([a_cat, b_cat])
+            setattr(L, f"lora_a_{name if name != 'out' else 'o'}", a_cat.data_ptr())
+            setattr(L, f"lora_b_{name if name != 'out' else 'o'}", b_cat.data_ptr())
+
         for i in range(ta.layers):
             lp = f"{pre}.encoder.layers.{i}"
             ap = f"{lp}.self_attn"
@@ -252,26 +267,20 @@ class B200ClipModel:
                                       sd[f"{ap}.v_proj.bias"]], dim=0), torch.float32)
             keep.append(bq)
             L.b_qkv = bq.data_ptr()
-            a_cat, b_cat = self._lora_operands(ap, ta.width, ["q_proj", "k_proj", "v_proj"])
-            if a_cat is not None:
-                keep += [a_cat, b_cat]
-                L.lora_a_qkv, L.lora_b_qkv = a_cat.data_ptr(), b_cat.data_ptr()
-                any_qkv = True
+            lora(L, "qkv", ap, ta.width, [("q_proj", ta.width), ("k_proj", ta.width), ("v_proj", ta.width)])
             L.w_o, L.b_o = bf16(sd[f"{ap}.out_proj.weight"]), f32(f"{ap}.out_proj.bias")
-            a_o, b_o = self._lora_operands(ap, ta.width, ["out_proj"])
-            if a_o is not None:
-                keep += [a_o, b_o]
-                L.lora_a_o, L.lora_b_o = a_o.data_ptr(), b_o.data_ptr()
-                any_out = True
+            lora(L, "out", ap, ta.width, [("out_proj", ta.width)])
             L.w_fc1, L.b_fc1 = bf16(sd[f"{lp}.mlp.fc1.weight"]), f32(f"{lp}.mlp.fc1.bias")
             L.w_fc2, L.b_fc2 = bf16(sd[f"{lp}.mlp.fc2.weight"]), f32(f"{lp}.mlp.fc2.bias")
+            lora(L, "fc1", f"{lp}.mlp", ta.width, [("fc1", ta.mlp)])
+            lora(L, "fc2", f"{lp}.mlp", ta.mlp, [("fc2", ta.width)])
 
         w = _lib.TowerWeights()
         cfg = _lib.TowerConfig()
         cfg.width, cfg.layers, cfg.heads, cfg.mlp = ta.width, ta.layers, ta.heads, ta.mlp
         cfg.proj_dim, cfg.ln_eps = arch.proj_dim, arch.ln_eps
-        cfg.lora_cols_qkv = LORA_COLS if any_qkv else 0
-        cfg.lora_cols_out = LORA_COLS if any_out else 0
+        cfg.lora_cols_qkv, cfg.lora_cols_out = cols["qkv"], cols["out"]
+        cfg.lora_cols_fc1, cfg.lora_cols_fc2 = cols["fc1"], cols["fc2"]
         w.pos_emb = f32(f"{pre}.embeddings.position_embedding.weight")
         if kind == "vision":
             cfg.kind, cfg.tokens, cfg.image, cfg.patch = 0, arch.vision_tokens, arch.image, arch.patch

@@ -24,7 +24,7 @@ from typing import Dict, Iterable, List, Optional, Tuple, Union
 import torch
 import yaml
 
-SUPPORTED_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj")
+SUPPORTED_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")
 ADAPTER_CONFIG = "adapter_config.json"
 ADAPTER_WEIGHTS = "adapter_model.safetensors"
 
@@ -118,8 +118,8 @@ def _check_supported(paths: Iterable[str]) -> None:
         if leaf not in SUPPORTED_TARGETS:
             raise NotImplementedError(
                 f"LoRA on '{p}' is not supported by the B200 path; supported targets are "
-                f"{SUPPORTED_TARGETS} (the reference default q_proj,v_proj and the shipped "
-                f"config's q,k,v,out)")
+                f"{SUPPORTED_TARGETS} (every Linear of the encoder layers; the two projection heads "
+                f"visual_projection / text_projection are not LoRA targets here)")
 
 
 def init_lora_adapter(model_dims: Dict[str, Tuple[int, int]], lora_config: LoraConfig,

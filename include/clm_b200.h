@@ -159,8 +159,13 @@ typedef struct {
   int32_t patch;    /* vision only */
   int32_t vocab;    /* text only */
   int32_t eos_id;   /* text only */
-  int32_t lora_cols_qkv; /* 0 or 64: padded total LoRA rank folded into the fused QKV GEMM */
-  int32_t lora_cols_out; /* 0 or 64: same for out_proj */
+  /* Padded total LoRA rank folded into each fused GEMM as extra K blocks: 0 (no adapter on that GEMM) or a
+   * multiple of 64 (any rank / any subset of q,k,v for the QKV GEMM; models/lora_adapter.py:33-41 passes any
+   * r and target_modules to peft). */
+  int32_t lora_cols_qkv;
+  int32_t lora_cols_out;
+  int32_t lora_cols_fc1;
+  int32_t lora_cols_fc2;
   float ln_eps;
 } clm_tower_config;
 
@@ -168,12 +173,14 @@ typedef struct {
 typedef struct {
   const float* ln1_g; const float* ln1_b;
   const void* w_qkv; const float* b_qkv;       /* [3D, D], [3D] */
-  const void* lora_a_qkv; const void* lora_b_qkv; /* [64, D], [3D, 64] or NULL */
+  const void* lora_a_qkv; const void* lora_b_qkv; /* [cols_qkv, D], [3D, cols_qkv] or NULL */
   const void* w_o; const float* b_o;           /* [D, D], [D] */
-  const void* lora_a_o; const void* lora_b_o;  /* [64, D], [D, 64] or NULL */
+  const void* lora_a_o; const void* lora_b_o;  /* [cols_out, D], [D, cols_out] or NULL */
   const float* ln2_g; const float* ln2_b;
   const void* w_fc1; const float* b_fc1;       /* [mlp, D] */
   const void* w_fc2; const float* b_fc2;       /* [D, mlp] */
+  const void* lora_a_fc1; const void* lora_b_fc1; /* [cols_fc1, D], [mlp, cols_fc1] or NULL */
+  const void* lora_a_fc2; const void* lora_b_fc2; /* [cols_fc2, mlp], [D, cols_fc2] or NULL */
 } clm_layer_weights;
 
 typedef struct {

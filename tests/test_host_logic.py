@@ -56,8 +56,8 @@ def test_cpu_tensors_are_rejected_loudly():
 def test_struct_layout_matches_header():
     import ctypes as C
 
-    assert C.sizeof(_lib.TowerConfig) == 14 * 4
-    assert C.sizeof(_lib.LayerWeights) == 16 * 8
+    assert C.sizeof(_lib.TowerConfig) == 16 * 4
+    assert C.sizeof(_lib.LayerWeights) == 20 * 8
     assert C.sizeof(_lib.TowerWeights) == 9 * 8
 
 
@@ -142,9 +142,16 @@ def test_adapter_layout_interoperates_with_peft_semantics(tmp_path):
 
 
 def test_unsupported_lora_targets_fail_loudly():
-    cfg = LA.LoraConfig(target_modules=["fc1"])
+    # every Linear of the encoder layers is a valid target (fc1 / fc2 included) ...
+    mlp = LA.init_lora_adapter(_dims(), LA.LoraConfig(r=4, target_modules=["fc1", "fc2"]))
+    assert all(p.endswith(("mlp.fc1", "mlp.fc2")) for p in mlp.weights) and len(mlp.weights) > 0
+    a, b = next(v for k, v in mlp.weights.items() if k.endswith("fc1"))
+    assert a.shape[0] == 4 and b.shape[1] == 4 and b.shape[0] == 4 * a.shape[1]
+    # ... the two projection heads are not
+    d = dict(_dims())
+    d["visual_projection"] = (64, 128)
     with pytest.raises(NotImplementedError):
-        LA.init_lora_adapter(_dims(), cfg)
+        LA.init_lora_adapter(d, LA.LoraConfig(target_modules=["visual_projection"]))
     with pytest.raises(FileNotFoundError):
         LA.load_lora_adapter("/nonexistent/adapter")
 

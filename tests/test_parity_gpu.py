@@ -53,6 +53,10 @@ CASES = [
     ("tiny-test", 5, 7, 8, 16, ("q_proj", "v_proj")),
     ("tiny-test", 3, 3, 8, 16, ("q_proj", "k_proj", "v_proj", "out_proj")),   # shipped YAML's targets
     ("tiny-test", 3, 3, 8, 16, ()),                                           # no LoRA
+    ("tiny-test", 4, 4, 32, 64, ("q_proj", "k_proj", "v_proj", "out_proj")),  # r=32 x 3 = 96 -> 128 LoRA columns (2 K blocks)
+    ("tiny-test", 4, 4, 8, 16, ("fc1", "fc2")),                               # MLP targets (K-extension on fc1 / fc2)
+    ("tiny-test", 3, 3, 24, 24, ("k_proj", "fc2", "out_proj")),               # odd rank, odd subset
+    ("openai/clip-vit-base-patch32", 3, 3, 32, 32, ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")),
     ("openai/clip-vit-base-patch32", 6, 6, 8, 16, ("q_proj", "v_proj")),      # config 1
     ("openai/clip-vit-base-patch16", 3, 3, 16, 32, ("q_proj", "v_proj")),     # config 2
     ("openai/clip-vit-large-patch14", 2, 2, 16, 32, ("q_proj", "v_proj")),    # config 3

@@ -44,7 +44,7 @@ def main():
         print(f"tile {t}: MMA S_issue={int(tr[1,t,0])-t0 if tr[1,t,0] else None} PV_issue={int(tr[1,t,1])-t0 if tr[1,t,1] else None} other={[int(x)-t0 if x else None for x in tr[1,t,2:].tolist()]}")
         if tr[0, t, 1]:
             print(f"   TMA warp, item {t}: wants_stage={int(tr[0,t,0])-t0} stage_free={int(tr[0,t,1])-t0}")
-        v1 = os.environ.get("CLM_ATTN_V1") == "1"
+        v1 = os.environ.get("CLM_ATTN_V2") != "1"
         tails = (18, 19) if v1 else (2, 3, 12, 13)
         softs = range(2, 18) if v1 else range(4, 12)
         for w in tails:

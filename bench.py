@@ -476,7 +476,8 @@ def main():
             "metric": "top-10 queries/sec over 10M-row index", "value": QUERY_BATCH * args.steps / (ms_s / 1e3),
             "unit": "queries/s", "index": [n_total, INDEX_DIM], "rows_per_gpu": hi - lo, "query_batch": QUERY_BATCH,
             "k": TOP_K, "scaling": "strong (index rows fixed, sharded over GPUs)", "ms_per_batch": ms_s / args.steps,
-            "exact": "bf16 tensor-core scan nominates k+6 per (query, split); fp32 re-score of the candidates",
+            "exact": "bf16 tensor-core scan nominates every row within 2*eps (eps = 2^-8) of the k-th best bf16 score; fp32 "
+                     "re-score of all of them; queries whose candidate list overflowed are redone with the exact fp32 scan",
             "e2e": {"value": QUERY_BATCH * args.steps / (ms_se / 1e3), "unit": "queries/s",
                     "h2d_bytes_per_step": q_host.numel() * 4, "d2h_bytes_per_step": QUERY_BATCH * TOP_K * 12},
             "roofline_q4096": {"bound": "tensor", "kernel": "search_kernel", "achieved": s_tf,

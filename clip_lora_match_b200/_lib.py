@@ -85,7 +85,7 @@ SIGNATURES = {
     "clm_encode_text": (_I, [_P, _P, _I, _P, _I, _P, C.c_size_t, _P]),
     "clm_encode_text_len": (_I, [_P, _P, _I, _I, _P, _I, _P, C.c_size_t, _P]),
     "clm_search_num_splits": (_I, [_I, _I]),
-    "clm_search_topk": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _F, _P, _P, _P]),
+    "clm_search_topk": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P]),
     "clm_kth_largest": (_I, [_P, _I, _I, _I, _F, _P, _P]),
     "clm_topk_merge": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _I, _I, C.c_int64, _P, _P, _P, _P]),
     "clm_topk_gather_chunk_bytes": (C.c_size_t, [_I, _I]),

@@ -41,8 +41,15 @@ struct SCfg {
 struct SearchParams {
   int nq, n, kblocks, q_tiles, splits, tiles_n, kc, stages;  // q_tiles: tiles of BM * kCtas queries
   int a_bytes;  // bytes of the query tile actually loaded per k-block (64-row box when nq <= 64)
-  float* thr_io;  // per-query running lower bound of the kc-th best score, shared by all units (or null)
+  int kb;         // a list holding kb entries proves a lower bound of the query's kb-th best score (kb = k)
+  float* thr_io;  // per-query running lower bound of the kb-th best score, shared by all units (or null)
   float margin;   // scores above (shared bound - margin) are kept: see clm_search_topk in include/clm_b200.h
+  // Per-query score histogram shared by ALL work units (or null): every kept candidate with score >= base[q]
+  // counts in bin (score - base[q]) / kHistStep (the top bin is open ended).  kb candidates counted at or above a
+  // bin edge prove that the query's kb-th best score is at least that edge -- over all rows any unit has seen,
+  // not only the rows of one unit -- which is what tightens the shared bound early on small shards.
+  const float* hist_base;
+  unsigned int* hist;
   float* cand_score;
   int32_t* cand_id;
 };
@@ -108,40 +115,77 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
 }
 
 // State of one thread's candidate list (the list itself is in shared memory, element j at sc[j * BM]).
+constexpr int kHistBins = 32;
+constexpr float kHistStep = 1.0f / 256.0f;
+
 struct ListState {
-  int cnt, minpos;
+  int cnt;
+  unsigned int* hist;  // this query's histogram (or null)
+  float hbase;
   float thr;        // a score must exceed this to enter the list: max(own, gbound - margin)
   float own;        // minimum of this list once it is full (-inf before)
+  float runmin;     // minimum of the entries appended so far (while the list is filling)
   float gbound;     // the shared per-query bound as last seen / published by this thread
   float margin;
 };
 
-// Insert (s, id) into a thread's list of the kc best; once the list is full, track its minimum (the thread's
-// threshold) and publish it to the query's shared bound.  Deliberately NOT inlined: the scan loop tests 32
-// scores per chunk and an inlined copy per score made the epilogue 32x larger than the instruction cache
-// likes (ncu: ~45 % of the warp samples of the Q = 4096 scan sat on instruction fetch after these blocks).
-__device__ __noinline__ ListState list_insert(ListState st, float s, int id, float* my_sc, int32_t* my_id, int kc,
-                                              float* gthr) {
-  int slot = st.minpos;
-  if (st.cnt < kc) slot = st.cnt++;
-  my_sc[slot * BM] = s;
-  my_id[slot * BM] = id;
-  if (st.cnt == kc) {
-    float m = my_sc[0];
-    int mp = 0;
-    for (int j = 1; j < kc; ++j) {
-      const float x = my_sc[j * BM];
-      if (x < m) { m = x; mp = j; }
-    }
-    st.own = m;
-    st.minpos = mp;
-    if (gthr && m > st.gbound) {  // publish: float max through the integer atomics
-      st.gbound = m;
-      if (m >= 0.f) atomicMax(reinterpret_cast<int*>(gthr), __float_as_int(m));
-      else atomicMin(reinterpret_cast<unsigned int*>(gthr), __float_as_uint(m));
-    }
-    st.thr = fmaxf(st.own, st.gbound - st.margin);
+__device__ __forceinline__ void publish_bound(ListState& st, float m, float* gthr) {
+  if (gthr && m > st.gbound) {  // float max through the integer atomics
+    st.gbound = m;
+    if (m >= 0.f) atomicMax(reinterpret_cast<int*>(gthr), __float_as_int(m));
+    else atomicMin(reinterpret_cast<unsigned int*>(gthr), __float_as_uint(m));
   }
+}
+
+// restore the min-heap property below node j (children 2j+1, 2j+2; element j at [j * BM])
+__device__ __forceinline__ void sift_down(float* my_sc, int32_t* my_id, int kc, int j, float s, int id) {
+  for (;;) {
+    int c = 2 * j + 1;
+    if (c >= kc) break;
+    float cs = my_sc[c * BM];
+    if (c + 1 < kc) {
+      const float rs = my_sc[(c + 1) * BM];
+      if (rs < cs) { cs = rs; ++c; }
+    }
+    if (cs >= s) break;
+    my_sc[j * BM] = cs;
+    my_id[j * BM] = my_id[c * BM];
+    j = c;
+  }
+  my_sc[j * BM] = s;
+  my_id[j * BM] = id;
+}
+
+// Insert (s, id) into a thread's list of the kc best.  While the list fills, entries are appended; once kb of
+// them exist their minimum is a lower bound of the query's kb-th best score and is published to the shared
+// bound.  When the list becomes full it is turned into a min-heap (root = the list minimum = the thread's own
+// threshold); from then on an insertion replaces the root and sifts down: O(log kc) shared-memory accesses
+// instead of a rescan of all kc slots.  Deliberately NOT inlined: the scan loop tests 32 scores per chunk and an
+// inlined copy per score made the epilogue 32x larger than the instruction cache likes (ncu: ~45 % of the warp
+// samples of the Q = 4096 scan sat on instruction fetch after these blocks).
+__device__ __noinline__ ListState list_insert(ListState st, float s, int id, float* my_sc, int32_t* my_id, int kc,
+                                              int kb, float* gthr) {
+  if (st.cnt < kc) {
+    my_sc[st.cnt * BM] = s;
+    my_id[st.cnt * BM] = id;
+    ++st.cnt;
+    st.runmin = fminf(st.runmin, s);
+    if (st.cnt == kb) publish_bound(st, st.runmin, gthr);
+    if (st.cnt == kc) {
+      for (int j = kc / 2 - 1; j >= 0; --j) sift_down(my_sc, my_id, kc, j, my_sc[j * BM], my_id[j * BM]);
+      st.own = my_sc[0];
+      if (kc >= kb) publish_bound(st, st.own, gthr);
+    }
+  } else {  // s > own (the caller's threshold): replace the minimum
+    sift_down(my_sc, my_id, kc, 0, s, id);
+    st.own = my_sc[0];
+    if (kc >= kb) publish_bound(st, st.own, gthr);
+  }
+  if (st.hist && s >= st.hbase) {
+    int b = static_cast<int>((s - st.hbase) * (1.0f / kHistStep));
+    atomicAdd(st.hist + (b < kHistBins - 1 ? b : kHistBins - 1), 1u);
+  }
+  st.thr = fmaxf(st.own, st.gbound - st.margin);
   return st;
 }
 
@@ -290,7 +334,7 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const bool warp_live = q0 + q * 32 < p.nq;  // rows past the last query: nothing to scan
       ListState ls;
       ls.cnt = 0;
-      ls.minpos = 0;
+      ls.runmin = INFINITY;
       // gbound is a lower bound of this query's kc-th best score over the WHOLE index: the kc-th best of
       // any subset of rows qualifies, so every unit publishes its own list minimum (atomic max in
       // global memory) and re-reads the shared bound once per tile.  Units that start after the
@@ -302,9 +346,30 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       ls.own = -INFINITY;
       ls.gbound = -INFINITY;
       ls.margin = p.margin;
+      ls.hist = nullptr;
+      ls.hbase = 0.f;
+      if (gthr && p.hist) {
+        ls.hbase = p.hist_base[q0 + r];
+        if (ls.hbase > -INFINITY) ls.hist = p.hist + static_cast<size_t>(q0 + r) * kHistBins;
+      }
       for (int t = t0; t < t1; ++t) {
         if (gthr) {
           ls.gbound = fmaxf(ls.gbound, __ldcg(gthr));
+          if (ls.hist) {
+            // highest bin edge with at least kb candidates counted at or above it (by any unit, so far)
+            const uint4* h4 = reinterpret_cast<const uint4*>(ls.hist);
+            unsigned int cum = 0;
+            int edge = -1;
+#pragma unroll
+            for (int j = kHistBins / 4 - 1; j >= 0; --j) {
+              const uint4 h = __ldcg(h4 + j);
+              cum += h.w; if (edge < 0 && cum >= static_cast<unsigned int>(p.kb)) edge = 4 * j + 3;
+              cum += h.z; if (edge < 0 && cum >= static_cast<unsigned int>(p.kb)) edge = 4 * j + 2;
+              cum += h.y; if (edge < 0 && cum >= static_cast<unsigned int>(p.kb)) edge = 4 * j + 1;
+              cum += h.x; if (edge < 0 && cum >= static_cast<unsigned int>(p.kb)) edge = 4 * j;
+            }
+            if (edge >= 0) publish_bound(ls, ls.hbase + edge * kHistStep, gthr);
+          }
           ls.thr = fmaxf(ls.own, ls.gbound - ls.margin);
         }
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -331,7 +396,7 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float s = __uint_as_float(v[i]);
-              if (s > ls.thr) ls = list_insert(ls, s, base + i, my_sc, my_id, kc, gthr);
+              if (s > ls.thr) ls = list_insert(ls, s, base + i, my_sc, my_id, kc, p.kb, gthr);
             }
           }
         }
@@ -708,13 +773,15 @@ constexpr int kMaxKc = 64;       // capacity of one (query, split) candidate lis
 constexpr int kMaxMergeK = 1024;  // largest k the merge emits (half of kMaxSel: room for the margin's extras)
 
 extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int nq, int n, int dim,
-                               int kc, int splits, float* thr_io, float margin, float* cand_score,
-                               int32_t* cand_id, void* stream) {
+                               int kc, int kb, int splits, float* thr_io, const float* hist_base,
+                               uint32_t* hist, float margin, float* cand_score, int32_t* cand_id, void* stream) {
   CLM_REQUIRE(q_bf16 && index_bf16 && cand_score && cand_id, "clm_search_topk: null argument");
   CLM_REQUIRE(nq > 0 && n > 0 && dim > 0 && dim % 8 == 0, "clm_search_topk: bad shape nq=%d n=%d dim=%d",
               nq, n, dim);
   CLM_REQUIRE(kc >= 1 && kc <= kMaxKc, "clm_search_topk: kc=%d must be in [1,%d]", kc, kMaxKc);
-  CLM_REQUIRE(margin >= 0.f, "clm_search_topk: margin must be >= 0");
+  CLM_REQUIRE(margin >= 0.f && kb >= 1, "clm_search_topk: margin must be >= 0 and kb >= 1");
+  CLM_REQUIRE(hist == nullptr || (reinterpret_cast<uintptr_t>(hist) & 15) == 0, "clm_search_topk: hist not 16-B aligned");
+  CLM_REQUIRE(thr_io == nullptr || kb <= kc, "clm_search_topk: a shared bound needs kb <= kc (kb=%d kc=%d)", kb, kc);
   const int ctas = search_ctas(nq);
   const int q_tiles = (nq + BM * ctas - 1) / (BM * ctas);
   const int tiles_n = (n + BN - 1) / BN;
@@ -740,9 +807,12 @@ extern "C" int clm_search_topk(const void* q_bf16, const void* index_bf16, int n
   p.splits = splits;
   p.tiles_n = tiles_n;
   p.kc = kc;
+  p.kb = kb;
   p.a_bytes = q_box_rows * BK * 2;
   p.thr_io = thr_io;
   p.margin = margin;
+  p.hist_base = (thr_io && hist && hist_base) ? hist_base : nullptr;
+  p.hist = p.hist_base ? hist : nullptr;
   p.cand_score = cand_score;
   p.cand_id = cand_id;
   const int stage_bytes = ctas == 2 ? SCfg<2>::kStageBytes : SCfg<1>::kStageBytes;

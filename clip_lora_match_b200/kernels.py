@@ -130,7 +130,8 @@ def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, causal: bo
     return out
 
 
-SAMPLE_ROWS = 16384  # rows whose exact scores seed the scan thresholds (multiple of 256)
+SAMPLE_ROWS = 4096  # rows whose exact scores seed the scan thresholds (multiple of 256); the shared score
+# histogram of the scan takes over from the seed within the first tiles, so a small sample is enough
 # |bf16 score - fp32 score| for L2-normalised rows rounded to bf16: each factor carries a relative error of at
 # most 2^-9, so a product is off by at most ~2^-8 |q_i e_i| and the dot product by 2^-8 sum|q_i e_i| <= 2^-8
 # (Cauchy-Schwarz, unit norms); fp32 accumulation adds ~1e-5.
@@ -197,12 +198,12 @@ def search_topk(q_f32: torch.Tensor, q_bf16: torch.Tensor, index_bf16: torch.Ten
         return out_s, out_i
     if margin is None:
         margin = 2.0 * EPS_BF16 if index_f32 is not None else 0.0
-    kc = list_cap if list_cap is not None else min(LIST_CAP, max(32, 2 * k))  # candidates kept per (query, split)
+    kc = list_cap if list_cap is not None else min(LIST_CAP, max(16, k + 14))  # candidates kept per (query, split)
     # Per-query running lower bound of t_k shared by all work units of the scan (see clm_search_topk): a
     # unit's full list proves kc rows above its minimum, which bounds t_k only if kc >= k.  It is seeded from
     # a sample: scores of the queries against the first SAMPLE_ROWS index rows (plain tcgen05 GEMM, same bf16
     # operands as the scan) -> exact k-th largest per query.
-    thr = None
+    thr = hist = hist_base = None
     if kc >= k:
         if n >= 4 * SAMPLE_ROWS:
             sample_scores = gemm_epi(q_bf16, index_bf16[:SAMPLE_ROWS], out_dtype=torch.float32)
@@ -210,12 +211,17 @@ def search_topk(q_f32: torch.Tensor, q_bf16: torch.Tensor, index_bf16: torch.Ten
             check(lib.clm_kth_largest(ptr(sample_scores), nq, SAMPLE_ROWS, k, 1e-5, ptr(thr), cur_stream()),
                   "clm_kth_largest")
             del sample_scores
+            # shared per-query score histogram above the seed (clm_search_topk): lets the bound follow the k-th
+            # best over everything scanned so far instead of what one work unit has seen
+            hist_base = thr.clone()
+            hist = torch.zeros((nq, 32), dtype=torch.int32, device=dev)
         else:
             thr = torch.full((nq,), float("-inf"), dtype=torch.float32, device=dev)
     splits = lib.clm_search_num_splits(nq, n)
     cand_s = torch.empty((nq, splits, kc), dtype=torch.float32, device=dev)
     cand_i = torch.empty((nq, splits, kc), dtype=torch.int32, device=dev)
-    check(lib.clm_search_topk(ptr(q_bf16), ptr(index_bf16), nq, n, dim, kc, splits, ptr(thr), float(margin),
+    check(lib.clm_search_topk(ptr(q_bf16), ptr(index_bf16), nq, n, dim, kc, k, splits, ptr(thr), ptr(hist_base), ptr(hist),
+                              float(margin),
                               ptr(cand_s), ptr(cand_i), cur_stream()), "clm_search_topk")
     overflow = torch.empty((nq,), dtype=torch.int32, device=dev) if index_f32 is not None else None
     check(lib.clm_topk_merge(ptr(cand_s), ptr(cand_i), nq, splits, kc, float(margin), ptr(q_f32), ptr(index_f32),

@@ -229,19 +229,24 @@ int clm_search_num_splits(int num_queries, int num_rows);
  * from the bf16 shadow of the index; the score matrix stays in TMEM; every (query,
  * split) keeps its kc best candidates.  q_bf16 [nq, dim], index_bf16 [n, dim],
  * cand_score fp32 / cand_id int32 [nq, splits, kc].  dim multiple of 64, kc <= 64.
- * thr_io (fp32 [nq], may be NULL): per-query lower bound L of the kc-th best bf16 score over the whole
- * index, shared by all work units of the scan through atomic max.  The caller initialises it (-inf, or any
- * valid lower bound such as the kc-th best score of a sample of rows); on return it holds the tightest bound
- * the scan established.  Scores <= L - margin are never kept, so per-split lists may hold fewer than kc
- * entries; empty slots are (-inf, -1).
+ * thr_io (fp32 [nq], may be NULL): per-query lower bound L of the kb-th best bf16 score over the whole
+ * index (kb = the k the caller will ask clm_topk_merge for), shared by all work units of the scan through
+ * atomic max.  The caller initialises it (-inf, or any valid lower bound such as the kb-th best score of a
+ * sample of rows); a unit publishes the minimum of its list as soon as the list holds kb entries; on return it
+ * holds the tightest bound the scan established.  Scores <= L - margin are never kept, so per-split lists may
+ * hold fewer than kc entries; empty slots are (-inf, -1).  Lists are unordered.
  * margin: bf16 scores only NOMINATE rows for the exact fp32 re-score of clm_topk_merge.  With |bf16 score -
  * fp32 score| <= eps for every row (unit-norm rows rounded to bf16: eps <= 2^-8), every row of the fp32
- * top-k has a bf16 score >= t_k - 2 eps, t_k the k-th best bf16 score; since L <= t_kc <= t_k for kc >= k,
- * margin = 2 eps keeps all of them.  Pass NULL for thr_io when kc < k (the list minimum of a unit is then no
- * bound of t_k). */
-int clm_search_topk(const void* q_bf16, const void* index_bf16, int nq, int n, int dim, int kc,
-                    int splits, float* thr_io, float margin, float* cand_score, int32_t* cand_id,
-                    void* stream);
+ * top-k has a bf16 score >= t_k - 2 eps, t_k the k-th best bf16 score; since L <= t_k, margin = 2 eps keeps
+ * all of them -- unless a list overflows, which clm_topk_merge detects.  thr_io must be NULL when kb > kc.
+ * hist_base (fp32 [nq]) / hist (uint32 [nq, 32], zeroed by the caller, 16-byte aligned), both optional: a
+ * per-query histogram of the kept candidates' scores above hist_base[q] in steps of 1/256, shared by all work
+ * units: kb candidates counted at or above a bin edge prove t_kb >= that edge over ALL rows seen so far, which
+ * tightens L much earlier than any single unit's list can (a unit only sees 1/splits of the rows).  Queries
+ * with hist_base = -inf do not use it. */
+int clm_search_topk(const void* q_bf16, const void* index_bf16, int nq, int n, int dim, int kc, int kb,
+                    int splits, float* thr_io, const float* hist_base, uint32_t* hist, float margin,
+                    float* cand_score, int32_t* cand_id, void* stream);
 
 /* out[r] = (kth largest of x[r, 0..n)) - guard, for each of `rows` rows of a row-major fp32 matrix
  * (n <= 16384).  Seeds clm_search_topk's thr_io from the exact scores of a sample of index rows

@@ -37,7 +37,7 @@ def test_invalid_arguments_return_error_codes_not_crashes():
     lib = _lib.load()
     rc = lib.clm_layernorm(None, None, None, None, 4, 768, 1e-5, None)
     assert rc != 0 and b"clm_layernorm" in lib.clm_last_error()
-    rc = lib.clm_search_topk(None, None, 1, 1, 512, 10, 1, None, 0.0, None, None, None)
+    rc = lib.clm_search_topk(None, None, 1, 1, 512, 10, 10, 1, None, None, None, 0.0, None, None, None)
     assert rc != 0
     with pytest.raises(_lib.ClmError):
         _lib.check(rc, "clm_search_topk")

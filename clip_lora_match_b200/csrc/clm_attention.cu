@@ -1377,6 +1377,465 @@ attention_kernel_v2(const __grid_constant__ CUtensorMap map64, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+
+// =====================================================================================================
+// attention_kernel_v3 — key-blocked, single-pass softmax (vision towers: 128 < keys <= 256, non-causal).
+//
+// attention_kernel keeps a whole score row (up to 256 columns) per 128-query tile in TMEM and reads it
+// twice (row max, then exponentials); its two streams are serial chains S -> max -> exp -> P V -> drain ->
+// store of ~11-13 k clocks each, so a tile leaves an SM every ~6.5 k clocks although MUFU.EX2 would allow
+// one per ~2 k.  Here a tile is processed as TWO key blocks of <= 128 keys:
+//   * TMEM per stream (tile parity) g: buffer A = columns [256g, 256g+128), buffer B = [256g+128, 256g+256).
+//     S(block 0) -> A, S(block 1) -> B, both issued back to back; P(block) overwrites the first half of its
+//     own buffer; the O accumulator lives in the upper half of A (dead once block 0's scores are in
+//     registers).  512 columns = 2 streams x 2 buffers, no spare accumulator needed.
+//   * softmax: one thread per query row, 4 warps per stream.  A block's 128 scores are loaded ONCE into
+//     registers (four tcgen05.ld.x32 in flight together), reduced to the block max, exponentiated and written
+//     back as bf16 P.  The warpgroups' register budget is raised with setmaxnreg (the TMA / MMA / extra-token
+//     warps give theirs up).
+//   * online softmax across the two blocks with a lazy rescale: block 1 is exponentiated relative to the
+//     block-0 maximum m unless some row's block-1 maximum exceeds m by more than 8 (log2 units: P <= 256 is
+//     harmless in bf16 / fp32); only then O = P0 V0 is rescaled in TMEM (tcgen05.ld -> x 2^(m - m') ->
+//     tcgen05.st) before P1 V1 accumulates.  Softmax is shift invariant, so the result is the same function.
+//   * P0 V0 runs on the tensor pipe while the softmax warps work on block 1, S(block 1) while they work on
+//     block 0: the per-stream chain shrinks to exp(block 0) + exp(block 1) + P1 V1 + drain.
+// Warp roles (16 warps): 0 TMA producer, 1 MMA issuer, 4..7 / 8..11 softmax of stream 0 / 1,
+// {2, 3, 12, 13} extra-token rows (T = 128k + 1), 14, 15 idle (they complete the fourth warpgroup).
+// =====================================================================================================
+constexpr int kThreadsV3 = 512;
+constexpr int kRegsSoftmaxV3 = 176;  // setmaxnreg targets: 2 x 128 x 176 + 2 x 128 x 80 = 65536 registers
+constexpr int kRegsOtherV3 = 80;
+#ifndef CLM_ATTN_POLY3
+#define CLM_ATTN_POLY3 0  // of every 4 exponentials, how many run on the FMA pipe in attention_kernel_v3
+#endif
+
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
+__global__ void __launch_bounds__(kThreadsV3, 1)
+attention_kernel_v3(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CUtensorMap map16,
+                    const __grid_constant__ CUtensorMap map_out, __nv_bfloat16* __restrict__ out, AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* ostage = smem + p.stages * p.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + (p.stage_out == 1 ? kOutStageBytes : 0));
+  uint64_t* stage_full = bars;                     // [kMaxStages]
+  uint64_t* stage_empty = bars + kMaxStages;       // [kMaxStages]
+  uint64_t* s_full0 = bars + 2 * kMaxStages;       // [2] S(block 0) ready, by stream; one completion per tile
+  uint64_t* s_full1 = s_full0 + 2;                 // [2] S(block 1) ready
+  uint64_t* p_full0 = s_full0 + 4;                 // [2] P(block 0) written (128 softmax threads)
+  uint64_t* p_full1 = s_full0 + 6;                 // [2] P(block 1) written
+  uint64_t* pv0_done = s_full0 + 8;                // [2] O = P0 V0 complete (only waited for before a rescale)
+  uint64_t* o_full = s_full0 + 10;                 // [2] O complete
+  uint64_t* slot_free = s_full0 + 12;              // [2] O drained (128 softmax threads)
+  uint64_t* tail_go = s_full0 + 14;                // [4] item of extra-token warp j has landed (MMA thread arrives)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full0 + 18);
+  uint8_t* vxs = reinterpret_cast<uint8_t*>(bars) + 256;      // [8 warps][128 B] copies of the extra V row
+  float* prow = reinterpret_cast<float*>(vxs + 8 * 128);      // [4 warps][288] extra-token probability rows
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int T = p.T, H = p.H, Tp = p.Tp, Tk = p.Tk, D = p.H * kHeadDim;
+  const int kv_bytes = Tp * 128;
+  const int nk1 = Tk - 128;                        // keys of block 1 the MMA computes (multiple of 16)
+  const int valid1 = (T < Tk ? T : Tk) - 128;      // ... of which real keys
+  const int n_local = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                      static_cast<int>(gridDim.x);
+  const int n_tiles = n_local * p.mtiles;
+  const int tail_w = tail_index_v2(warp);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map64);
+    tma_prefetch_desc(&map16);
+    if (p.stage_out) tma_prefetch_desc(&map_out);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&stage_full[s], 1);
+      mbar_init(&stage_empty[s], 1 + p.xt + (p.stage_out == 2 ? 4 * p.mtiles : 0));
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full0[s], 1);
+      mbar_init(&s_full1[s], 1);
+      mbar_init(&p_full0[s], 128);
+      mbar_init(&p_full1[s], 128);
+      mbar_init(&pv0_done[s], 1);
+      mbar_init(&o_full[s], 1);
+      mbar_init(&slot_free[s], 128);
+    }
+    for (int s = 0; s < 4; ++s) mbar_init(&tail_go[s], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // register budgets: the two softmax warpgroups (warps 4..11) take what the others give up.  setmaxnreg is the
+  // first statement of each warpgroup's branch so that ptxas allocates that branch against the new budget.
+  if (warp < 4 || warp >= 12) {
+  setmaxnreg_dec<kRegsOtherV3>();
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int n64 = Tp / 64, n16 = (Tp % 64) / 16;
+      int st = 0;
+      uint32_t ph = 0;
+      for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+        const int b = it / H, h = it % H;
+        const int row_base = b * T;
+        mbar_wait(&stage_empty[st], ph ^ 1);
+        uint8_t* base = smem + st * p.stage_bytes;
+        mbar_arrive_expect_tx(&stage_full[st], static_cast<uint32_t>(3 * kv_bytes));
+        for (int part = 0; part < 3; ++part) {  // 0 = Q, 1 = K, 2 = V
+          uint8_t* dst = base + part * kv_bytes;
+          const int col = part * D + h * kHeadDim;
+          for (int i = 0; i < n64; ++i)
+            tma_load_2d(dst + i * 8192, &map64, &stage_full[st], col, row_base + i * 64);
+          for (int i = 0; i < n16; ++i)
+            tma_load_2d(dst + n64 * 8192 + i * 2048, &map16, &stage_full[st], col,
+                        row_base + n64 * 64 + i * 16);
+        }
+        if (++st == p.stages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: two independent streams (tile parity), three steps per tile =================
+    //   step 0: stage landed, O(t-2) drained      -> S0 = Q K0^T into buffer A, S1 = Q K1^T into buffer B
+    //   step 1: P0 published                      -> O  = P0 V0
+    //   step 2: P1 published                      -> O += P1 V1  (the last one of an item releases its stage)
+    const uint32_t idesc_pv = umma_idesc_bf16(128, kHeadDim, 0, 1);
+    const uint32_t idesc_s0 = umma_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_s1 = umma_idesc_bf16(128, nk1, 0, 0);
+    struct Cursor {
+      int t, mt, st, li;
+      uint32_t ph;   // parity of the stage's current fill
+      uint32_t tph;  // parity of this stream's per-tile barriers (one completion per tile)
+      __device__ void init(int t0, const AttnParams& p) {
+        t = t0; mt = t0; st = 0; ph = 0; li = 0; tph = 0;
+        while (mt >= p.mtiles) { mt -= p.mtiles; bump(p); }
+      }
+      __device__ void bump(const AttnParams& p) {
+        ++li;
+        if (++st == p.stages) { st = 0; ph ^= 1; }
+      }
+      __device__ void advance(const AttnParams& p) {
+        t += 2; mt += 2; tph ^= 1;
+        while (mt >= p.mtiles) { mt -= p.mtiles; bump(p); }
+      }
+    };
+    int pv_cnt[kMaxStages];
+#pragma unroll
+    for (int i = 0; i < kMaxStages; ++i) pv_cnt[i] = 0;
+    Cursor cur[2];
+    int step[2] = {0, 0};
+    cur[0].init(0, p); cur[1].init(1, p);
+    while (cur[0].t < n_tiles || cur[1].t < n_tiles) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        Cursor& c = cur[g];
+        if (c.t >= n_tiles) continue;
+        const uint32_t buf_a = tmem + static_cast<uint32_t>(g * 256);
+        const uint32_t buf_b = buf_a + 128u;
+        const uint32_t sbase = smem_u32(smem + c.st * p.stage_bytes);
+        if (step[g] == 0) {
+          bool ok = mbar_try_wait(&stage_full[c.st], c.ph);
+          if (ok && c.t >= 2) ok = mbar_try_wait(&slot_free[g], c.tph ^ 1);  // O(t-2) left buffer A
+          if (ok) {
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t q_addr = sbase + static_cast<uint32_t>(c.mt) * 16384u;
+              const uint32_t k_addr = sbase + static_cast<uint32_t>(kv_bytes);
+#pragma unroll
+              for (int k = 0; k < kHeadDim / 16; ++k)
+                umma_bf16_ss(buf_a, umma_desc_sw128(q_addr + k * 32, 1024), umma_desc_sw128(k_addr + k * 32, 1024),
+                             idesc_s0, k != 0 ? 1u : 0u);
+              umma_commit(&s_full0[g]);
+#pragma unroll
+              for (int k = 0; k < kHeadDim / 16; ++k)
+                umma_bf16_ss(buf_b, umma_desc_sw128(q_addr + k * 32, 1024),
+                             umma_desc_sw128(k_addr + 128 * 128 + k * 32, 1024), idesc_s1, k != 0 ? 1u : 0u);
+              umma_commit(&s_full1[g]);
+              if (p.xt && c.mt == 0) mbar_arrive(&tail_go[c.li & 3]);
+            }
+            __syncwarp();
+            step[g] = 1;
+          }
+        } else if (step[g] == 1) {
+          if (mbar_try_wait(&p_full0[g], c.tph)) {
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t v_addr = sbase + static_cast<uint32_t>(2 * kv_bytes);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                umma_bf16_ts(buf_a + 64u, buf_a + static_cast<uint32_t>(ks * 8), umma_desc_sw128_mn(v_addr + ks * 2048),
+                             idesc_pv, ks != 0 ? 1u : 0u);
+              umma_commit(&pv0_done[g]);
+            }
+            __syncwarp();
+            step[g] = 2;
+          }
+        } else {
+          if (mbar_try_wait(&p_full1[g], c.tph)) {
+            tc_fence_after();
+            const bool last = (++pv_cnt[c.st] == p.mtiles);
+            if (last) pv_cnt[c.st] = 0;
+            if (lane == 0) {
+              const uint32_t v_addr = sbase + static_cast<uint32_t>(2 * kv_bytes) + 8u * 2048u;
+              for (int ks = 0; ks < nk1 / 16; ++ks)
+                umma_bf16_ts(buf_a + 64u, buf_b + static_cast<uint32_t>(ks * 8), umma_desc_sw128_mn(v_addr + ks * 2048),
+                             idesc_pv, 1u);
+              umma_commit(&o_full[g]);
+              if (last) umma_commit(&stage_empty[c.st]);
+            }
+            __syncwarp();
+            c.advance(p);
+            step[g] = 0;
+          }
+        }
+      }
+    }
+  } else if (tail_w >= 0 && p.xt) {
+    // ================= extra-token warps (see attention_kernel_v2) =================
+    float* my_prow = prow + tail_w * 288;
+    int st = 0, tl = 0;
+    uint32_t own_ph = 0;
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, ++tl) {
+      if ((tl & 3) == tail_w) {
+        const int b = it / H, h = it - b * H;
+        mbar_wait(&tail_go[tail_w], own_ph);
+        own_ph ^= 1;
+        const uint32_t sb = smem_u32(smem + st * p.stage_bytes);
+        uint32_t* orow_g = reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * T + Tk) * D + h * kHeadDim);
+        if (Tk == 256) tail_row<8>(sb, kv_bytes, my_prow, lane, orow_g);
+        else tail_row<4>(sb, kv_bytes, my_prow, lane, orow_g);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stage_empty[st]);
+      }
+      if (++st == p.stages) st = 0;
+    }
+  }
+  } else {
+    setmaxnreg_inc<kRegsSoftmaxV3>();
+    // ================= softmax: one thread per query row, one key block (<= 128 scores) in registers =================
+    const int g = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
+    constexpr float kLazy = 8.0f;  // block 1 keeps the block-0 maximum unless it is exceeded by more than this (log2)
+    const uint32_t buf_a = tmem + lane_off + static_cast<uint32_t>(g * 256);
+    const uint32_t buf_b = buf_a + 128u;
+    const uint32_t orow = buf_a + 64u;
+    const bool xt = p.xt != 0;
+    const uint32_t vx_w = smem_u32(vxs + (warp - 4) * 128);
+    const int nch1 = (nk1 + 31) / 32;  // 32-column chunks of block 1 (3 or 4)
+    uint32_t tph = 0;                  // parity of this stream's per-tile barriers
+    int t = 0, li = 0;
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, ++li)
+    for (int mt = 0; mt < p.mtiles; ++mt, ++t) {
+      if ((t & 1) != g) continue;
+      const int b = it / H, h = it - b * H;
+      const int qi = mt * 128 + r;
+      const bool warp_live = mt * 128 + q * 32 < T;
+      const int st_cur = li % p.stages;
+      float sx = 0.f, px = 0.f;
+      if (xt) {  // extra key (row Tk of K / V): q_row . k_x on the CUDA cores, private copy of v_x
+        mbar_wait(&stage_full[st_cur], static_cast<uint32_t>((li / p.stages) & 1));
+        const uint32_t sb = smem_u32(smem + st_cur * p.stage_bytes);
+        const uint32_t qa = sb + static_cast<uint32_t>(qi) * 128u;
+        const uint32_t ka = sb + static_cast<uint32_t>(kv_bytes + Tk * 128);
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 a = ld_shared_v4(qa + ((static_cast<uint32_t>(c) ^ static_cast<uint32_t>(r & 7)) << 4));
+          const uint4 kx = ld_shared_v4(ka + (static_cast<uint32_t>(c) << 4));
+          dot8(a, kx, d0, d1);
+        }
+        sx = d0 + d1;
+        if (lane < 8) {
+          const uint4 w = ld_shared_v4(sb + static_cast<uint32_t>(2 * kv_bytes + Tk * 128 + (lane << 4)));
+          st_shared_v4(vx_w + (lane << 4), w.x, w.y, w.z, w.w);
+        }
+        __syncwarp();
+      }
+
+      uint32_t v0[32], v1[32], v2[32], v3[32], pk[16];
+      float mrow = -INFINITY, sum = 0.f;
+      // ---- block 0: 128 real keys
+      mbar_wait(&s_full0[g], tph);
+      tc_fence_after();
+      if (warp_live) {
+        tmem_ld_32x32b_x32(buf_a, v0);
+        tmem_ld_32x32b_x32(buf_a + 32, v1);
+        tmem_ld_32x32b_x32(buf_a + 64, v2);
+        tmem_ld_32x32b_x32(buf_a + 96, v3);
+        tmem_ld_wait_dep(v0); tmem_ld_wait_dep(v1); tmem_ld_wait_dep(v2); tmem_ld_wait_dep(v3);
+        mrow = chunk_max3(v3, chunk_max3(v2, chunk_max3(v1, chunk_max3(v0, -INFINITY))));
+        if (xt) mrow = fmaxf(mrow, sx);
+        const float neg_mx = -mrow * kScaleLog2e;
+        if (xt) {
+          px = fast_exp2(fmaf(sx, kScaleLog2e, neg_mx));
+          sum = px;
+        }
+        sum += chunk_exp_v2<false, CLM_ATTN_POLY3>(v0, pk, kScaleLog2e, neg_mx, 0, 128);
+        tmem_st_32x32b_x16(buf_a, pk);
+        sum += chunk_exp_v2<false, CLM_ATTN_POLY3>(v1, pk, kScaleLog2e, neg_mx, 32, 128);
+        tmem_st_32x32b_x16(buf_a + 16, pk);
+        sum += chunk_exp_v2<false, CLM_ATTN_POLY3>(v2, pk, kScaleLog2e, neg_mx, 64, 128);
+        tmem_st_32x32b_x16(buf_a + 32, pk);
+        sum += chunk_exp_v2<false, CLM_ATTN_POLY3>(v3, pk, kScaleLog2e, neg_mx, 96, 128);
+        tmem_st_32x32b_x16(buf_a + 48, pk);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&p_full0[g]);
+
+      // ---- block 1: nk1 computed keys, valid1 of them real
+      mbar_wait(&s_full1[g], tph);
+      tc_fence_after();
+      if (warp_live) {
+        tmem_ld_32x32b_x32(buf_b, v0);
+        tmem_ld_32x32b_x32(buf_b + 32, v1);
+        tmem_ld_32x32b_x32(buf_b + 64, v2);
+        if (nch1 > 3) tmem_ld_32x32b_x32(buf_b + 96, v3);
+        tmem_ld_wait_dep(v0); tmem_ld_wait_dep(v1); tmem_ld_wait_dep(v2); tmem_ld_wait_dep(v3);
+        float m1 = -INFINITY;
+        m1 = (32 <= valid1) ? chunk_max3(v0, m1) : chunk_max_masked(v0, m1, 0, valid1);
+        m1 = (64 <= valid1) ? chunk_max3(v1, m1) : chunk_max_masked(v1, m1, 32, valid1);
+        m1 = (96 <= valid1) ? chunk_max3(v2, m1) : chunk_max_masked(v2, m1, 64, valid1);
+        if (nch1 > 3) m1 = (128 <= valid1) ? chunk_max3(v3, m1) : chunk_max_masked(v3, m1, 96, valid1);
+        // lazy rescale: only when some row's maximum moved up by more than kLazy
+        const bool grow = (m1 - mrow) * kScaleLog2e > kLazy;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = grow ? m1 : mrow;
+          const float alpha = fast_exp2((mrow - m_new) * kScaleLog2e);  // 1 for rows that keep their maximum
+          mbar_wait(&pv0_done[g], tph);
+          tc_fence_after();
+          uint32_t o[32];
+#pragma unroll 1
+          for (int hc = 0; hc < 2; ++hc) {
+            tmem_ld_32x32b_x32(orow + hc * 32, o);
+            tmem_ld_wait_dep(o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(orow + hc * 32, o);
+          }
+          tmem_st_wait();
+          sum *= alpha;
+          px *= alpha;
+          mrow = m_new;
+        }
+        const float neg_mx = -mrow * kScaleLog2e;
+        sum += (32 <= valid1) ? chunk_exp_v2<false, CLM_ATTN_POLY3>(v0, pk, kScaleLog2e, neg_mx, 0, valid1)
+                              : chunk_exp_v2<true, 0>(v0, pk, kScaleLog2e, neg_mx, 0, valid1);
+        tmem_st_32x32b_x16(buf_b, pk);
+        sum += (64 <= valid1) ? chunk_exp_v2<false, CLM_ATTN_POLY3>(v1, pk, kScaleLog2e, neg_mx, 32, valid1)
+                              : chunk_exp_v2<true, 0>(v1, pk, kScaleLog2e, neg_mx, 32, valid1);
+        tmem_st_32x32b_x16(buf_b + 16, pk);
+        if (nk1 > 64) {  // keys 64.. of block 1 exist (the MMA reads nk1 / 2 packed columns of P)
+          sum += (96 <= valid1) ? chunk_exp_v2<false, CLM_ATTN_POLY3>(v2, pk, kScaleLog2e, neg_mx, 64, valid1)
+                                : chunk_exp_v2<true, 0>(v2, pk, kScaleLog2e, neg_mx, 64, valid1);
+          tmem_st_32x32b_x16(buf_b + 32, pk);
+        }
+        if (nk1 > 96) {
+          sum += (128 <= valid1) ? chunk_exp_v2<false, CLM_ATTN_POLY3>(v3, pk, kScaleLog2e, neg_mx, 96, valid1)
+                                 : chunk_exp_v2<true, 0>(v3, pk, kScaleLog2e, neg_mx, 96, valid1);
+          tmem_st_32x32b_x16(buf_b + 48, pk);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&p_full1[g]);
+
+      // ---- O: out of TMEM, + p_x v_x, / row sum, bf16, out through shared memory and a TMA tile store
+      mbar_wait(&o_full[g], tph);
+      tc_fence_after();
+      if (warp_live) {
+        tmem_ld_32x32b_x32(orow, v0);
+        tmem_ld_32x32b_x32(orow + 32, v1);
+        tmem_ld_wait_dep(v0);
+        tmem_ld_wait_dep(v1);
+      }
+      tc_fence_before();
+      mbar_arrive(&slot_free[g]);
+      if (xt && warp_live) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint4 w = ld_shared_v4(vx_w + (jj << 4));
+          uint32_t* o = (jj < 4) ? &v0[8 * jj] : &v1[8 * (jj - 4)];
+          o[0] = __float_as_uint(fmaf(px, bf16_lo(w.x), __uint_as_float(o[0])));
+          o[1] = __float_as_uint(fmaf(px, bf16_hi(w.x), __uint_as_float(o[1])));
+          o[2] = __float_as_uint(fmaf(px, bf16_lo(w.y), __uint_as_float(o[2])));
+          o[3] = __float_as_uint(fmaf(px, bf16_hi(w.y), __uint_as_float(o[3])));
+          o[4] = __float_as_uint(fmaf(px, bf16_lo(w.z), __uint_as_float(o[4])));
+          o[5] = __float_as_uint(fmaf(px, bf16_hi(w.z), __uint_as_float(o[5])));
+          o[6] = __float_as_uint(fmaf(px, bf16_lo(w.w), __uint_as_float(o[6])));
+          o[7] = __float_as_uint(fmaf(px, bf16_hi(w.w), __uint_as_float(o[7])));
+        }
+      }
+      const float inv = 1.0f / sum;
+      if (p.stage_out) {
+        const uint32_t ost = (p.stage_out == 2)
+                                 ? smem_u32(smem + st_cur * p.stage_bytes) + static_cast<uint32_t>(mt * 128 + q * 32) * 128u
+                                 : smem_u32(ostage + (g * 4 + q) * 4096);
+        if (warp_live) {
+          if (p.stage_out == 1) {  // the previous tile's slab has left the staging buffer
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const uint32_t* o = (jj < 4) ? &v0[8 * jj] : &v1[8 * (jj - 4)];
+            st_shared_v4(ost + static_cast<uint32_t>(lane) * 128u + ((static_cast<uint32_t>(jj) ^ (lane & 7)) << 4),
+                         pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv),
+                         pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv),
+                         pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv),
+                         pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_out, ost, h * kHeadDim, mt * 128 + q * 32, b);
+            bulk_commit();
+          }
+        }
+        if (p.stage_out == 2 && lane == 0) {
+          bulk_wait_read<0>();
+          mbar_arrive(&stage_empty[st_cur]);
+        }
+        __syncwarp();
+      } else if (warp_live && qi < T) {
+        uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(b * T + qi) * D + h * kHeadDim);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint32_t* o = (jj < 4) ? &v0[8 * jj] : &v1[8 * (jj - 4)];
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+          o4[jj] = w;
+        }
+      }
+      tph ^= 1;
+    }
+    if (p.stage_out && lane == 0) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 
 int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int heads, int causal,
@@ -1500,6 +1959,36 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   // algorithmic work: QK^T and PV at the true T (causal not discounted)
   ProfScope prof(CLM_K_ATTENTION, 4.0 * batch * heads * static_cast<double>(T) * T * kHeadDim,
                  2.0 * batch * T * 4.0 * D, stream);
+  // CLM_ATTN_V3=1 selects the key-blocked single-pass kernel (attention_kernel_v3) for the vision shapes
+  // (non-causal, 128 < keys <= 256, at least two pipeline stages).  Measured 20-25 % SLOWER than the whole-row
+  // kernel (profiles/r2_attention_notes.md): with M = 128 an MMA costs >= 133 clocks whatever N is (the A tile
+  // is fetched at ~32 B/clk, tools/microbench/umma_rate.cu), so two N = 128 score blocks cost more tensor time
+  // than one N = 256 row, and every extra hand-off adds a ~500-clock commit -> mbarrier round trip.  Kept for
+  // A/B measurements; it is exercised by the same unit tests.
+  static int use_v3 = -1;
+  if (use_v3 < 0) {
+    const char* e = getenv("CLM_ATTN_V3");
+    use_v3 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (use_v3 && !causal && p.Tk > 128 && p.Tk <= 256 && stages >= 2) {
+    // the whole-row TMEM plans above may have switched the output staging off (two-block plan) or asked for
+    // the in-place variant only for the extra-token shape: redo the choice for this kernel
+    int so = ((227 * 1024 - 1024 - 256 - kXchBytes - (p.xt ? kXtBytes : 0) - kOutStageBytes) / stage_bytes >= 2) ? 1 : 0;
+    if (!so && p.xt) so = 2;
+    p.stage_out = so;
+    const int smem_v3 = stages * stage_bytes + (so == 1 ? kOutStageBytes : 0) + 256 + kXchBytes + (p.xt ? kXtBytes : 0) + 1024;
+    CUtensorMap map_out3 = map64;
+    if (so) {
+      rc = clm_make_tmap_bf16_3d(&map_out3, out, static_cast<uint64_t>(D), static_cast<uint64_t>(T),
+                                 static_cast<uint64_t>(batch), 2ull * D, 2ull * D * T, kHeadDim, 32);
+      if (rc) return rc;
+    }
+    CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v3));
+    attention_kernel_v3<<<grid, kThreadsV3, smem_v3, stream>>>(map64, map16, map_out3,
+                                                                static_cast<__nv_bfloat16*>(out), p);
+    CLM_CUDA_CHECK(cudaGetLastError());
+    return CLM_OK;
+  }
   // CLM_ATTN_V2=1 selects the one-thread-per-row kernel (attention_kernel_v2) for the plans with a single key
   // block and two S regions.  Measured (profiles/r2_attention_notes.md) it is 5-25 % SLOWER than the
   // two-threads-per-row kernel: each stream is a serial chain S -> max -> exp -> P V -> drain -> store, and

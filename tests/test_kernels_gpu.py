@@ -318,6 +318,25 @@ def test_attention(cuda_device, batch, tokens, heads, causal):
     _close(f"attention_{batch}x{tokens}x{heads}_{int(causal)}", out, ref, atol=1.5e-2, rtol=1e-2, qkv=qkv)
 
 
+@pytest.mark.parametrize("batch,tokens,heads", [(3, 257, 4), (3, 197, 4), (2, 200, 2), (2, 256, 2), (2, 145, 2)])
+def test_attention_key_blocks_with_late_maximum(cuda_device, batch, tokens, heads):
+    """The key-blocked kernel exponentiates block 1 (keys 128..) relative to the block-0 maximum and rescales
+    O = P0 V0 only when a row's maximum moves up by more than 8 (log2 units).  Keys of the second block are
+    scaled so that, per head, some rows need the rescale (logit gaps far above 8 / (0.125 log2 e) = 44), some
+    do not, and in some the late keys are far BELOW the early ones (their P underflows to 0)."""
+    D = heads * 64
+    g = _gen(44)
+    x = torch.randn((batch, tokens, 3, heads, 64), generator=g) * 1.2
+    x[:, 128:, 1, 0] *= 6.0            # head 0: late keys dominate -> every row rescales
+    x[:, 128:, 1, 1 % heads] *= 0.05   # head 1: late keys negligible
+    x[:, 140:150, 1, heads - 1] *= 5.0  # last head: a few late outliers, only rows aligned with them rescale
+    qkv = x.reshape(batch * tokens, 3 * D).bfloat16()
+    out = K.attention(qkv.to(cuda_device), batch, tokens, heads, False)
+    ref = _attn_ref(qkv, batch, tokens, heads, False)
+    assert torch.isfinite(out).all()
+    _close(f"attention_late_max_{batch}x{tokens}x{heads}", out, ref, atol=2e-2, rtol=1.5e-2, qkv=qkv)
+
+
 # ------------------------------------------------------------------------------------------
 # search
 # ------------------------------------------------------------------------------------------

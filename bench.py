@@ -297,14 +297,53 @@ def main():
     value = BATCH * world * args.steps / (ms / 1e3)
 
     # ---- per-kernel durations, measured live with events around every launch -----------
+    # The profiled pass brackets every launch with two CUDA events on the launching stream.  Its accounting
+    # (sum of kernel durations, sum of the gaps between consecutive launches, its own wall time) is reported
+    # beside the unprofiled step time so that the difference between ms_per_step and the kernel sum is explained
+    # rather than assumed: see detail.step_accounting.
+    # Three profiled steps follow two unprofiled ones without any host synchronisation in between, and only the
+    # LAST step's records are used: a single step launched after a synchronize starts with power headroom and
+    # runs ~10 % faster than the sustained state the timed region is in (measured: 46.3 vs 50.9 ms).
+    PROF_STEPS = 3
+    for _ in range(2):
+        step()
     lib.clm_prof_enable(1)
-    step()
-    prof = {k: _lib.prof_summary(k) for k in ("gemm", "attention", "elementwise")}
-    recs = _lib.prof_records()
+    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pa.record()
+    for _ in range(PROF_STEPS):
+        step()
+    pb.record()
+    torch.cuda.synchronize()
+    prof_step_ms = pa.elapsed_time(pb) / PROF_STEPS
+    recs_all = _lib.prof_records()
+    tl_all = _lib.prof_timeline()
     lib.clm_prof_enable(0)
+    n_step = len(recs_all) // PROF_STEPS
+    recs, tl = recs_all[-n_step:], tl_all[-n_step:]
+    prof = {}
+    for kname in ("gemm", "attention", "elementwise"):
+        sel = [r for r in recs if r[0] == kname]
+        prof[kname] = {"ms": sum(r[3] for r in sel), "flops": sum(r[1] for r in sel), "bytes": sum(r[2] for r in sel),
+                       "launches": len(sel)}
     gemm = prof["gemm"]
     step_kernel_ms = sum(p["ms"] for p in prof.values())
-    # dominant kernel: the fc1 launches of gemm_kernel<256,2,bf16-store> (largest single share of the step)
+    gaps = [tl[i + 1][1] - (tl[i][1] + tl[i][2]) for i in range(len(tl) - 1)]
+    big_gaps = sorted(((g, i) for i, g in enumerate(gaps)), reverse=True)[:3]
+    accounting = {
+        "ms_per_step_unprofiled": ms / args.steps,
+        "profiled_step_wall_ms": prof_step_ms,
+        "sum_kernel_ms_profiled": step_kernel_ms,
+        "sum_gaps_between_launches_ms_profiled": sum(g for g in gaps if g > 0),
+        "launches": len(tl),
+        "largest_gaps_ms": [{"after_launch": i, "kind_before": tl[i][0], "kind_after": tl[i + 1][0], "gap_ms": round(g, 4)}
+                            for g, i in big_gaps],
+        "note": "kernel durations are those of the last of three back-to-back profiled steps (two events around every "
+                "launch) that follow unprofiled steps without a host synchronisation, i.e. of the sustained power-capped "
+                "state; a single profiled step launched after a synchronize ran ~10 % faster (boost clocks), which is what "
+                "made round 1's kernel sum fall short of ms_per_step",
+    }
+    # dominant kernel TYPE: every gemm_kernel launch of the step (77 % of its kernel time); the fc1 launches
+    # (largest single shape) are reported as a sub-entry
     fc1_flops = 2.0 * BATCH * 197 * arch.vision.mlp * arch.vision.width
     fc1_bytes = 2.0 * (BATCH * 197 * arch.vision.width + arch.vision.mlp * arch.vision.width) + \
         2.0 * BATCH * 197 * arch.vision.mlp  # fc2 has the same FLOPs but other bytes
@@ -314,20 +353,29 @@ def main():
     fc1_tf = fc1_flops / (fc1_ms * 1e-3) / 1e12 if fc1 else 0.0
     all_tf = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
+    for tname in ("r2_traffic.json", "r1_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
+            break
+    n_gemm = max(1, gemm["launches"])
     roofline = {"bound": "tensor",
-                "kernel": "gemm_kernel<256,2,store_bf16>: vision fc1 + QuickGELU, M=201728 N=3072 K=768 (tcgen05 cta_group::2)",
-                "achieved": fc1_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": fc1_tf / peaks["tf_sustained"], "frac_of_burst": fc1_tf / peaks["tf_burst"],
-                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                "algorithmic_flops_per_launch": fc1_flops, "algorithmic_bytes_per_launch": fc1_bytes, "avg_launch_ms": fc1_ms, "launches_per_step": len(fc1),
-                "share_of_step_kernel_time": sum(r[3] for r in fc1) / step_kernel_ms,
-                "traffic": traffic, "traffic_source": "ncu --set full, profiles/r1_traffic.json (bytes per launch)",
-                "all_gemm_launches": {"achieved": all_tf, "frac": all_tf / peaks["tf_sustained"],
-                                      "frac_of_burst": all_tf / peaks["tf_burst"], "launches_per_step": gemm["launches"],
-                                      "share_of_step_kernel_time": gemm["ms"] / step_kernel_ms}}
+                "kernel": "gemm_kernel<*>: all tcgen05 GEMM launches of the step (QKV + LoRA, out-proj, fc1 + QuickGELU, "
+                          "fc2, patch embed, projections; cta_group::2 256x256 tiles for the large ones)",
+                "achieved": all_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": all_tf / peaks["tf_sustained"], "frac_of_burst": all_tf / peaks["tf_burst"],
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernels timed inside a long step)",
+                "algorithmic_flops_per_launch": gemm["flops"] / n_gemm, "algorithmic_bytes_per_launch": gemm["bytes"] / n_gemm,
+                "avg_launch_ms": gemm["ms"] / n_gemm, "launches_per_step": gemm["launches"],
+                "share_of_step_kernel_time": gemm["ms"] / step_kernel_ms,
+                "traffic": traffic,
+                "traffic_source": "ncu --set full of the vision fc1 launch (bytes per launch; profiles/), the largest single shape",
+                "fc1_launches": {"kernel": "gemm_kernel<256,2,store_bf16>: vision fc1 + QuickGELU, M=201728 N=3072 K=768",
+                                 "achieved": fc1_tf, "frac": fc1_tf / peaks["tf_sustained"],
+                                 "frac_of_burst": fc1_tf / peaks["tf_burst"], "avg_launch_ms": fc1_ms,
+                                 "launches_per_step": len(fc1), "algorithmic_flops_per_launch": fc1_flops,
+                                 "algorithmic_bytes_per_launch": fc1_bytes,
+                                 "share_of_step_kernel_time": sum(r[3] for r in fc1) / step_kernel_ms}}
     va, ta = arch.vision, arch.text
     fl_img = flops_per_item(197, va.width, va.layers, va.mlp, arch.proj_dim, LORA_R, 2, 3 * 16 * 16, 196)
     fl_txt = flops_per_item(77, ta.width, ta.layers, ta.mlp, arch.proj_dim, LORA_R, 2)
@@ -343,6 +391,7 @@ def main():
         "whole_step_tflops_per_gpu": step_tf, "whole_step_frac_of_sustained_peak": step_tf / peaks["tf_sustained"],
         "whole_step_frac_of_burst_peak": step_tf / peaks["tf_burst"],
         "kernel_ms_per_step": {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in prof.items()},
+        "step_accounting": accounting,
     }
 
     # ---- the reference's own calling pattern: one image + one caption at a time (launch bound; the
@@ -398,10 +447,16 @@ def main():
         lv = arch_l.vision
         fl_l = flops_per_item(257, lv.width, lv.layers, lv.mlp, arch_l.proj_dim, LORA_R, 2, 3 * 14 * 14, 256)
         tf_l = fl_l * L14_BATCH / (ms_l / args.steps * 1e-3) / 1e12
+        for _ in range(2):  # sustained state: see the configs[1] profile above
+            model_l.encode_images(pv_l)
         lib.clm_prof_enable(1)
-        model_l.encode_images(pv_l)
-        prof_l = {k: _lib.prof_summary(k) for k in ("gemm", "attention", "elementwise")}
+        for _ in range(2):
+            model_l.encode_images(pv_l)
+        recs_l = _lib.prof_records()
         lib.clm_prof_enable(0)
+        recs_l = recs_l[-(len(recs_l) // 2):]
+        prof_l = {kn: {"ms": sum(r[3] for r in recs_l if r[0] == kn), "flops": sum(r[1] for r in recs_l if r[0] == kn),
+                       "launches": sum(1 for r in recs_l if r[0] == kn)} for kn in ("gemm", "attention", "elementwise")}
         l14 = {"workload": "configs[2]: CLIP ViT-L/14 + LoRA r=16 (q,v) image tower, batch 512 per GPU, random-init weights",
                "images_per_s": L14_BATCH * world * args.steps / (ms_l / 1e3), "ms_per_step": ms_l / args.steps,
                "algorithmic_gflop_per_image": fl_l / 1e9, "tflops_per_gpu": tf_l,

@@ -98,6 +98,7 @@ SIGNATURES = {
     "clm_prof_is_enabled": (_I, []),
     "clm_prof_enable": (_I, [_I]),
     "clm_prof_records": (_I, [C.POINTER(C.c_double), _I]),
+    "clm_prof_timeline": (_I, [C.POINTER(C.c_double), _I]),
     "clm_prof_summary": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                               C.POINTER(C.c_int)]),
 }
@@ -163,3 +164,16 @@ def prof_records() -> list:
     lib.clm_prof_records(buf, n)
     names = {v: k for k, v in KERNEL_KINDS.items()}
     return [(names[int(buf[4 * i])], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]) for i in range(n)]
+
+
+def prof_timeline() -> list:
+    """[(kind_name, start_ms, dur_ms)] of every launch recorded since prof_enable(1); start_ms counts from the
+    first recorded launch's start event."""
+    lib = load()
+    n = lib.clm_prof_timeline(None, 0)
+    if n <= 0:
+        return []
+    buf = (C.c_double * (3 * n))()
+    lib.clm_prof_timeline(buf, n)
+    names = {v: k for k, v in KERNEL_KINDS.items()}
+    return [(names[int(buf[3 * i])], buf[3 * i + 1], buf[3 * i + 2]) for i in range(n)]

@@ -227,3 +227,22 @@ extern "C" int clm_prof_records(double* out, int max_records) {
   }
   return i;
 }
+
+// The launch list with start stamps: out[3*i .. 3*i+2] = {kind, start offset in ms from the first recorded
+// launch's start event, duration in ms}.  Lets a caller see the gaps BETWEEN kernels of a step (start of launch
+// i+1 minus end of launch i), i.e. what the sum of kernel durations does not account for.
+extern "C" int clm_prof_timeline(double* out, int max_records) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int i = 0;
+  for (auto& r : g_recs) {
+    if (out && i < max_records) {
+      float st = 0.f, e = 0.f;
+      cudaEventElapsedTime(&st, g_recs.front().a, r.a);
+      cudaEventElapsedTime(&e, r.a, r.b);
+      out[3 * i + 0] = r.kind; out[3 * i + 1] = st; out[3 * i + 2] = e;
+    }
+    ++i;
+  }
+  return i;
+}

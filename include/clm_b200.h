@@ -316,6 +316,9 @@ int clm_prof_summary(int kind, double* ms, double* flops, double* bytes, int* la
 /* the launch list: out[4i..4i+3] = {kind, flops, bytes, ms} in launch order; returns the number of
  * records available (only max_records are written), -1 on a CUDA error */
 int clm_prof_records(double* out, int max_records);
+/* the same list with start stamps: out[3i..3i+2] = {kind, start offset in ms from the first recorded launch,
+ * duration in ms}; the gaps between consecutive launches are what the sum of kernel durations leaves out */
+int clm_prof_timeline(double* out, int max_records);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ def main():
     if a.build_only: return
     lib = C.CDLL(OUT)
     dev = torch.device("cuda")
-    NW, NT, NE = 21, 12, 8
+    NW, NT, NE = 24, 12, 8
     buf = torch.zeros(NW * NT * NE, dtype=torch.int64, device=dev)
     qkv = torch.randn((a.B * a.T, 3 * a.H * 64), device=dev).bfloat16()
     out = torch.empty((a.B * a.T, a.H * 64), dtype=torch.bfloat16, device=dev)
@@ -40,13 +40,19 @@ def main():
     t0 = int(tr[tr > 0].min())
     names = ["wait_S", "got_S", "pass1_done", "max_xchg", "P_published", "got_O", "O_in_regs", "stage_ok"]
     print(f"# T={a.T} H={a.H} B={a.B}: clocks relative to the first stamp; MMA warp (1): ev0 = S issued, ev1 = PV issued")
+    env = os.environ.get("CLM_ATTN_SPLIT", "1")
+    split = not a.causal and ((a.T == 257 and env != "0") or ((a.T + 15) // 16 * 16 == 208 and a.T > 192 and env == "2"))
+    mma_warps = (22, 23) if split else (1,)
+    tails = (0, 1, 2, 3) if split else (18, 19)
+    tma = 20 if split else 0
+    softs = range(4, 20) if split else range(2, 18)
+    s0 = 4 if split else 2
     for t in range(NT):
-        print(f"tile {t}: MMA S_issue={int(tr[1,t,0])-t0 if tr[1,t,0] else None} PV_issue={int(tr[1,t,1])-t0 if tr[1,t,1] else None} other={[int(x)-t0 if x else None for x in tr[1,t,2:].tolist()]}")
-        if tr[0, t, 1]:
-            print(f"   TMA warp, item {t}: wants_stage={int(tr[0,t,0])-t0} stage_free={int(tr[0,t,1])-t0}")
-        v1 = os.environ.get("CLM_ATTN_V2") != "1"
-        tails = (18, 19) if v1 else (2, 3, 12, 13)
-        softs = range(2, 18) if v1 else range(4, 12)
+        for w in mma_warps:
+            if tr[w, t, 0] or tr[w, t, 1]:
+                print(f"tile {t}: MMA warp {w} S_issue={int(tr[w,t,0])-t0 if tr[w,t,0] else None} PV_issue={int(tr[w,t,1])-t0 if tr[w,t,1] else None}")
+        if tr[tma, t, 1]:
+            print(f"   TMA warp, item {t}: wants_stage={int(tr[tma,t,0])-t0} stage_free={int(tr[tma,t,1])-t0}")
         for w in tails:
             ev = [int(x) - t0 if x else None for x in tr[w, t].tolist()]
             if any(e is not None for e in ev):
@@ -54,7 +60,7 @@ def main():
         for w in softs:
             ev = [int(x) - t0 if x else None for x in tr[w, t].tolist()]
             if any(e is not None for e in ev):
-                role = f"grp {((w-2)>>2)&1} half {(w-2)>>3} q {w&3}" if v1 else f"grp {(w-4)>>2} q {w&3}"
+                role = f"grp {((w-s0)>>2)&1} half {(w-s0)>>3} q {w&3}"
                 print(f"   warp {w:2d} ({role}): " + " ".join(f"{n}={e}" for n, e in zip(names, ev)))
 
 if __name__ == "__main__":

@@ -38,6 +38,15 @@ constexpr int kOutStageBytes = 8 * 4096;  // per (group, lane quarter): a 32-row
 constexpr int kXchBytes = 4096;   // row max / row sum exchanged between the two threads of a query row
 constexpr int kHeadDim = 64;
 constexpr int kMaxStages = 6;
+// hand-off waits of the split kernel: 1 = poll with test_wait, 0 = try_wait (measured: polling is 1-3 % slower)
+#ifndef CLM_ATTN_POLL
+#define CLM_ATTN_POLL 0
+#endif
+#if CLM_ATTN_POLL
+#define MBAR_WAIT_HOT mbar_wait_poll
+#else
+#define MBAR_WAIT_HOT mbar_wait
+#endif
 #ifndef CLM_ATTN_SPLIT_POLY
 #define CLM_ATTN_SPLIT_POLY 0  // split kernel: of every 4 exponentials, how many run on the FMA pipe (0..4)
 #endif
@@ -1236,7 +1245,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
         const uint32_t par = n & 1;
         const uint32_t q_addr = smem_u32(smem + st * p.stage_bytes);
         const uint32_t k_addr = q_addr + kv_bytes, v_addr = k_addr + kv_bytes;
-        if (alias && n >= 1) mbar_wait(&slot_free[b], (n - 1) & 1);  // O(t-2) has left the region
+        if (alias && n >= 1) MBAR_WAIT_HOT(&slot_free[b], (n - 1) & 1);  // O(t-2) has left the region
         mbar_wait(&stage_full[st], ph);
         tc_fence_after();
         TRACE(t, 0);
@@ -1248,7 +1257,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
           umma_commit(&s_full[b]);
         }
         __syncwarp();
-        mbar_wait(&p_half[b], par);
+        MBAR_WAIT_HOT(&p_half[b], par);
         tc_fence_after();
         if (lane == 0) {
 #pragma unroll
@@ -1256,7 +1265,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
             umma_bf16_ts(obase, sbase + ks * 8, umma_desc_sw128_mn(v_addr + ks * 2048), idesc_pv, ks != 0 ? 1u : 0u);
         }
         __syncwarp();
-        mbar_wait(&p_full[b], par);
+        MBAR_WAIT_HOT(&p_full[b], par);
         tc_fence_after();
         TRACE(t, 1);
         if (lane == 0) {
@@ -1342,7 +1351,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
       const int buf = n & 1;
       const bool warp_live = mt * 128 + q * 32 < T;
       TRACE(t, 0);
-      mbar_wait(&s_full[g], par);
+      MBAR_WAIT_HOT(&s_full[g], par);
       tc_fence_after();
       TRACE(t, 1);
       uint32_t v0[32], v1[32];
@@ -1430,7 +1439,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
       bool pro_done = !(xt && have_next);
       if (!pro_done) pro_done = prologue(n_mt, n_li, buf ^ 1, false);
 
-      mbar_wait(&o_full[g], par);
+      MBAR_WAIT_HOT(&o_full[g], par);
       tc_fence_after();
       TRACE(t, 5);
       sum += *other_sum;  // published before the partner's p_full arrive, which o_full transitively follows

@@ -140,6 +140,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Polling wait: mbarrier.test_wait never suspends the thread, so a completed phase is seen one probe (~150
+// clocks) after the arrive; try_wait may park the thread for a system-dependent time.  For the hand-offs on a
+// kernel's critical path; costs a few issue slots per probe.
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("clm: mbarrier poll timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
 // ---- TMA ------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");

@@ -18,6 +18,9 @@ WANT = [
     ("launch__shared_mem_per_block_dynamic", "dynamic smem/block"),
     ("sm__cycles_elapsed.max", "sm cycles elapsed"),
     ("smsp__cycles_active.avg", "smsp cycles active"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU) pipe % of peak (of active cycles)"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("sm__inst_executed.avg.per_cycle_active", "warp instructions per cycle per SM"),
 ]
 
 def main():

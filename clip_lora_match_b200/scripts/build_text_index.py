@@ -3,9 +3,9 @@
 Same inputs and the same on-disk product: a CSV with `text` and `image_path` columns goes in,
 `torch.save({"embeddings": (N,d) fp32 unit rows, "image_path": [...], "text": [...]})` comes out
 (reference :64-75), readable by both the reference's and this repo's TextSearchIndex.  The
-reference's N-iteration batch-1 loop (:57-59) becomes batched clm_encode_text calls; under
-torch.distributed each rank encodes a contiguous slice (data parallel, no collective on the
-data path) and rank 0 concatenates.
+reference's N-iteration batch-1 loop (:57-59) becomes batched clm_encode_text calls.  This script is single
+process, like the reference's; the data-parallel builder (one rank per GPU, a shard directory, no collective
+on the data path) is scripts/build_image_index.py.
 """
 from __future__ import annotations
 

@@ -58,6 +58,7 @@ class FinderService:
         self.crop_fn = crop_fn
         self.on_item = on_item
         self._next_id = 1
+        self._writer = None
 
     # ---- index update ------------------------------------------------------------------------
     def _is_directory_index(self) -> bool:
@@ -67,8 +68,12 @@ class FinderService:
     def _append(self, emb: torch.Tensor, image_path: str, text: str) -> None:
         p = Path(self.config.index_path)
         if self._is_directory_index():
-            IS.ShardedIndexWriter(p, emb.shape[-1]).append(emb, [image_path], [text])   # O(new rows)
-            IS.write_manifest(p)
+            # one writer per service (its constructor scans the directory once) and an incremental manifest
+            # update: a report costs O(new rows), not a rescan of every earlier report's sidecar
+            if self._writer is None or self._writer.dir != p or self._writer.dim != emb.shape[-1]:
+                self._writer = IS.ShardedIndexWriter(p, emb.shape[-1])
+            self._writer.append(emb, [image_path], [text])
+            IS.append_to_manifest(p, self._writer.last_shard, self._writer.dim)
             return
         # one-file index: the reference's load -> cat -> save (:74-102,172-185), plural keys
         if p.exists():

@@ -80,7 +80,15 @@ class ShardedIndexWriter:
             raise ValueError(f"metadata length mismatch: {n} rows, {len(image_paths)} image paths, {len(texts)} texts")
         if self.renormalize and n:
             e = _normalize_cpu(e)
-        name = f"shard-{self.order_major:03d}-{self._seq:06d}"
+        # claim the sequence number with an exclusive create, so two producers that share an order_major (two
+        # finder processes appending reports) can never write the same shard name
+        while True:
+            name = f"shard-{self.order_major:03d}-{self._seq:06d}"
+            try:
+                os.close(os.open(self.dir / (name + ".claim"), os.O_CREAT | os.O_EXCL | os.O_WRONLY))
+                break
+            except FileExistsError:
+                self._seq += 1
         path = self.dir / (name + ".pt")
         _atomic_write(path, lambda p: torch.save({"embeddings": e.contiguous(), "image_paths": image_paths,
                                                   "texts": texts}, p))
@@ -88,6 +96,7 @@ class ShardedIndexWriter:
         _atomic_write(self.dir / (name + ".json"),
                       lambda p: p.write_text(json.dumps({"dim": self.dim, **info.to_json()})))
         self._seq += 1
+        self.last_shard = info
         return path
 
 
@@ -104,6 +113,25 @@ def scan_shards(directory: Union[str, Path]) -> List[ShardInfo]:
             out.append(ShardInfo(j["file"], int(j["rows"]), (int(j["order"][0]), int(j["order"][1]))))
     out.sort(key=lambda s: s.order)
     return out
+
+
+def append_to_manifest(directory: Union[str, Path], info: "ShardInfo", dim: int) -> dict:
+    """Add ONE new shard to manifest.json without re-reading every sidecar (the finder appends a shard per
+    report: rebuilding the manifest each time would be O(reports^2) small-file reads).  Falls back to a full
+    rebuild when the manifest is missing, unreadable, of another width, or does not end before the new shard."""
+    d = Path(directory)
+    try:
+        man = json.loads((d / "manifest.json").read_text())
+        last = tuple(man["shards"][-1]["order"]) if man["shards"] else (-1, -1)
+        if man.get("format") != FORMAT or int(man.get("dim", 0)) not in (0, int(dim)) or last >= tuple(info.order):
+            raise ValueError("rebuild")
+    except (OSError, ValueError, KeyError, IndexError, TypeError):
+        return write_manifest(d)
+    man["dim"] = int(dim)
+    man["shards"].append(info.to_json())
+    man["rows"] = int(man["rows"]) + int(info.rows)
+    _atomic_write(d / "manifest.json", lambda p: p.write_text(json.dumps(man, indent=1)))
+    return man
 
 
 def write_manifest(directory: Union[str, Path]) -> dict:

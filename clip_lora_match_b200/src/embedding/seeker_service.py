@@ -74,8 +74,30 @@ class SeekerService:
             p = Path(config.index_path)
             index = (TextSearchIndex.from_directory(p, device=device, distributed=distributed) if p.is_dir()
                      else TextSearchIndex(p, device=device, distributed=distributed))
-        self.index = index          # resident: NOT reloaded per query (reference :183 does)
+        self.index = index          # resident: NOT reloaded per query (reference :183 does) ...
+        self._stamp = self._index_stamp()  # ... but refreshed when the file / manifest on disk has changed
         self.crop_fn = crop_fn
+
+    def _index_stamp(self):
+        """(mtime_ns, size) of the index file, or of manifest.json for a shard directory; None without a config."""
+        if self.config is None:
+            return None
+        p = Path(self.config.index_path)
+        f = p / "manifest.json" if p.is_dir() else p
+        try:
+            st = f.stat()
+            return (st.st_mtime_ns, st.st_size)
+        except OSError:
+            return None
+
+    def refresh_if_stale(self) -> bool:
+        """Reload the resident index if the finder side has published new rows since it was loaded (one stat()
+        per query instead of the reference's torch.load per query, seeker_service.py:183)."""
+        stamp = self._index_stamp()
+        if stamp is None or stamp == self._stamp:
+            return False
+        self.reload_index()
+        return True
 
     def reload_index(self) -> None:
         """Explicit refresh after the finder side appended items (replaces the per-query reload)."""
@@ -84,6 +106,7 @@ class SeekerService:
         p = Path(self.config.index_path)
         self.index = (TextSearchIndex.from_directory(p, device=self.device, distributed=self.index.distributed)
                       if p.is_dir() else TextSearchIndex(p, device=self.device, distributed=self.index.distributed))
+        self._stamp = self._index_stamp()
 
     def _build_query_embedding(self, query_text: Optional[str], query_image_path: Optional[Path],
                                w_text: float = 0.5, w_image: float = 0.5) -> torch.Tensor:
@@ -112,6 +135,7 @@ class SeekerService:
             if not img_path.exists():
                 raise FileNotFoundError(f"Query image not found: {img_path}")
         query_emb = self._build_query_embedding(query_text=query_text, query_image_path=img_path)
+        self.refresh_if_stale()  # items the finder reported since the index was loaded (reference: reload per query)
         return self.index.search_with_embedding(query_emb, top_k=top_k)
 
     def search_batch(self, text_embs: Optional[torch.Tensor], image_embs: Optional[torch.Tensor],

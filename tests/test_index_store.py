@@ -234,3 +234,29 @@ def test_finder_service_report_item_appends_like_the_reference(tmp_path):
         assert paths == ["data/reported/images/tas-pink.jpg"] * 2 and texts == seen
         with pytest.raises(FileNotFoundError):
             svc.report_item(root / "incoming" / "missing.png", "x")
+
+
+def test_two_writers_with_the_same_order_major_never_collide_and_manifest_appends_incrementally(tmp_path):
+    """Two finder processes appending to one shard directory (same order_major) used to compute the same next
+    sequence number and os.replace one report's shard with the other's; the number is now claimed with an
+    exclusive create.  append_to_manifest adds one shard without re-reading the sidecars and must agree with a
+    full rebuild; it falls back to the rebuild when the manifest is missing or behind."""
+    d = tmp_path / "idx"
+    w1 = IS.ShardedIndexWriter(d, 4)
+    w2 = IS.ShardedIndexWriter(d, 4)          # constructed before w1 wrote anything: same starting number
+    rows = [torch.eye(4)[i:i + 1] for i in range(4)]
+    p1 = w1.append(rows[0], ["a.png"], ["a"])
+    man = IS.append_to_manifest(d, w1.last_shard, w1.dim)     # no manifest yet -> full rebuild
+    p2 = w2.append(rows[1], ["b.png"], ["b"])
+    man = IS.append_to_manifest(d, w2.last_shard, w2.dim)
+    p3 = w1.append(rows[2], ["c.png"], ["c"])
+    man = IS.append_to_manifest(d, w1.last_shard, w1.dim)
+    assert len({p1.name, p2.name, p3.name}) == 3
+    assert man["rows"] == 3 and man == IS.write_manifest(d)
+    emb, paths, texts = IS.load_rows(d, 0, 3)
+    assert sorted(paths) == ["a.png", "b.png", "c.png"] and emb.shape == (3, 4)
+    # a manifest that already lists a later shard (another process got ahead) -> rebuilt, not corrupted
+    p4 = w2.append(rows[3], ["d.png"], ["d"])
+    stale = w1.last_shard
+    man = IS.append_to_manifest(d, stale, 4)
+    assert man["rows"] == 4 and man == IS.write_manifest(d)

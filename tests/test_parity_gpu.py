@@ -563,6 +563,37 @@ def test_sharded_image_index_build_then_resident_seeker_search(cuda_device, tmp_
     assert res[0].index == top and res[0].image_path == f"img{top}.png" and res[0].text == f"item {top}"
 
 
+def test_seeker_sees_rows_the_finder_reported_after_it_loaded_the_index(cuda_device, tmp_path):
+    """The reference reloads the index file on every query (seeker_service.py:183); the resident SeekerService
+    instead stats the file / manifest per query and reloads when the finder side has published new rows."""
+    from clip_lora_match_b200.src.embedding import index_store as IS
+    from clip_lora_match_b200.src.embedding.finder_service import FinderConfig, FinderService
+    from clip_lora_match_b200.src.embedding.seeker_service import SeekerConfig, SeekerService
+
+    d = tmp_path / "data" / "index" / "sharded"
+    rows = O.synth_unit_rows(12, 64, 3)
+    w = IS.ShardedIndexWriter(d, 64)
+    w.append(rows[:10], [f"img{j}.png" for j in range(10)], [f"item {j}" for j in range(10)])
+    IS.write_manifest(d)
+    cfg = SeekerConfig(root_dir=tmp_path, clip_config_path=tmp_path / "none.yaml", lora_dir=tmp_path / "none",
+                       index_path=d)
+    svc = SeekerService(cfg, model=object(), processor=None, device=cuda_device)
+    svc._build_query_embedding = lambda query_text, query_image_path: rows[11]   # the query IS the row reported below
+    before = svc.search_items(query_text="x", top_k=3)
+    assert svc.index.num_items == 10 and all(r.index < 10 for r in before)
+    assert svc.refresh_if_stale() is False
+    (tmp_path / "in.jpg").write_bytes(b"jpeg")
+    texts = iter([rows[10], rows[11]])
+    fcfg = FinderConfig(root_dir=tmp_path, clip_config_path=tmp_path / "none.yaml", lora_dir=tmp_path / "none",
+                        index_path=d, upload_dir=tmp_path / "data" / "reported")
+    finder = FinderService(fcfg, encode_fn=lambda t: next(texts))
+    finder.report_item(tmp_path / "in.jpg", "first")
+    finder.report_item(tmp_path / "in.jpg", "second")
+    after = svc.search_items(query_text="x", top_k=3)
+    assert svc.index.num_items == 12
+    assert after[0].index == 11 and after[0].text == "second" and abs(after[0].score - 1.0) < 1e-5
+
+
 def test_gpu_preprocessing_is_bit_exact_with_the_pillow_oracle(cuda_device):
     """clm_preprocess_images vs oracle/pil_resample.c (itself pinned bit-exact against Pillow): the
     uint8 stage and the float stage must agree to the bit, for a ragged batch of image sizes

@@ -203,9 +203,11 @@ def search_topk(q_f32: torch.Tensor, q_bf16: torch.Tensor, index_bf16: torch.Ten
     # unit's full list proves kc rows above its minimum, which bounds t_k only if kc >= k.  It is seeded from
     # a sample: scores of the queries against the first SAMPLE_ROWS index rows (plain tcgen05 GEMM, same bf16
     # operands as the scan) -> exact k-th largest per query.
+    # (k > kc: the lists cannot prove a bound themselves, the seed and the histogram still can; without them a
+    # top-100 scan of a 1.25M-row shard took 44.6 ms instead of ~10)
     thr = hist = hist_base = None
-    if kc >= k:
-        if n >= 4 * SAMPLE_ROWS:
+    if kc >= k or (n >= 4 * SAMPLE_ROWS and k <= SAMPLE_ROWS):
+        if n >= 4 * SAMPLE_ROWS and k <= SAMPLE_ROWS:
             sample_scores = gemm_epi(q_bf16, index_bf16[:SAMPLE_ROWS], out_dtype=torch.float32)
             thr = torch.empty((nq,), dtype=torch.float32, device=dev)
             check(lib.clm_kth_largest(ptr(sample_scores), nq, SAMPLE_ROWS, k, 1e-5, ptr(thr), cur_stream()),

@@ -238,7 +238,8 @@ int clm_search_num_splits(int num_queries, int num_rows);
  * margin: bf16 scores only NOMINATE rows for the exact fp32 re-score of clm_topk_merge.  With |bf16 score -
  * fp32 score| <= eps for every row (unit-norm rows rounded to bf16: eps <= 2^-8), every row of the fp32
  * top-k has a bf16 score >= t_k - 2 eps, t_k the k-th best bf16 score; since L <= t_k, margin = 2 eps keeps
- * all of them -- unless a list overflows, which clm_topk_merge detects.  thr_io must be NULL when kb > kc.
+ * all of them -- unless a list overflows, which clm_topk_merge detects.  kb > kc is allowed: such lists never
+ * publish their own minimum, the bound then comes from the caller's seed and the histogram only.
  * hist_base (fp32 [nq]) / hist (uint32 [nq, 32], zeroed by the caller, 16-byte aligned), both optional: a
  * per-query histogram of the kept candidates' scores above hist_base[q] in steps of 1/256, shared by all work
  * units: kb candidates counted at or above a bin edge prove t_kb >= that edge over ALL rows seen so far, which

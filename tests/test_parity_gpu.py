@@ -473,6 +473,23 @@ def test_search_exact_under_adversarial_near_ties(cuda_device, k, contiguous):
         assert 0 < hits < 40
 
 
+def test_search_top_k_beyond_the_list_capacity_keeps_a_shared_bound(cuda_device):
+    """k > 64 (the capacity of one (query, split) candidate list) on an index large enough for the sampled seed:
+    the scan's bound comes from the seed and the shared histogram only; ids and scores must still equal
+    torch.topk of the fp32 scores."""
+    from clip_lora_match_b200.src.embedding.search import TextSearchIndex
+
+    e = O.synth_unit_rows(60000, 256, 14)
+    q = O.synth_unit_rows(130, 256, 15)
+    idx = TextSearchIndex(embeddings=e, device=cuda_device, verbose=False)
+    sims = q @ e.T
+    for k in (65, 100, 300):
+        s, i = idx.search_batch(q, top_k=k)
+        ref_s, ref_i = torch.topk(sims, k, dim=-1)
+        assert torch.allclose(s.cpu(), ref_s, atol=2e-6)
+        assert O.ids_match_with_ties(ref_s, ref_i, i.cpu(), sims)
+
+
 def test_search_top_k_is_unbounded_like_the_reference(cuda_device):
     """search_with_embedding(q, top_k) = torch.topk(sims, min(top_k, N)) for ANY top_k (reference
     src/embedding/search.py:98-99): 0, 1, 64, 65, 100, 1000, beyond N."""

@@ -87,6 +87,7 @@ SIGNATURES = {
     "clm_search_num_splits": (_I, [_I, _I]),
     "clm_search_topk": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P]),
     "clm_kth_largest": (_I, [_P, _I, _I, _I, _F, _P, _P]),
+    "clm_kth_lower_bound": (_I, [_P, _I, _I, _I, _F, _P, _P]),
     "clm_topk_merge": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _I, _I, C.c_int64, _P, _P, _P, _P]),
     "clm_topk_gather_chunk_bytes": (C.c_size_t, [_I, _I]),
     "clm_topk_merge_gathered": (_I, [_P, _I, _I, _I, _P, _P, _P]),

@@ -729,6 +729,40 @@ kth_largest_kernel(const float* __restrict__ x, int n, int kth, float guard, flo
   if (threadIdx.x == 0) out[blockIdx.x] = v - guard;
 }
 
+// A LOWER BOUND of the kth largest value of each row, cheap enough for a 16 K-row sample: the row is cut into
+// kSeedGroups strided groups (element i belongs to group i mod kSeedGroups), each thread keeps the maxima of its
+// groups while it streams the row once (coalesced), and the kth largest of the kSeedGroups group maxima is
+// selected exactly.  The kth largest group maximum has kth distinct elements at or above it, so it never
+// exceeds the row's kth largest value; for kth << kSeedGroups it is close to it (the top kth elements fall into
+// ~kth distinct groups: kth = 50 of 1024 groups -> it is about the 51st largest element).  The exact radix
+// select over 16 K clustered scores costs 0.52 ms for 4096 queries (thousands of same-bin shared-memory atomics),
+// this one 0.06 ms.
+constexpr int kSeedGroups = 1024;
+__global__ void __launch_bounds__(kSelThreads)
+kth_lower_bound_kernel(const float* __restrict__ x, int n, int kth, float guard, float* __restrict__ out) {
+  __shared__ float gmax[kSeedGroups];
+  __shared__ int hist[256];
+  __shared__ uint32_t ctl[2];
+  constexpr int kPer = kSeedGroups / kSelThreads;  // groups per thread: thread t owns groups t + kSelThreads * j
+  const float* row = x + static_cast<size_t>(blockIdx.x) * n;
+  float m[kPer];
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) m[j] = -INFINITY;
+  // element i = t + kSelThreads * c belongs to group i mod kSeedGroups = t + kSelThreads * (c mod kPer)
+  for (int c0 = 0; c0 * kSelThreads < n; c0 += kPer) {
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = (c0 + j) * kSelThreads + static_cast<int>(threadIdx.x);
+      if (i < n) m[j] = fmaxf(m[j], __ldg(row + i));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) gmax[threadIdx.x + kSelThreads * j] = m[j];
+  __syncthreads();
+  const float v = block_kth_largest(gmax, kSeedGroups, kth, hist, ctl);
+  if (threadIdx.x == 0) out[blockIdx.x] = v - guard;
+}
+
 // Exact top-k of ONE row of n fp32 scores (the reference's torch.topk(sims, k), src/embedding/search.py:99),
 // for the cases the fused scan hands back (an overflowed candidate list, k larger than the lists hold).
 // One block: radix select of the k-th largest value tau, gather of everything above tau plus enough entries
@@ -931,6 +965,16 @@ extern "C" int clm_cosine_gemv(const float* q_f32, const float* index_f32, int n
   ProfScope prof(CLM_K_SEARCH, 2.0 * n * dim, 4.0 * dim * (static_cast<double>(n) + 1) + 4.0 * n,
                  static_cast<cudaStream_t>(stream));
   gemv_kernel<<<(n + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(q_f32, index_f32, n, dim, out);
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}
+
+extern "C" int clm_kth_lower_bound(const float* x, int rows, int n, int kth, float guard, float* out, void* stream) {
+  CLM_REQUIRE(x && out && rows > 0 && n >= kSeedGroups && kth >= 1 && kth <= kSeedGroups / 4,
+              "clm_kth_lower_bound: bad argument (rows=%d n=%d kth=%d; n >= %d, kth <= %d)", rows, n, kth, kSeedGroups,
+              kSeedGroups / 4);
+  ProfScope prof(CLM_K_MERGE, 0.0, 4.0 * rows * n, static_cast<cudaStream_t>(stream));
+  kth_lower_bound_kernel<<<rows, kSelThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, n, kth, guard, out);
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
 }

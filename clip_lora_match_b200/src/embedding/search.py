@@ -67,6 +67,20 @@ def gather_shard_topk(scores: Optional[torch.Tensor], ids: Optional[torch.Tensor
     return out
 
 
+def gather_overflow_counts(overflow: Optional[torch.Tensor], device: torch.device, group=None) -> List[int]:
+    """How many queries of the last local scan every rank has to redo exactly (kernels.search_topk's overflow
+    flags; None = none).  A redo on ANY rank repeats the exchange on ALL of them, so every rank has to see the same
+    numbers: a 4-byte all_gather_into_tensor that is enqueued without a host round trip, then ONE host read."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    cnt = (overflow.sum(dtype=torch.int32) if overflow is not None
+           else torch.zeros((), dtype=torch.int32, device=device)).reshape(1)
+    cnts = torch.empty((world,), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(cnts, cnt, group=group)
+    return cnts.tolist()
+
+
 def unpack_gathered_topk(gathered: torch.Tensor, world: int, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """[Q, world, k] scores / ids views of a gathered buffer (host-side checks and tests; the GPU merge reads
     the buffer in place)."""
@@ -216,13 +230,26 @@ class TextSearchIndex:
         qn, qb = K.l2norm(q, want_bf16=True)  # reference :93
         k_local = min(k, self.local_rows)
         s = i = None
-        if k_local > 0:
+        if not sharded:
             s, i = K.search_topk(qn, qb, self.embeddings_bf16, self.embeddings, k_local,
                                  id_offset=self.row_offset, stats=self.last_search_stats)
-        if not sharded:
             return s, i
-        gathered = gather_shard_topk(s, i, nq, k, self.device)
-        return K.topk_merge_gathered(gathered, self.world, nq, k)
+        # sharded: the exchange and the cross-shard merge are enqueued BEFORE the host reads the scan's overflow
+        # flags, so the GPU does not idle through that round trip; a flagged query (rare: a candidate list that
+        # filled up inside the exactness window) is redone exactly and the exchange repeated
+        overflow = None
+        if k_local > 0:
+            s, i, overflow = K.search_topk(qn, qb, self.embeddings_bf16, self.embeddings, k_local,
+                                           id_offset=self.row_offset, stats=self.last_search_stats,
+                                           defer_overflow=True)
+        out = K.topk_merge_gathered(gather_shard_topk(s, i, nq, k, self.device), self.world, nq, k)
+        counts = gather_overflow_counts(overflow, self.device)  # the ONE host synchronisation of the call
+        self.last_search_stats["overflow_queries"] = counts[self.rank]
+        if any(counts):
+            if counts[self.rank]:
+                K.resolve_overflow(overflow, qn, self.embeddings, k_local, self.row_offset, s, i)
+            out = K.topk_merge_gathered(gather_shard_topk(s, i, nq, k, self.device), self.world, nq, k)
+        return out
 
     # ---- reference API -------------------------------------------------------------------
     def search_with_embedding(self, query_emb: torch.Tensor, top_k: int = 5) -> List[SearchResult]:

@@ -34,6 +34,13 @@ def _worker(rank, world, port, n, d, nq, k, ret):
             i = i + lo
         else:
             s = i = None
+        from clip_lora_match_b200.src.embedding.search import gather_overflow_counts
+
+        # the per-rank "queries to redo exactly" counts reach every rank identically (rank 1 pretends it has two)
+        flags = torch.zeros(nq, dtype=torch.int32)
+        if rank == 1:
+            flags[:2] = 1
+        assert gather_overflow_counts(flags if rank else None, torch.device("cpu")) == [0, 2][:world]
         buf = gather_shard_topk(s, i, nq, k, torch.device("cpu"))  # ONE all_gather_into_tensor of packed chunks
         assert buf.dtype == torch.uint8 and buf.numel() == world * (((nq * k + 1) // 2 * 2) * 12)
         gs, gi = unpack_gathered_topk(buf, world, nq, k)

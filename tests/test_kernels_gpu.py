@@ -424,6 +424,32 @@ def test_search_id_offset_and_merge(cuda_device):
     _check_topk("search_sharded_merge", s, i, q, e, k)
 
 
+def test_kth_lower_bound_is_a_valid_and_tight_seed(cuda_device):
+    """clm_kth_lower_bound (k-th largest of 1024 strided-group maxima) never exceeds the exact k-th largest of
+    the row -- that is what makes it a valid seed of the scan's bound -- and for k << 1024 it is at least the
+    (2k + 8)-th largest (tight enough to be useful); ties, -inf padding, ragged row lengths."""
+    from clip_lora_match_b200 import _lib
+    from clip_lora_match_b200._lib import check, cur_stream, ptr
+
+    lib = _lib.load()
+    g = _gen(71)
+    for rows, n in ((33, 16384), (7, 5000), (5, 1024), (3, 40000)):
+        x = torch.randn((rows, n), generator=g) * 0.04
+        x[0, ::5] = x[0, 2]                      # ties
+        x[1, 300:] = float("-inf")               # fewer than 1024 finite values
+        xd = x.to(cuda_device)
+        srt = torch.sort(x, dim=-1, descending=True).values
+        for kth in (1, 10, 50, 256):
+            out = torch.empty(rows, dtype=torch.float32, device=cuda_device)
+            check(lib.clm_kth_lower_bound(ptr(xd), rows, n, kth, 0.0, ptr(out), cur_stream()), "clm_kth_lower_bound")
+            o = out.cpu()
+            assert (o <= srt[:, kth - 1]).all(), f"n={n} kth={kth}: not a lower bound"
+            loose = srt[:, min(2 * kth + 8, n) - 1]
+            assert (o[2:] >= loose[2:]).all(), f"n={n} kth={kth}: bound too loose"
+    with pytest.raises(RuntimeError):
+        check(lib.clm_kth_lower_bound(ptr(xd), 3, 40000, 300, 0.0, ptr(out), cur_stream()), "clm_kth_lower_bound")
+
+
 def test_kth_largest_and_topk_row_match_torch(cuda_device):
     """The two selection primitives against torch on adversarial value sets: heavy ties, negatives, -inf padding."""
     from clip_lora_match_b200 import _lib

@@ -9,7 +9,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=1_250_000); ap.add_argument("--q", type=int, default=4096)
     ap.add_argument("--d", type=int, default=768); ap.add_argument("--k", type=int, nargs="+", default=[10, 50])
-    ap.add_argument("--list-cap", type=int, default=0); ap.add_argument("--margin", type=float, default=-1.0)
+    ap.add_argument("--list-cap", type=int, default=0); ap.add_argument("--margin", type=float, default=-1.0); ap.add_argument("--sample-rows", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda")
     g = torch.Generator(device=dev).manual_seed(4)
@@ -21,6 +21,7 @@ def main():
     for k in a.k:
         kw = {"list_cap": a.list_cap} if a.list_cap else {}
         if a.margin >= 0: kw["margin"] = a.margin
+        if a.sample_rows: kw["sample_rows"] = a.sample_rows
         st = {}
         for _ in range(3): K.search_topk(q, qb, eb, e, k, stats=st, **kw)
         torch.cuda.synchronize()

@@ -1,7 +1,7 @@
 """Multi-GPU check of the row-sharded search (run under torchrun, one rank per GPU): every rank builds the same
 random unit-norm index, keeps its shard, and search_batch's merged top-k must equal torch.topk of the fp32 scores
 of the WHOLE index (computed by each rank on its own GPU as the checker) up to 1e-4 ties; also prints ms per batch.
-Usage: torchrun --nproc-per-node N tools/dist_search_check.py [--n 2000000] [--q 1024] [--k 10 50]"""
+Usage: torchrun --nproc-per-node N tools/dist_search_check.py [--rows 2000000] [--queries 1024] [--topk 10 50]"""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -9,8 +9,8 @@ import torch.distributed as dist
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=2_000_000); ap.add_argument("--q", type=int, default=1024)
-    ap.add_argument("--d", type=int, default=768); ap.add_argument("--k", type=int, nargs="+", default=[10, 50])
+    ap.add_argument("--rows", dest="n", type=int, default=2_000_000); ap.add_argument("--queries", dest="q", type=int, default=1024)
+    ap.add_argument("--dim", dest="d", type=int, default=768); ap.add_argument("--topk", dest="k", type=int, nargs="+", default=[10, 50])
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))

@@ -337,6 +337,27 @@ def test_attention_split_and_alternate_kernels(cuda_device, monkeypatch, mode, b
     _close(f"attention_split{mode}_{batch}x{tokens}x{heads}", out, ref, atol=1.5e-2, rtol=1e-2, qkv=qkv)
 
 
+@pytest.mark.parametrize("mode,batch,tokens,heads", [("1", 300, 257, 16), ("2", 411, 197, 12)])
+def test_attention_split_kernel_is_deterministic_with_many_items_per_cta(cuda_device, monkeypatch, mode, batch, tokens, heads):
+    """30+ items per CTA (stage ring, TMEM regions, mbarrier phases wrap many times; the four cooperative
+    extra-token warps and both MMA issuers run far ahead of / behind the softmax groups): the kernel has no atomics,
+    so five runs must agree bit for bit -- a hand-off race shows up as a difference -- and sampled items must match
+    the fp32 reference."""
+    monkeypatch.setenv("CLM_ATTN_SPLIT", mode)
+    D = heads * 64
+    qkv = _randn((batch * tokens, 3 * D), 43, 1.5).bfloat16()
+    qd = qkv.to(cuda_device)
+    outs = [K.attention(qd, batch, tokens, heads, False) for _ in range(5)]
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    pick = [0, 1, batch // 2, batch - 2, batch - 1]
+    sub = torch.cat([qkv[b * tokens:(b + 1) * tokens] for b in pick])
+    ref = _attn_ref(sub, len(pick), tokens, heads, False)
+    got = torch.cat([outs[0][b * tokens:(b + 1) * tokens] for b in pick]).float().cpu()
+    assert torch.allclose(got, ref, atol=1.5e-2, rtol=1e-2), float((got - ref).abs().max())
+
+
 @pytest.mark.parametrize("batch,tokens,heads", [(3, 257, 4), (3, 197, 4), (2, 200, 2), (2, 256, 2), (2, 145, 2)])
 def test_attention_key_blocks_with_late_maximum(cuda_device, batch, tokens, heads):
     """The key-blocked kernel exponentiates block 1 (keys 128..) relative to the block-0 maximum and rescales

@@ -77,6 +77,17 @@ SIGNATURES = {
                           _I, _P]),
     "clm_last_gemm_variant": (_I, []),
     "clm_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "clm_quickgelu_fwd": (_I, [_P, _P, C.c_longlong, _P]),
+    "clm_quickgelu_bwd": (_I, [_P, _P, _P, C.c_longlong, _P]),
+    "clm_layernorm_bwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _F, _I, _P, _I, _I, _P]),
+    "clm_transpose_to_bf16": (_I, [_P, _I, C.c_longlong, C.c_longlong, _I, _I, _P, C.c_longlong, C.c_longlong, _I,
+                                   _F, _P]),
+    "clm_cast_to_bf16": (_I, [_P, _P, C.c_longlong, _F, _P]),
+    "clm_attention_bwd_scratch_bytes": (C.c_size_t, [_I, _I, _I]),
+    "clm_attention_bwd": (_I, [_P, _P, _P, _P, C.c_size_t, _I, _I, _I, _I, _P]),
+    "clm_clip_loss_workspace_bytes": (C.c_size_t, [_I, _I]),
+    "clm_clip_loss": (_I, [_P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "clm_adamw_step": (_I, [_P, _P, _P, _P, _P, C.c_longlong, _P, _P, _F, _F, _F, _F, _F, _P]),
     "clm_tower_create": (_I, [C.POINTER(TowerConfig), C.POINTER(TowerWeights),
                               C.POINTER(LayerWeights), C.POINTER(_P)]),
     "clm_tower_destroy": (None, [_P]),

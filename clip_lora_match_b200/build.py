@@ -23,6 +23,7 @@ SOURCES = [
     "clm_attention.cu",
     "clm_search.cu",
     "clm_tower.cu",
+    "clm_train.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -219,6 +219,69 @@ int clm_encode_text_len(clm_tower* t, const int32_t* ids, int batch, int tokens,
                         int normalize, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * LoRA training step (reference scripts/train_lora.py:83-108,170-211)
+ *
+ * The forward of a training step is the same clm_layernorm / clm_gemm_epi / clm_attention sequence as the
+ * encoder, run layer by layer by the host mirror (models/lora_trainer.py) so that it can keep the activations;
+ * every GEMM-shaped piece of the backward (dgrad through the frozen weights with the LoRA term as a K extension,
+ * the LoRA projections, their weight gradients) is clm_gemm_epi on transposed operands.  The entry points below
+ * are the rest.  Only the LoRA factors receive gradients (models/lora_adapter.py:46-56: the base is frozen).
+ * ---------------------------------------------------------------------------------- */
+
+/* g = z * sigmoid(1.702 z) on a stored bf16 pre-activation (the training forward keeps z for the backward; the
+ * encoder fuses the activation into the fc1 epilogue instead), and dz = dg * d/dz quickgelu(z).  n % 8 == 0.
+ * transformers/activations.py QuickGELUActivation as reached from modeling_clip.py:344-350. */
+int clm_quickgelu_fwd(const void* z_bf16, void* g_bf16, long long n, void* stream);
+int clm_quickgelu_bwd(const void* dg_bf16, const void* z_bf16, void* dz_bf16, long long n, void* stream);
+
+/* Input gradient of nn.LayerNorm (gamma, beta frozen): x fp32 [rows, dim] is the saved LN input, dy the gradient
+ * of the LN output (bf16, or fp32 when dy_is_f32); dres fp32 [rows, dim] is the gradient of the residual stream:
+ * dres = (accumulate ? dres : 0) + dx, and dres_bf16 (optional) receives its bf16 copy -- the next dgrad GEMM's
+ * operand.  gather != 0: the pooled rows (modeling_clip.py:685-686 class token, :577-584 first EOS): item b
+ * reads dy row b and works on row b * tokens + (row_idx ? row_idx[b] : 0) of x / dres / dres_bf16. */
+int clm_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const float* gamma, float* dres,
+                      void* dres_bf16_or_null, int rows, int dim, float eps, int accumulate,
+                      const int32_t* row_idx_or_null, int tokens, int gather, void* stream);
+
+/* out[b][c][r] = bf16(scale * in[b][r][c]) for b < batch: in is bf16 or fp32 [rows, cols] (leading dim ld_in,
+ * batch stride in elements), out bf16 [cols, rows] (ld_out >= rows).  Operands of the weight-gradient GEMMs
+ * (dB = dy^T t, dA^T = x^T u contract over the token rows) and the bf16 [cols, in] copy of the LoRA masters. */
+int clm_transpose_to_bf16(const void* in, int in_is_f32, long long ld_in, long long batch_stride_in, int rows,
+                          int cols, void* out_bf16, long long ld_out, long long batch_stride_out, int batch,
+                          float scale, void* stream);
+/* out = bf16(scale * in), n % 4 == 0 */
+int clm_cast_to_bf16(const float* in, void* out_bf16, long long n, float scale, void* stream);
+
+/* Backward of clm_attention: qkv as in the forward, dout bf16 [batch*tokens, dim] -> dqkv bf16
+ * [batch*tokens, 3*dim] (dq | dk | dv).  P is recomputed from q and k (fp32 softmax, modeling_clip.py:261-279).
+ * scratch: clm_attention_bwd_scratch_bytes() of device memory (P and dS, transposed, between the two kernels).
+ * tokens <= 384.  Deterministic (no atomics). */
+size_t clm_attention_bwd_scratch_bytes(int batch, int tokens, int heads);
+int clm_attention_bwd(const void* qkv_bf16, const void* dout_bf16, void* dqkv_bf16, void* scratch,
+                      size_t scratch_bytes, int batch, int tokens, int heads, int causal, void* stream);
+
+/* Symmetric InfoNCE of scripts/train_lora.py:83-108 on UN-normalised features fp32 [n, dim]:
+ *   n_* = feat_* / ||feat_*||;  L = n_i n_t^T / temperature;  loss = (CE(L, arange) + CE(L^T, arange)) / 2.
+ * loss_out (device fp32 scalar) = loss * loss_scale (loss_scale = 1 / gradient_accumulation_steps, :186);
+ * dfeat_* fp32 [n, dim] (both or neither; optional bf16 copies) = d(loss * loss_scale) / d feat_*.  fp32 throughout. */
+size_t clm_clip_loss_workspace_bytes(int n, int dim);
+int clm_clip_loss(const float* feat_i, const float* feat_t, int n, int dim, float temperature, float loss_scale,
+                  float* loss_out, float* dfeat_i, float* dfeat_t, void* dfeat_i_bf16, void* dfeat_t_bf16,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* torch.nn.utils.clip_grad_norm_(max_grad_norm) + torch.optim.AdamW.step() over one flat fp32 buffer
+ * (scripts/train_lora.py:141,190-193).  The effective gradient of entry i is grads[i] * grad_mult[i]; entries
+ * with grad_mult == 0 (padding columns / off-diagonal blocks of the fused LoRA layouts) are never touched.
+ * hyper_dev (device fp32[4]) = {lr, 1/(1-beta1^t), 1/sqrt(1-beta2^t), -}: device-resident so that a captured
+ * CUDA graph of the step can be replayed with a new learning rate.  max_grad_norm <= 0 disables clipping.
+ * sumsq_scratch: device fp32[CLM_ADAMW_SCRATCH_FLOATS]; element 0 receives the squared global gradient norm (before
+ * clipping), the rest holds per-block partial sums (summed in a fixed order: the update is reproducible bit for bit). */
+#define CLM_ADAMW_SCRATCH_FLOATS 1185
+int clm_adamw_step(float* params, const float* grads, const float* grad_mult, float* exp_avg, float* exp_avg_sq,
+                   long long n, const float* hyper_dev, float* sumsq_scratch, float max_grad_norm, float beta1,
+                   float beta2, float eps, float weight_decay, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Search: similarity GEMM with fused per-tile top-k, merge, exact fp32 re-score
  * ---------------------------------------------------------------------------------- */
 

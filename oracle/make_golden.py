@@ -237,14 +237,62 @@ def fusion_golden():
     print(f"fusion golden: {both.shape} fused rows, error message {raised!r}")
 
 
+def train_golden():
+    """Run the reference's OWN compute_clip_contrastive_loss (scripts/train_lora.py:83-108) with autograd on
+    seeded features, and its OWN lr_lambda closure (train_lora.py:148-151; the nested function is compiled from
+    the reference's source, unmodified, with total_steps / warmup_steps bound as in train()).  `datasets.dataset`
+    (the CSV / PIL loader the script imports at module level) is stubbed: it needs the repo's working directory
+    layout and is not part of the arithmetic under test."""
+    import ast
+    import types
+
+    stub = types.ModuleType("datasets.dataset")
+    stub.ClipPairDataset = object
+    pkg = types.ModuleType("datasets")
+    pkg.dataset = stub
+    sys.modules["datasets"], sys.modules["datasets.dataset"] = pkg, stub
+    import scripts.train_lora as ref_tl
+
+    out = {}
+    cases = [(8, 512, 0.07), (32, 512, 0.07), (5, 64, 0.07), (16, 768, 0.2), (64, 128, 0.05)]
+    for ci, (n, d, temp) in enumerate(cases):
+        g = torch.Generator().manual_seed(100 + ci)
+        fi = (torch.randn((n, d), generator=g) * 3.0).requires_grad_(True)
+        # correlated text features so that the loss is not just log(n)
+        ft = (0.1 * fi.detach() + torch.randn((n, d), generator=g) * 2.0).requires_grad_(True)
+        loss = ref_tl.compute_clip_contrastive_loss(fi, ft, temp)  # reference code
+        loss.backward()
+        out[f"c{ci}_shape"] = np.array([n, d], dtype=np.int64)
+        out[f"c{ci}_temp"] = np.array(temp, dtype=np.float64)
+        out[f"c{ci}_fi"], out[f"c{ci}_ft"] = fi.detach().numpy(), ft.detach().numpy()
+        out[f"c{ci}_loss"] = np.array(loss.item(), dtype=np.float64)
+        out[f"c{ci}_dfi"], out[f"c{ci}_dft"] = fi.grad.numpy(), ft.grad.numpy()
+    out["n_cases"] = np.array(len(cases))
+    # the schedule closure, from the reference's source
+    src = (REF / "scripts" / "train_lora.py").read_text()
+    fn = [n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "lr_lambda"][0]
+    sched = []
+    for total, ratio in [(100, 0.1), (7, 0.1), (50, 0.0), (20, 0.5)]:
+        env = {"total_steps": total, "warmup_steps": int(total * ratio)}  # train_lora.py:144-146
+        exec(compile(ast.Module(body=[fn], type_ignores=[]), "train_lora.py", "exec"), env)
+        sched.append([total, env["warmup_steps"]] + [env["lr_lambda"](s) for s in range(total + 2)] + [0.0] * (100 - total))
+    out["sched"] = np.array(sched, dtype=np.float64)
+    np.savez_compressed(GOLD / "train_golden.npz", **out)
+    print(f"train golden: {len(cases)} loss cases, losses {[float(out[f'c{i}_loss']) for i in range(len(cases))]}")
+
+
 def main():
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     ref_cm, ref_la, ref_search, ref_sim = import_reference()
+    if "--train-only" in sys.argv:
+        train_golden()
+        return
     if "--fusion-only" not in sys.argv:
         search_golden(ref_search, ref_sim)
         encoder_golden(ref_cm, ref_la)
     fusion_golden()
+    train_golden()
 
 
 if __name__ == "__main__":

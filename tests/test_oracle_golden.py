@@ -135,3 +135,26 @@ def test_fusion_oracle_matches_reference_seeker_service():
     assert torch.equal(torch.stack([O.fuse_query(None, t) for t in img]), torch.from_numpy(g["only_image"]))
     with pytest.raises(ValueError, match=str(g["error"])):
         O.fuse_query(None, None)
+
+
+# ------------------------------------------------------------------------------------------
+# training step: the oracle's loss and schedule against the reference's own functions
+# ------------------------------------------------------------------------------------------
+def test_train_oracle_loss_and_schedule_match_reference():
+    import torch
+
+    from oracle import train_oracle as T
+
+    g = np.load(os.path.join(GOLD, "train_golden.npz"))
+    for ci in range(int(g["n_cases"])):
+        fi = torch.tensor(g[f"c{ci}_fi"], requires_grad=True)
+        ft = torch.tensor(g[f"c{ci}_ft"], requires_grad=True)
+        loss = T.contrastive_loss(fi, ft, float(g[f"c{ci}_temp"]))
+        loss.backward()
+        assert abs(loss.item() - float(g[f"c{ci}_loss"])) <= 1e-6 * max(1.0, abs(float(g[f"c{ci}_loss"])))
+        assert np.allclose(fi.grad.numpy(), g[f"c{ci}_dfi"], rtol=1e-5, atol=1e-8)
+        assert np.allclose(ft.grad.numpy(), g[f"c{ci}_dft"], rtol=1e-5, atol=1e-8)
+    for row in g["sched"]:
+        total, warm = int(row[0]), int(row[1])
+        for s in range(total + 2):
+            assert T.lr_lambda(s, total, warm) == row[2 + s]

@@ -32,6 +32,7 @@ ARCH = "openai/clip-vit-base-patch16"
 LORA_R, LORA_ALPHA, LORA_TARGETS = 16, 32, ["q_proj", "v_proj"]
 BATCH = 1024
 L14_ARCH, L14_BATCH = "openai/clip-vit-large-patch14", 512
+TRAIN_ARCH, TRAIN_TARGETS, TRAIN_BATCHES = "openai/clip-vit-base-patch32", ["q_proj", "k_proj", "v_proj", "out_proj"], (8, 256)
 INDEX_ROWS, INDEX_DIM, QUERY_BATCH, TOP_K = 10_000_000, 768, 4096, 10
 
 
@@ -148,6 +149,30 @@ def cpu_encode_rate(target_seconds=12.0, per_step=8):
     return n / dt, cores, f"{n} image+caption pairs of configs[1] (ViT-B/16+LoRA r=16, fp32, batch {per_step}) in {dt:.1f}s"
 
 
+def cpu_train_rate(steps=2, batch=8):
+    """The training oracle (transformers fp32 CLIPModel + LoRA wrappers, torch autograd, torch AdamW: the reference's
+    step loop, scripts/train_lora.py:172-193) on all host threads: pairs per second over `steps` steps of the
+    reference's own batch of 8."""
+    import torch
+
+    from oracle import clip_oracle as O
+    from oracle import train_oracle as T
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = O.build_model(TRAIN_ARCH, seed=0)
+    O.synthetic_lora(model, 8, 16, TRAIN_TARGETS, seed=1, b_std=0.0)
+    oracle = T.TrainOracle(model, lr=1e-4)
+    pv = O.synth_images(batch, seed=8)
+    ids, mask = O.synth_captions(batch, seed=9)
+    oracle.step(pv, ids, mask)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.step(pv, ids, mask)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, cores, f"{steps} optimizer steps of batch {batch} (ViT-B/32 + LoRA r=8 q,k,v,out, fp32 autograd) in {dt:.1f}s"
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -209,6 +234,7 @@ def main():
     ap.add_argument("--no-search", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l14", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--index-rows", type=int, default=INDEX_ROWS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -576,6 +602,60 @@ def main():
         del idx
         torch.cuda.empty_cache()
 
+    # ---- LoRA training step (reference scripts/train_lora.py) -------------------
+    # The reference's own training configuration (config/lora_config.yaml: ViT-B/32, r = 8 on q,k,v,out, batch 8,
+    # temperature 0.07, AdamW + clip) and a batch of 256: forward + backward + clip + AdamW per step through
+    # LoraTrainer.step (CUDA-graph replay), device-resident inputs, and end to end from pinned host inputs with
+    # the loss read back.  One process (the reference's training is single process): N = 1 only.
+    train = None
+    if world == 1 and not args.no_train:
+        from clip_lora_match_b200.models.lora_trainer import LoraTrainer
+
+        arch_t = CM.arch_from_name(TRAIN_ARCH)
+        sd_t = CM.random_init_state_dict(arch_t, seed=0)
+        train = {"workload": "reference config/lora_config.yaml: CLIP ViT-B/32 + LoRA r=8 (q,k,v,out), symmetric "
+                             "InfoNCE T=0.07, clip 1.0 + AdamW, random-init weights, synthetic pairs; LoRA dropout not applied",
+                 "batches": {}}
+        for tb in TRAIN_BATCHES:
+            model_t = CM.B200ClipModel(arch_t, sd_t, device=dev)
+            model_t.set_lora(init_lora_adapter(model_t.linear_dims(), LoraConfig(r=8, lora_alpha=16, target_modules=TRAIN_TARGETS),
+                                               seed=1, base_model_name=TRAIN_ARCH))
+            tr = LoraTrainer(model_t, lr=1e-4, weight_decay=0.01, max_grad_norm=1.0, temperature=0.07)
+            gt = torch.Generator(device=dev).manual_seed(8)
+            pv_t = torch.randn((tb, 3, 224, 224), generator=gt, device=dev)
+            ids_t = synth_captions(tb, seed=9)[0].to(dev, torch.int32)
+            pv_h, ids_h = pv_t.cpu().pin_memory(), ids_t.cpu().pin_memory()
+            for _ in range(max(args.warmup, 3)):
+                tr.step(pv_t, ids_t)
+            n0 = lib.clm_launch_count()
+            ms_t = timed(lambda: tr.step(pv_t, ids_t), args.steps)
+            launches_t = (lib.clm_launch_count() - n0) // args.steps
+            loss_last = []
+
+            def t_e2e():
+                loss_last.append(tr.step(pv_h.to(dev, non_blocking=True), ids_h.to(dev, non_blocking=True)).item())
+
+            ms_te = timed(t_e2e, args.steps)
+            lib.clm_prof_enable(1)
+            tr.step(pv_t, ids_t)
+            prof_t = {kn: _lib.prof_summary(kn) for kn in ("gemm", "attention", "elementwise")}
+            lib.clm_prof_enable(0)
+            train["batches"][str(tb)] = {
+                "pairs_per_s": tb * args.steps / (ms_t / 1e3), "ms_per_step": ms_t / args.steps,
+                "e2e_pairs_per_s": tb * args.steps / (ms_te / 1e3), "e2e_ms_per_step": ms_te / args.steps,
+                "h2d_bytes_per_step": pv_h.numel() * 4 + ids_h.numel() * 4, "d2h_bytes_per_step": 4,
+                "launches_per_step": int(launches_t), "trainable_parameters": tr.num_trainable_parameters(),
+                "loss_first_last": [loss_last[0], loss_last[-1]],
+                "kernel_ms_eager_step": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                             "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1)}
+                                         for k, v in prof_t.items()}}
+            del tr, model_t
+            torch.cuda.empty_cache()
+        if not args.no_cpu_baseline:
+            v, cores, sample = cpu_train_rate()
+            train["cpu_baseline"] = {"value": v, "unit": "image-caption pairs/s", "cores": cores, "kind": "port",
+                                     "sample": sample}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_encode_rate()
@@ -590,7 +670,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "detail": detail, "vit_l14": l14, "search": search,
+            "roofline": roofline, "cpu_baseline": cpu, "detail": detail, "vit_l14": l14, "search": search, "train": train,
         }
         print(json.dumps(line), flush=True)
 

@@ -234,7 +234,8 @@ def test_text_length_buckets_cover_every_caption_and_merge_small_groups():
 
 
 @pytest.mark.parametrize("name", ["build_text_index", "build_custom_index", "rebuild_index", "build_image_index",
-                                  "demo_search_text", "demo_search_image", "demo_seeker", "demo_finder_report"])
+                                  "demo_search_text", "demo_search_image", "demo_seeker", "demo_finder_report",
+                                  "train_lora"])
 def test_every_script_mirror_imports_and_parses_its_arguments(name):
     """The reference's scripts have hard-coded paths; the mirrors take them as arguments.  Importing a script
     must not need a GPU, and --help must describe it."""
@@ -310,3 +311,31 @@ def test_pooling_eos_id_maps_the_legacy_value():
     cfg = CLIPConfig(text_config={"eos_token_id": 2})  # what the published openai/clip-vit-* configs carry
     assert cfg.text_config.eos_token_id == 2
     assert CM.arch_from_hf_config(cfg).eos_id == cfg.text_config.vocab_size - 1
+
+
+def test_train_lora_mirror_host_logic(tmp_path):
+    """scripts/train_lora.py mirror: the schedule equals the reference's closure (golden from its own source), the
+    config / CSV errors are the reference's, and the loss front end refuses CPU tensors (no fallback)."""
+    import numpy as np
+
+    from clip_lora_match_b200.scripts import train_lora as TL
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "train_golden.npz"))
+    for row in g["sched"]:
+        total, warm = int(row[0]), int(row[1])
+        assert [TL.lr_lambda(s, total, warm) for s in range(total + 2)] == list(row[2:2 + total + 2])
+    with pytest.raises(FileNotFoundError, match="LoRA config file not found"):
+        TL.load_lora_training_config(tmp_path / "nope.yaml")
+    with pytest.raises(ValueError, match="train_csv"):
+        TL.build_dataloaders({"data": {}})
+    with pytest.raises(FileNotFoundError, match="CSV not found"):
+        TL.ClipPairDataset(tmp_path / "nope.csv", processor=object())
+    bad = tmp_path / "bad.csv"
+    bad.write_text("a,b\n1,2\n")
+    with pytest.raises(ValueError, match="image_path"):
+        TL.ClipPairDataset(bad, processor=object())
+    with pytest.raises(ValueError, match="CUDA"):
+        TL.compute_clip_contrastive_loss(torch.randn(4, 8), torch.randn(4, 8))
+    # the shipped YAML carries the reference's training section
+    cfg = TL.load_lora_training_config(os.path.join(ROOT, "clip_lora_match_b200", "config", "lora_config.yaml"))
+    assert cfg["training"]["temperature"] == 0.07 and cfg["training"]["batch_size"] == 8

@@ -381,3 +381,50 @@ def test_gradient_accumulation_matches_one_big_loss_scale(cuda_device):
     fr = torch.cat([torch.cat([ref_grads[k][0].flatten(), ref_grads[k][1].flatten()]) for k in ref_grads])
     assert _cos(fg, fr) >= 0.99
     assert abs(float(fg.norm() / fr.norm()) - 1.0) < 0.05
+
+
+def test_train_script_mirror_end_to_end(cuda_device, tmp_path):
+    """scripts/train_lora.train() on synthetic loaders: two epochs with gradient accumulation off and on, per-epoch
+    PEFT checkpoints (reference :243-247) that load_clip_model(use_lora=True) accepts, and
+    compute_clip_contrastive_loss equal to the oracle's restatement of the reference's."""
+    import yaml
+
+    from clip_lora_match_b200.models import clip_model as CM
+    from clip_lora_match_b200.scripts import train_lora as TL
+
+    arch = CM.arch_from_hf_config(O.hf_config("tiny-test"), "tiny-test")
+    sd = O.base_state_dict(O.build_model("tiny-test", seed=0))
+
+    def batches(n, seed):
+        out = []
+        for k in range(n):
+            ids, mask = O.synth_captions(8, seed=seed + 2 * k + 1)
+            out.append({"pixel_values": O.synth_images(8, seed=seed + 2 * k), "input_ids": ids, "attention_mask": mask})
+        return out
+
+    for accum in (1, 2):
+        cfg = {"model": {"base_model_name": "tiny-test", "target_modules": ["q_proj", "k_proj", "v_proj", "out_proj"]},
+               "lora": {"r": 8, "alpha": 16, "dropout": 0.1},
+               "training": {"seed": 1, "batch_size": 8, "learning_rate": 2e-3, "num_epochs": 2, "logging_steps": 2,
+                            "gradient_accumulation_steps": accum, "warmup_ratio": 0.25,
+                            "output_dir": str(tmp_path / f"out{accum}")}}
+        ypath = tmp_path / f"lora{accum}.yaml"
+        ypath.write_text(yaml.safe_dump(cfg))
+        model = CM.B200ClipModel(arch, sd, lora=None, device=cuda_device)
+        train, val = batches(4, 100), batches(1, 900)
+        pv, ids, mask = (val[0][k].to(cuda_device) for k in ("pixel_values", "input_ids", "attention_mask"))
+        trainer = TL.train(ypath, loaders=(train, val), model=model)
+        assert trainer.opt_step == 2 * 4 // accum
+        for e in (1, 2):
+            d = tmp_path / f"out{accum}" / f"epoch_{e}"
+            assert (d / "adapter_config.json").exists() and (d / "adapter_model.safetensors").exists()
+        # B is zero at attach time: any non-zero B proves the optimizer moved the factors
+        w = trainer.export_adapter().weights
+        assert all(float(b.abs().max()) > 0 for _, b in w.values())
+        # the trained model (sync_model) reproduces the trainer's own features
+        trainer.eval_loss(pv, ids, mask)
+        fi, ft = (f.clone() for f in trainer.features())
+        assert O.parity_metrics(model.encode_images(pv, normalize=False).cpu(), fi.cpu())["rel_l2_max"] < 2e-2
+        assert O.parity_metrics(model.encode_texts(ids, normalize=False).cpu(), ft.cpu())["rel_l2_max"] < 2e-2
+        got = TL.compute_clip_contrastive_loss(fi, ft, 0.07).item()
+        assert abs(got - float(T.contrastive_loss(fi.cpu(), ft.cpu(), 0.07))) < 1e-4

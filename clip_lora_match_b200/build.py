@@ -24,6 +24,7 @@ SOURCES = [
     "clm_search.cu",
     "clm_tower.cu",
     "clm_train.cu",
+    "clm_attention_bwd.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -559,6 +559,11 @@ inline int attn_tp(int tokens) { return (tokens + 31) / 32 * 32; }
 
 }  // namespace
 
+// clm_attention_bwd.cu: the tcgen05 kernel for sequences of at most 128 tokens
+int clm_attention_bwd_tc_supported(int tokens);
+int clm_attention_bwd_tc_launch(const void* qkv, const void* dout, void* dqkv, int batch, int tokens, int heads,
+                                int causal, cudaStream_t stream);
+
 extern "C" int clm_quickgelu_fwd(const void* z_bf16, void* g_bf16, long long n, void* stream) {
   CLM_REQUIRE(z_bf16 && g_bf16 && n >= 0 && n % 8 == 0, "clm_quickgelu_fwd: bad argument (n must be a multiple of 8)");
   if (n == 0) return CLM_OK;
@@ -652,6 +657,8 @@ extern "C" int clm_attention_bwd(const void* qkv_bf16, const void* dout_bf16, vo
               clm_attention_bwd_scratch_bytes(batch, tokens, heads));
   CLM_REQUIRE(static_cast<long long>(batch) * heads <= 65535, "clm_attention_bwd: batch * heads > 65535");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (clm_attention_bwd_tc_supported(tokens))
+    return clm_attention_bwd_tc_launch(qkv_bf16, dout_bf16, dqkv_bf16, batch, tokens, heads, causal, s);
   const int T = tokens, Tp = attn_tp(tokens);
   const size_t smem1 = static_cast<size_t>(2) * T * kRowStrideW * 4 + static_cast<size_t>(2) * 32 * (Tp + 2) * 2 +
                        static_cast<size_t>(kWarps) * Tp * 4;

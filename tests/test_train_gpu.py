@@ -117,7 +117,10 @@ def test_transpose_and_cast(cuda_device):
 
 
 @pytest.mark.parametrize("batch,tokens,heads,causal", [
-    (3, 50, 2, 0), (2, 77, 8, 1), (2, 197, 12, 0), (1, 257, 16, 0), (4, 16, 2, 1), (1, 384, 1, 0), (2, 33, 2, 1)])
+    (3, 50, 2, 0), (2, 77, 8, 1), (2, 197, 12, 0), (1, 257, 16, 0), (4, 16, 2, 1), (1, 384, 1, 0), (2, 33, 2, 1),
+    # T <= 128: the tcgen05 kernel (Tp = 64 / 96 / 128), several items per CTA; T > 128: the CUDA-core kernels
+    (40, 50, 12, 0), (32, 77, 8, 1), (3, 128, 2, 0), (3, 128, 2, 1), (2, 96, 3, 1), (2, 65, 2, 0), (5, 1, 2, 1),
+    (2, 129, 2, 1)])
 def test_attention_bwd_vs_autograd(cuda_device, batch, tokens, heads, causal):
     L, lib = _lib()
     from clip_lora_match_b200 import kernels as K
@@ -142,8 +145,8 @@ def test_attention_bwd_vs_autograd(cuda_device, batch, tokens, heads, causal):
     ref = x.grad
     for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
         got, want = dqkv[:, sl].float(), ref[:, sl]
-        rel = float((got - want).norm() / want.norm())
-        assert rel < 2e-2, f"{name}: rel L2 {rel}"
+        err, ref_n = float((got - want).norm()), float(want.norm())
+        assert err <= 2e-2 * ref_n + 1e-6, f"{name}: error {err} against a gradient of norm {ref_n}"  # T = 1: dq = dk = 0
     # the forward kernel agrees with the same reference (the backward recomputes ITS softmax)
     fwd = K.attention(qkv, batch, tokens, heads, bool(causal)).float()
     assert float((fwd - o.detach()).norm() / o.detach().norm()) < 2e-2

@@ -14,6 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libclm_b200.so"
 
 EPI_NONE = 0
 EPI_QUICKGELU = 1
+EPI_SPLIT_K = 2
 OUT_BF16 = 0
 OUT_F32 = 1
 

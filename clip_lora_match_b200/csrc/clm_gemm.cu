@@ -79,6 +79,10 @@ struct EpiParams {
   int ldr;
   int out_f32;
   int act;
+  // split-K (reduce-add epilogue only): a tile's k-blocks are cut into ksplit ranges of kb_per blocks, each range a
+  // work unit of its own that adds its partial product into out; range 0 also adds the bias.  1 = off.
+  int ksplit;
+  int kb_per;
 };
 
 // ---- cta_group::2 helpers ---------------------------------------------------------------
@@ -169,7 +173,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   constexpr int TM = BM * kCtas;  // tile rows per worker
   const int n_tiles = (N + BN - 1) / BN;
   const int m_tiles = (M + TM - 1) / TM;
-  const int num_tiles = m_tiles * n_tiles;
+  const int ksplit = ep.ksplit;
+  const int num_tiles = m_tiles * n_tiles * ksplit;  // work units: (tile, k range), k range fastest
   const int kb_total = kb_main + kb_ext;
 
   if (warp == kTmaWarp && lane == 0) {
@@ -209,10 +214,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      for (int unit = worker; unit < num_tiles; unit += num_workers) {
+        const int tile = unit / ksplit, ks = unit - tile * ksplit;
+        const int kb_lo = ks * ep.kb_per, kb_hi = (ksplit == 1 || kb_lo + ep.kb_per > kb_total) ? kb_total : kb_lo + ep.kb_per;
         const int m0 = (tile / n_tiles) * TM + static_cast<int>(rank) * BM;
         const int n0 = (tile % n_tiles) * BN + static_cast<int>(rank) * (BN / kCtas);
-        for (int kb = 0; kb < kb_total; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
@@ -241,11 +248,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      for (int unit = worker; unit < num_tiles; unit += num_workers) {
+        const int ks = unit % ksplit;
+        const int kb_lo = ks * ep.kb_per, kb_hi = (ksplit == 1 || kb_lo + ep.kb_per > kb_total) ? kb_total : kb_lo + ep.kb_per;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < kb_total; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (lane == 0) {
@@ -256,15 +265,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               // advancing 16 bf16 (32 B) along K inside the 128-B swizzle atom
               const uint64_t da = umma_desc_sw128(a_addr + k * 32, 1024);
               const uint64_t db = umma_desc_sw128(b_addr + k * 32, 1024);
-              if (kCtas == 2) umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (kCtas == 2) umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb != kb_lo || k != 0) ? 1u : 0u);
+              else umma_bf16_ss(tmem_d, da, db, idesc, (kb != kb_lo || k != 0) ? 1u : 0u);
             }
             if (kCtas == 2) {
               umma_commit_2sm(&empty[stage]);                           // frees the slot in both CTAs
-              if (kb == kb_total - 1) umma_commit_2sm(&tmem_full[acc]);  // accumulators ready (both)
+              if (kb == kb_hi - 1) umma_commit_2sm(&tmem_full[acc]);  // accumulators ready (both)
             } else {
               umma_commit(&empty[stage]);
-              if (kb == kb_total - 1) umma_commit(&tmem_full[acc]);
+              if (kb == kb_hi - 1) umma_commit(&tmem_full[acc]);
             }
           }
           __syncwarp();
@@ -294,7 +303,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+    for (int unit = worker; unit < num_tiles; unit += num_workers) {
+      const int tile = unit / ksplit;
+      const float* bias = (unit - tile * ksplit == 0) ? ep.bias : nullptr;  // the first k range of a tile adds the bias
       const int m0 = (tile / n_tiles) * TM + static_cast<int>(rank) * BM + q * 32;
       const int n0 = (tile % n_tiles) * BN + (kSplit ? half * (BN / 2) : 0);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -325,7 +336,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ep.bias && col0 + 4 * p < N) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 4 * p));
+              if (bias && col0 + 4 * p < N) b = __ldg(reinterpret_cast<const float4*>(bias + col0 + 4 * p));
               float x0 = __uint_as_float(v[4 * p + 0]) + b.x, x1 = __uint_as_float(v[4 * p + 1]) + b.y;
               float x2 = __uint_as_float(v[4 * p + 2]) + b.z, x3 = __uint_as_float(v[4 * p + 3]) + b.w;
               if (ep.act == CLM_EPI_QUICKGELU) {
@@ -354,9 +365,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
             for (int p = 0; p < 8; ++p) {  // piece p = columns col0 + 8p .. + 7
               float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-              if (ep.bias && col0 + 8 * p < N) {
-                b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 8 * p));
-                b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 8 * p + 4));
+              if (bias && col0 + 8 * p < N) {
+                b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * p));
+                b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * p + 4));
               }
               const uint32_t* src = (p < 4) ? &v0[8 * p] : &v1[8 * (p - 4)];
               float x0 = __uint_as_float(src[0]) + b0.x, x1 = __uint_as_float(src[1]) + b0.y;
@@ -500,7 +511,7 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = ((M + BM * kCtas - 1) / (BM * kCtas)) * ((N + BN - 1) / BN);
+  const int tiles = ((M + BM * kCtas - 1) / (BM * kCtas)) * ((N + BN - 1) / BN) * ep.ksplit;  // work units
   const int max_workers = clm_num_sms() / kCtas;
   const int workers = tiles < max_workers ? tiles : max_workers;
   cudaLaunchConfig_t cfg = {};
@@ -604,7 +615,7 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
   ep.ldo = ldo;
   ep.ldr = ldr;
   ep.out_f32 = (out_dtype == CLM_OUT_F32);
-  ep.act = epilogue;
+  ep.act = epilogue & CLM_EPI_QUICKGELU;
   // epilogue variant: TMA tile stores, or a TMA reduce-add for the in-place residual update; the
   // per-thread legacy path only for residual != out / bf16 out + residual (CLM_GEMM_EPI=legacy forces it)
   static int force_legacy = -1;
@@ -625,6 +636,26 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
   }
   const int kb_main = (K + BK - 1) / BK;
   const int kb_ext = has_ext ? (K2 + BK - 1) / BK : 0;
+  // Split-K for deep, narrow products with the in-place reduce-add epilogue (the LoRA weight gradients of the
+  // training step: out [features, 64] += dy^T t over tens of thousands of token rows -- 4 to 18 tiles on 148 SMs):
+  // cut K so that every SM has a work unit, but keep at least 8 k-blocks per unit.
+  ep.ksplit = 1;
+  ep.kb_per = kb_main + kb_ext;
+  if (epi == kEpiReduceF32 && (epilogue & CLM_EPI_SPLIT_K)) {
+    const long long sms = clm_num_sms();
+    const long long tiles = pair ? static_cast<long long>((M + 255) / 256) * (N / 256)
+                                 : static_cast<long long>((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const long long ctas = tiles * (pair ? 2 : 1);
+    const int kb_total = kb_main + kb_ext;
+    if (ctas * 2 <= sms && kb_total >= 32) {
+      long long want = sms / ctas;
+      if (want > kb_total / 8) want = kb_total / 8;
+      if (want > 1) {
+        ep.kb_per = static_cast<int>((kb_total + want - 1) / want);
+        ep.ksplit = (kb_total + ep.kb_per - 1) / ep.kb_per;
+      }
+    }
+  }
   const double flops = 2.0 * M * N * (static_cast<double>(K) + (has_ext ? K2 : 0));
   const double bytes = 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) +
                        static_cast<double>(M) * N * (ep.out_f32 ? 4 : 2) +

@@ -30,7 +30,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from .. import _lib
-from .._lib import EPI_NONE, OUT_BF16, OUT_F32, check, cur_stream, ptr
+from .._lib import EPI_NONE, EPI_SPLIT_K, OUT_BF16, OUT_F32, check, cur_stream, ptr
 from .clip_model import LORA_COLS, B200ClipModel
 from .lora_adapter import LoraAdapter
 
@@ -66,7 +66,7 @@ class _Tower:
 class LoraTrainer:
     def __init__(self, model: B200ClipModel, lr: float = 1e-4, weight_decay: float = 0.01,
                  max_grad_norm: float = 1.0, temperature: float = 0.07, betas: Tuple[float, float] = (0.9, 0.999),
-                 eps: float = 1e-8, grad_accum_steps: int = 1, use_graph: bool = True):
+                 eps: float = 1e-8, grad_accum_steps: int = 1, use_graph: bool = True, deterministic: bool = False):
         if model.lora is None:
             raise ValueError("LoraTrainer needs a model with a LoRA adapter (attach_lora_to_clip first)")
         self.model = model
@@ -77,6 +77,9 @@ class LoraTrainer:
         self.temperature, self.betas, self.eps = float(temperature), betas, float(eps)
         self.grad_accum_steps = int(grad_accum_steps)
         self.use_graph = use_graph
+        # False: the weight-gradient GEMMs may split K (partial products added through the L2 in arrival order:
+        # reproducible to fp32 rounding); True: one work unit per tile, every step reproducible bit for bit
+        self.deterministic = deterministic
         self.opt_step = 0      # optimizer steps taken
         self._micro = 0        # micro-batches since the last optimizer step
         self.config = model.lora.config
@@ -298,7 +301,8 @@ class LoraTrainer:
         self.loss_ws = torch.empty(nb, dtype=torch.uint8, device=dev)
 
     # ---- thin launch helpers -----------------------------------------------------------------------------------
-    def _gemm(self, a, w, out, bias=None, a2=None, w2=None, accumulate=False, M=None, N=None, K=None, K2=None):
+    def _gemm(self, a, w, out, bias=None, a2=None, w2=None, accumulate=False, M=None, N=None, K=None, K2=None,
+              split_k=False):
         M = a.shape[0] if M is None else M
         K = a.shape[1] if K is None else K
         N = w.shape[0] if N is None else N
@@ -311,7 +315,9 @@ class LoraTrainer:
                                     ptr(a2), a2.stride(0) if a2 is not None else 0,
                                     ptr(w2), w2.stride(0) if w2 is not None else 0, k2,
                                     ptr(out), out.stride(0), od, ptr(bias), ptr(res),
-                                    out.stride(0) if accumulate else 0, EPI_NONE, cur_stream()), "clm_gemm_epi")
+                                    out.stride(0) if accumulate else 0,
+                                    EPI_SPLIT_K if (split_k and not self.deterministic) else EPI_NONE, cur_stream()),
+              "clm_gemm_epi")
 
     def _transpose(self, src, dst, rows, cols):
         check(self.lib.clm_transpose_to_bf16(ptr(src), 0, src.stride(0), 0, rows, cols, ptr(dst), dst.stride(0), 0, 1,
@@ -388,10 +394,10 @@ class LoraTrainer:
         ga = self._master(key, "a", self.grad)[layer]
         self._transpose(dy, t.dyT, rows, n_out)
         self._transpose(t.t[name][layer], t.tT, rows, g.cols)
-        self._gemm(t.dyT, t.tT, gb, accumulate=True, M=n_out, N=g.cols, K=rows)
+        self._gemm(t.dyT, t.tT, gb, accumulate=True, M=n_out, N=g.cols, K=rows, split_k=True)
         self._transpose(x, t.xT, rows, in_dim)
         self._transpose(u, t.uT, rows, g.cols)
-        self._gemm(t.xT, t.uT, ga, accumulate=True, M=in_dim, N=g.cols, K=rows)
+        self._gemm(t.xT, t.uT, ga, accumulate=True, M=in_dim, N=g.cols, K=rows, split_k=True)
 
     def _backward_tower(self, t: _Tower, batch: int) -> None:
         a, lib, st = self.arch, self.lib, cur_stream()

@@ -33,6 +33,12 @@ extern "C" {
 /* epilogue selector for clm_gemm_epi (bit flags) */
 #define CLM_EPI_NONE 0
 #define CLM_EPI_QUICKGELU 1 /* x * sigmoid(1.702 x); transformers/activations.py QuickGELU */
+/* Allow split-K for an in-place fp32 accumulation (out == residual) that has fewer tiles than half the SMs and
+ * K >= 2048: the k range of a tile is cut into work units that add their partial products into out through the
+ * L2 (TMA reduce-add).  The additions arrive in no fixed order: the result is reproducible to fp32 rounding, not
+ * bit for bit.  Used by the training step's LoRA weight gradients (out [features, 64] += dy^T t over all token
+ * rows).  No effect on any other call. */
+#define CLM_EPI_SPLIT_K 2
 #define CLM_OUT_BF16 0
 #define CLM_OUT_F32 1
 

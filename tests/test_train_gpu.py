@@ -343,7 +343,8 @@ def test_training_trajectory_graph_and_export(cuda_device, tmp_path):
     runs = {}
     for use_graph in (False, True):
         _, gpu = _pair("tiny-test", 8, 16, targets, cuda_device)
-        tr = LoraTrainer(gpu, lr=2e-3, weight_decay=0.01, max_grad_norm=1.0, temperature=0.07, use_graph=use_graph)
+        tr = LoraTrainer(gpu, lr=2e-3, weight_decay=0.01, max_grad_norm=1.0, temperature=0.07, use_graph=use_graph,
+                         deterministic=True)
         losses = [tr.step(pv.to(cuda_device), ids.to(cuda_device), mask.to(cuda_device), lr=2e-3).item() for _ in range(6)]
         runs[use_graph] = (losses, tr.theta.clone(), tr)
     print(f"[train] oracle {ref_losses}\n[train] eager  {runs[False][0]}\n[train] graph  {runs[True][0]}")
@@ -431,3 +432,32 @@ def test_train_script_mirror_end_to_end(cuda_device, tmp_path):
         assert O.parity_metrics(model.encode_texts(ids, normalize=False).cpu(), ft.cpu())["rel_l2_max"] < 2e-2
         got = TL.compute_clip_contrastive_loss(fi, ft, 0.07).item()
         assert abs(got - float(T.contrastive_loss(fi.cpu(), ft.cpu(), 0.07))) < 1e-4
+
+
+def test_split_k_weight_gradients(cuda_device):
+    """Deep-K weight-gradient GEMMs with CLM_EPI_SPLIT_K (several work units per tile adding through the L2) give the
+    one-unit-per-tile result up to fp32 rounding, at a batch whose token count (12,800 / 19,712 rows) triggers it."""
+    from clip_lora_match_b200 import _lib as L
+    from clip_lora_match_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(11)
+    rows = 19712
+    for feats in (512, 2304):
+        dyT = torch.randn((feats, rows), generator=g).to(cuda_device, torch.bfloat16)
+        tT = torch.randn((64, rows), generator=g).to(cuda_device, torch.bfloat16)
+        bias = torch.randn(64, generator=g).to(cuda_device)
+        base = torch.randn((feats, 64), generator=g).to(cuda_device)
+        ref = base.double() + dyT.double() @ tT.double().t() + bias.double()
+        outs = []
+        for flag in (L.EPI_NONE, L.EPI_SPLIT_K):
+            out = base.clone()
+            K.gemm_epi(dyT, tT, bias=bias, residual=out, out=out, act=flag)
+            outs.append(out)
+            rel = float((out.double() - ref).norm() / ref.norm())
+            assert rel < 1e-4, (feats, flag, rel)
+        diff = float((outs[0] - outs[1]).abs().max())
+        assert diff < 2e-3 * float(ref.abs().max()), (feats, diff)
+    # the flag is ignored where it does not apply (bf16 store): same bits as without it
+    a = torch.randn((300, 4096), generator=g).to(cuda_device, torch.bfloat16)
+    w = torch.randn((64, 4096), generator=g).to(cuda_device, torch.bfloat16)
+    assert torch.equal(K.gemm_epi(a, w, act=L.EPI_SPLIT_K), K.gemm_epi(a, w))

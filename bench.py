@@ -149,10 +149,10 @@ def cpu_encode_rate(target_seconds=12.0, per_step=8):
     return n / dt, cores, f"{n} image+caption pairs of configs[1] (ViT-B/16+LoRA r=16, fp32, batch {per_step}) in {dt:.1f}s"
 
 
-def cpu_train_rate(steps=2, batch=8):
+def cpu_train_rate(target_seconds=10.0, batch=8):
     """The training oracle (transformers fp32 CLIPModel + LoRA wrappers, torch autograd, torch AdamW: the reference's
-    step loop, scripts/train_lora.py:172-193) on all host threads: pairs per second over `steps` steps of the
-    reference's own batch of 8."""
+    step loop, scripts/train_lora.py:172-193) on all host threads: pairs per second over ~10 s of optimizer steps at
+    the reference's own batch of 8."""
     import torch
 
     from oracle import clip_oracle as O
@@ -166,10 +166,13 @@ def cpu_train_rate(steps=2, batch=8):
     pv = O.synth_images(batch, seed=8)
     ids, mask = O.synth_captions(batch, seed=9)
     oracle.step(pv, ids, mask)  # warm-up
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    steps, t0 = 0, time.perf_counter()
+    while True:
         oracle.step(pv, ids, mask)
-    dt = time.perf_counter() - t0
+        steps += 1
+        dt = time.perf_counter() - t0
+        if dt >= target_seconds:
+            break
     return batch * steps / dt, cores, f"{steps} optimizer steps of batch {batch} (ViT-B/32 + LoRA r=8 q,k,v,out, fp32 autograd) in {dt:.1f}s"
 
 

@@ -162,6 +162,34 @@ transpose_kernel(const void* __restrict__ in, long long ld_in, long long bs_in, 
   }
 }
 
+// bf16 -> bf16 transpose of a [rows, cols] matrix with 32-bit global accesses on both sides: a 64 x 64 tile is
+// staged as halfwords (row stride 66: the column walk of the write-out is at most 2-way bank conflicted), and every
+// thread assembles output words from two input rows.  cols, ld_in, ld_out even, rows padded by the caller's ld_out.
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, int rows, int cols,
+                      __nv_bfloat16* __restrict__ out, long long ld_out) {
+  __shared__ uint16_t tile[64][66];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = r0 + wy + 8 * k, c = c0 + 2 * lane;
+    uint32_t w = 0;
+    if (r < rows && c < cols) w = *reinterpret_cast<const uint32_t*>(in + static_cast<size_t>(r) * ld_in + c);
+    *reinterpret_cast<uint32_t*>(&tile[wy + 8 * k][2 * lane]) = w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + wy + 8 * k, r = r0 + 2 * lane;
+    if (c < cols && r < rows) {  // rows beyond `rows` inside the pair were staged as zeros
+      const uint32_t w = static_cast<uint32_t>(tile[2 * lane][wy + 8 * k]) |
+                         (static_cast<uint32_t>(tile[2 * lane + 1][wy + 8 * k]) << 16);
+      *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(c) * ld_out + r) = w;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t n4, float scale) {
   const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
@@ -617,6 +645,14 @@ extern "C" int clm_transpose_to_bf16(const void* in, int in_is_f32, long long ld
   CLM_REQUIRE(batch <= 65535 && (rows + 31) / 32 <= 65535, "clm_transpose_to_bf16: too many tiles");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   ProfScope prof(CLM_K_ELEMENTWISE, 0.0, (in_is_f32 ? 6.0 : 4.0) * rows * cols * batch, s);
+  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  if (!in_is_f32 && batch == 1 && scale == 1.0f && cols % 2 == 0 && ld_in % 2 == 0 && ld_out % 2 == 0 &&
+      (reinterpret_cast<uintptr_t>(in) & 3) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 3) == 0) {
+    transpose_bf16_kernel<<<dim3((cols + 63) / 64, (rows + 63) / 64), 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(in), ld_in, rows, cols, ob, ld_out);
+    CLM_CUDA_CHECK(cudaGetLastError());
+    return CLM_OK;
+  }
   const dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
   if (in_is_f32)
     transpose_kernel<true><<<grid, 256, 0, s>>>(in, ld_in, batch_stride_in, rows, cols,

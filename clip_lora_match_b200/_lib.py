@@ -84,6 +84,7 @@ SIGNATURES = {
     "clm_transpose_to_bf16": (_I, [_P, _I, C.c_longlong, C.c_longlong, _I, _I, _P, C.c_longlong, C.c_longlong, _I,
                                    _F, _P]),
     "clm_cast_to_bf16": (_I, [_P, _P, C.c_longlong, _F, _P]),
+    "clm_lora_wgrad_small": (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P]),
     "clm_attention_bwd_scratch_bytes": (C.c_size_t, [_I, _I, _I]),
     "clm_attention_bwd": (_I, [_P, _P, _P, _P, C.c_size_t, _I, _I, _I, _I, _P]),
     "clm_clip_loss_workspace_bytes": (C.c_size_t, [_I, _I]),

@@ -571,6 +571,92 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, const float* __
   p[i] = pi;
 }
 
+// ------------------------------------------------------------------------------------------------
+// LoRA weight gradients for FEW token rows (the reference's batch of 8: 400 / 616 rows), where the tensor-core
+// route -- four transposes and two deep-K GEMMs -- is six launches of a few microseconds each:
+//   gB[f][c] += sum_r dy[r][f] t[r][c]   (f < n_out)        gA[f][c] += sum_r x[r][f] u[r][c]   (f < n_in)
+// One launch, CUDA cores, fp32 accumulation: a CTA (128 threads, 4 x 4 outputs each) owns 32 features x 64 LoRA columns of one of
+// the two products and walks its token rows in chunks of 64 staged in shared memory, the next chunk's loads in flight.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+lora_wgrad_small_kernel(const __nv_bfloat16* __restrict__ dy, int ld_dy, int n_out, const __nv_bfloat16* __restrict__ t,
+                        int ld_t, const __nv_bfloat16* __restrict__ x, int ld_x, int n_in,
+                        const __nv_bfloat16* __restrict__ u, int ld_u, int cols, int rows, float* __restrict__ gB,
+                        float* __restrict__ gA) {
+  constexpr int kChunk = 64;  // token rows per staged chunk
+  __shared__ __align__(16) float fs[kChunk][36], cs[kChunk][68];  // 16-byte aligned rows: 128-bit reads in the product loop
+  const int blocks_b = (n_out + 31) / 32;
+  const int cblocks = cols / 64;
+  const int fb = blockIdx.x / cblocks, cb = blockIdx.x - fb * cblocks;
+  const bool is_b = fb < blocks_b;
+  const __nv_bfloat16* F = is_b ? dy : x;
+  const __nv_bfloat16* Cm = is_b ? t : u;
+  const int ldf = is_b ? ld_dy : ld_x, ldc = is_b ? ld_t : ld_u;
+  const int nf = is_b ? n_out : n_in;
+  const int f0 = (is_b ? fb : fb - blocks_b) * 32, c0 = cb * 64;
+  float* out = is_b ? gB : gA;
+  // gridDim.y CTAs share the token rows of a tile (contiguous slices, multiples of the chunk) and add their partial
+  // sums with atomics; gridDim.y == 1: one CTA per tile, plain read-modify-write, bit-for-bit reproducible
+  const int per = ((rows + gridDim.y - 1) / gridDim.y + kChunk - 1) / kChunk * kChunk;
+  const int r_lo = blockIdx.y * per, r_hi = min(rows, r_lo + per);
+  if (r_lo >= r_hi) return;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 4 columns x 4 features per thread: 16 x 8 threads
+  const int w = threadIdx.x & 31, rbase = threadIdx.x >> 5;  // staging: bf16 pair w of rows rbase + 4 k
+  const bool f_ok = w < 16 && f0 + 2 * w < nf;
+  float acc[4][4] = {};
+  uint32_t fw[16], cw[16];
+  // every load of a chunk is issued before anything waits on one, and the next chunk's loads are in flight while
+  // this one is multiplied: a CTA walks its rows alone, so the L2 latency would otherwise be paid once per chunk
+  auto load_chunk = [&](int r0) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int r = r0 + rbase + 4 * k;
+      fw[k] = cw[k] = 0u;
+      if (r < r_hi) {
+        if (f_ok) fw[k] = __ldg(reinterpret_cast<const uint32_t*>(F + static_cast<size_t>(r) * ldf + f0 + 2 * w));
+        cw[k] = __ldg(reinterpret_cast<const uint32_t*>(Cm + static_cast<size_t>(r) * ldc + c0 + 2 * w));
+      }
+    }
+  };
+  load_chunk(r_lo);
+  for (int r0 = r_lo; r0 < r_hi; r0 += kChunk) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int rr = rbase + 4 * k;
+      if (w < 16) { fs[rr][2 * w] = bf16_lo(fw[k]); fs[rr][2 * w + 1] = bf16_hi(fw[k]); }
+      cs[rr][2 * w] = bf16_lo(cw[k]); cs[rr][2 * w + 1] = bf16_hi(cw[k]);
+    }
+    __syncthreads();
+    if (r0 + kChunk < r_hi) load_chunk(r0 + kChunk);
+#pragma unroll 8
+    for (int rr = 0; rr < kChunk; ++rr) {
+      const float4 av = *reinterpret_cast<const float4*>(&fs[rr][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&cs[rr][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int f = f0 + ty * 4 + i;
+    if (f < nf) {
+      float* o = out + static_cast<size_t>(f) * cols + c0 + tx * 4;
+      if (gridDim.y == 1) {
+        float4 v = *reinterpret_cast<float4*>(o);
+        v.x += acc[i][0]; v.y += acc[i][1]; v.z += acc[i][2]; v.w += acc[i][3];
+        *reinterpret_cast<float4*>(o) = v;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(o + j, acc[i][j]);
+      }
+    }
+  }
+}
+
 #define CLM_TRAIN_DISPATCH_DIM(dim, CALL)                                     \
   switch (dim) {                                                              \
     case 128: { constexpr int NV = 1; CALL; break; }                          \
@@ -672,6 +758,35 @@ extern "C" int clm_cast_to_bf16(const float* in, void* out_bf16, long long n, fl
   const size_t n4 = static_cast<size_t>(n) / 4;
   cast_bf16_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(
       reinterpret_cast<const float4*>(in), static_cast<uint2*>(out_bf16), n4, scale);
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}
+
+extern "C" int clm_lora_wgrad_small(const void* dy_bf16, int ld_dy, int n_out, const void* t_bf16, int ld_t,
+                                    const void* x_bf16, int ld_x, int n_in, const void* u_bf16, int ld_u, int cols,
+                                    int rows, float* grad_b, float* grad_a_t, int deterministic, void* stream) {
+  CLM_REQUIRE(dy_bf16 && t_bf16 && x_bf16 && u_bf16 && grad_b && grad_a_t, "clm_lora_wgrad_small: null argument");
+  CLM_REQUIRE(rows >= 0 && n_out > 0 && n_in > 0 && cols > 0 && cols % 64 == 0 && n_out % 2 == 0 && n_in % 2 == 0 &&
+                  ld_dy % 2 == 0 && ld_t % 2 == 0 && ld_x % 2 == 0 && ld_u % 2 == 0 && ld_dy >= n_out && ld_x >= n_in &&
+                  ld_t >= cols && ld_u >= cols,
+              "clm_lora_wgrad_small: bad shape (cols a multiple of 64, feature counts and leading dims even)");
+  if (rows == 0) return CLM_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int blocks = ((n_out + 31) / 32 + (n_in + 31) / 32) * (cols / 64);
+  // few tiles: up to four CTAs share a tile's token rows (atomic adds, arrival order) unless reproducibility is asked for
+  int splits = 1;
+  if (!deterministic) {
+    splits = clm_num_sms() / blocks;
+    if (splits > 4) splits = 4;
+    if (splits > (rows + 127) / 128) splits = (rows + 127) / 128;
+    if (splits < 1) splits = 1;
+  }
+  ProfScope prof(CLM_K_GEMM, 2.0 * rows * cols * (static_cast<double>(n_out) + n_in),
+                 2.0 * rows * (static_cast<double>(n_out) + n_in + 2 * cols) + 8.0 * cols * (static_cast<double>(n_out) + n_in), s);
+  lora_wgrad_small_kernel<<<dim3(blocks, splits), 128, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(dy_bf16), ld_dy, n_out, static_cast<const __nv_bfloat16*>(t_bf16), ld_t,
+      static_cast<const __nv_bfloat16*>(x_bf16), ld_x, n_in, static_cast<const __nv_bfloat16*>(u_bf16), ld_u, cols, rows,
+      grad_b, grad_a_t);
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
 }

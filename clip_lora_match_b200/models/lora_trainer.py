@@ -64,6 +64,8 @@ class _Tower:
 
 
 class LoraTrainer:
+    SMALL_WGRAD_ROWS = 2048  # token rows up to which the LoRA weight gradients take the one-launch CUDA-core kernel
+
     def __init__(self, model: B200ClipModel, lr: float = 1e-4, weight_decay: float = 0.01,
                  max_grad_norm: float = 1.0, temperature: float = 0.07, betas: Tuple[float, float] = (0.9, 0.999),
                  eps: float = 1e-8, grad_accum_steps: int = 1, use_graph: bool = True, deterministic: bool = False):
@@ -392,6 +394,13 @@ class LoraTrainer:
             self._gemm(dy, wT, dx, a2=u, w2=ops["a_catT"][layer], M=rows, N=in_dim, K=n_out, K2=g.cols)
         gb = self._master(key, "b", self.grad)[layer]
         ga = self._master(key, "a", self.grad)[layer]
+        if rows <= self.SMALL_WGRAD_ROWS:
+            # few token rows: one CUDA-core launch instead of four transposes + two deep-K GEMMs (launch bound there)
+            tt = t.t[name][layer]
+            check(self.lib.clm_lora_wgrad_small(ptr(dy), dy.stride(0), n_out, ptr(tt), tt.stride(0), ptr(x), x.stride(0),
+                                                in_dim, ptr(u), u.stride(0), g.cols, rows, ptr(gb), ptr(ga),
+                                                int(self.deterministic), cur_stream()), "clm_lora_wgrad_small")
+            return
         self._transpose(dy, t.dyT, rows, n_out)
         self._transpose(t.t[name][layer], t.tT, rows, g.cols)
         self._gemm(t.dyT, t.tT, gb, accumulate=True, M=n_out, N=g.cols, K=rows, split_k=True)

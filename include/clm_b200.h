@@ -258,6 +258,18 @@ int clm_transpose_to_bf16(const void* in, int in_is_f32, long long ld_in, long l
 /* out = bf16(scale * in), n % 4 == 0 */
 int clm_cast_to_bf16(const float* in, void* out_bf16, long long n, float scale, void* stream);
 
+/* Both LoRA weight gradients of one adapted GEMM in ONE launch, for few token rows (the reference's batch of 8:
+ * 400 / 616 rows -- there the tensor-core route, four transposes and two deep-K clm_gemm_epi calls, is launch bound):
+ *   grad_b  [n_out, cols] += dy^T t      dy bf16 [rows, n_out], t = x A_cat^T bf16 [rows, cols]
+ *   grad_a_t [n_in, cols] += x^T u       x  bf16 [rows, n_in],  u = dy (sB_cat) bf16 [rows, cols]
+ * fp32 accumulation on the CUDA cores.  deterministic != 0: one CTA per output tile, bit-for-bit reproducible;
+ * 0: when there are fewer tiles than SMs up to four CTAs share a tile's rows and add their partial sums with atomics
+ * (reproducible to fp32 rounding).  cols a multiple of 64.  The gradients PEFT's autograd
+ * produces for lora_B / lora_A (models/lora_adapter.py:35-42) in the fused layouts of models/lora_trainer.py. */
+int clm_lora_wgrad_small(const void* dy_bf16, int ld_dy, int n_out, const void* t_bf16, int ld_t, const void* x_bf16,
+                         int ld_x, int n_in, const void* u_bf16, int ld_u, int cols, int rows, float* grad_b,
+                         float* grad_a_t, int deterministic, void* stream);
+
 /* Backward of clm_attention: qkv as in the forward, dout bf16 [batch*tokens, dim] -> dqkv bf16
  * [batch*tokens, 3*dim] (dq | dk | dv).  P is recomputed from q and k (fp32 softmax, modeling_clip.py:261-279).
  * scratch: clm_attention_bwd_scratch_bytes() of device memory (P and dS, transposed, between the two kernels).

@@ -461,3 +461,40 @@ def test_split_k_weight_gradients(cuda_device):
     a = torch.randn((300, 4096), generator=g).to(cuda_device, torch.bfloat16)
     w = torch.randn((64, 4096), generator=g).to(cuda_device, torch.bfloat16)
     assert torch.equal(K.gemm_epi(a, w, act=L.EPI_SPLIT_K), K.gemm_epi(a, w))
+
+
+def test_lora_wgrad_small_vs_torch(cuda_device):
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(13)
+    for rows, n_out, n_in, cols in [(400, 2304, 768, 64), (616, 512, 512, 64), (77, 256, 128, 128), (33, 130, 66, 64)]:
+        dy = torch.randn((rows, n_out), generator=g).to(cuda_device, torch.bfloat16)
+        t = torch.randn((rows, cols), generator=g).to(cuda_device, torch.bfloat16)
+        x = torch.randn((rows, n_in), generator=g).to(cuda_device, torch.bfloat16)
+        u = torch.randn((rows, cols), generator=g).to(cuda_device, torch.bfloat16)
+        gb0 = torch.randn((n_out, cols), generator=g).to(cuda_device)
+        ga0 = torch.randn((n_in, cols), generator=g).to(cuda_device)
+        for det in (1, 0):  # one CTA per tile / up to four CTAs per tile adding with atomics
+            gb, ga = gb0.clone(), ga0.clone()
+            L.check(lib.clm_lora_wgrad_small(dy.data_ptr(), n_out, n_out, t.data_ptr(), cols, x.data_ptr(), n_in, n_in,
+                                             u.data_ptr(), cols, cols, rows, gb.data_ptr(), ga.data_ptr(), det, _st()))
+            assert torch.allclose(gb, gb0 + dy.float().t() @ t.float(), rtol=1e-4, atol=1e-3)
+            assert torch.allclose(ga, ga0 + x.float().t() @ u.float(), rtol=1e-4, atol=1e-3)
+
+
+def test_small_and_tensor_core_weight_gradients_agree(cuda_device):
+    """The same micro-batch through the one-launch CUDA-core weight-gradient kernel (few rows) and through the
+    transposes + tcgen05 GEMMs (forced): the same gradients up to bf16-product / fp32-order rounding."""
+    from clip_lora_match_b200.models.lora_trainer import LoraTrainer
+
+    targets = ("q_proj", "k_proj", "v_proj", "out_proj")
+    pv = O.synth_images(6, seed=2)
+    ids, mask = O.synth_captions(6, seed=3)
+    flats = []
+    for small_rows in (LoraTrainer.SMALL_WGRAD_ROWS, 0):
+        _, gpu = _pair("tiny-test", 8, 16, targets, cuda_device)
+        tr = LoraTrainer(gpu, use_graph=False, deterministic=True)
+        tr.SMALL_WGRAD_ROWS = small_rows
+        tr.forward_backward(pv.to(cuda_device), ids.to(cuda_device), mask.to(cuda_device))
+        flats.append((tr.grad * tr.mult).clone())
+    assert _cos(flats[0], flats[1]) > 0.999999
+    assert float((flats[0] - flats[1]).abs().max()) <= 1e-4 * float(flats[1].abs().max()) + 1e-7

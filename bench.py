@@ -609,9 +609,10 @@ def main():
     # The reference's own training configuration (config/lora_config.yaml: ViT-B/32, r = 8 on q,k,v,out, batch 8,
     # temperature 0.07, AdamW + clip) and a batch of 256: forward + backward + clip + AdamW per step through
     # LoraTrainer.step (CUDA-graph replay), device-resident inputs, and end to end from pinned host inputs with
-    # the loss read back.  One process (the reference's training is single process): N = 1 only.
+    # the loss read back.  N > 1: data-parallel (an extension: the reference's script is one process) -- every rank
+    # steps on its own batch and the flat fp32 gradient buffer is all-reduced once per step over NCCL (weak scaling).
     train = None
-    if world == 1 and not args.no_train:
+    if not args.no_train:
         from clip_lora_match_b200.models.lora_trainer import LoraTrainer
 
         arch_t = CM.arch_from_name(TRAIN_ARCH)
@@ -623,10 +624,11 @@ def main():
             model_t = CM.B200ClipModel(arch_t, sd_t, device=dev)
             model_t.set_lora(init_lora_adapter(model_t.linear_dims(), LoraConfig(r=8, lora_alpha=16, target_modules=TRAIN_TARGETS),
                                                seed=1, base_model_name=TRAIN_ARCH))
-            tr = LoraTrainer(model_t, lr=1e-4, weight_decay=0.01, max_grad_norm=1.0, temperature=0.07)
-            gt = torch.Generator(device=dev).manual_seed(8)
+            tr = LoraTrainer(model_t, lr=1e-4, weight_decay=0.01, max_grad_norm=1.0, temperature=0.07,
+                             distributed=world > 1)
+            gt = torch.Generator(device=dev).manual_seed(8 + rank)
             pv_t = torch.randn((tb, 3, 224, 224), generator=gt, device=dev)
-            ids_t = synth_captions(tb, seed=9)[0].to(dev, torch.int32)
+            ids_t = synth_captions(tb, seed=9 + rank)[0].to(dev, torch.int32)
             pv_h, ids_h = pv_t.cpu().pin_memory(), ids_t.cpu().pin_memory()
             for _ in range(max(args.warmup, 3)):
                 tr.step(pv_t, ids_t)
@@ -644,8 +646,10 @@ def main():
             prof_t = {kn: _lib.prof_summary(kn) for kn in ("gemm", "attention", "elementwise")}
             lib.clm_prof_enable(0)
             train["batches"][str(tb)] = {
-                "pairs_per_s": tb * args.steps / (ms_t / 1e3), "ms_per_step": ms_t / args.steps,
-                "e2e_pairs_per_s": tb * args.steps / (ms_te / 1e3), "e2e_ms_per_step": ms_te / args.steps,
+                "pairs_per_s": tb * world * args.steps / (ms_t / 1e3), "ms_per_step": ms_t / args.steps,
+                "e2e_pairs_per_s": tb * world * args.steps / (ms_te / 1e3), "e2e_ms_per_step": ms_te / args.steps,
+                "batch_per_gpu": tb, "n_gpus": world, "scaling": "weak",
+                "exchange_bytes_per_step": (tr.grad.numel() * 4 + 4) if world > 1 else 0,
                 "h2d_bytes_per_step": pv_h.numel() * 4 + ids_h.numel() * 4, "d2h_bytes_per_step": 4,
                 "launches_per_step": int(launches_t), "trainable_parameters": tr.num_trainable_parameters(),
                 "loss_first_last": [loss_last[0], loss_last[-1]],
@@ -654,7 +658,7 @@ def main():
                                          for k, v in prof_t.items()}}
             del tr, model_t
             torch.cuda.empty_cache()
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_train_rate()
             train["cpu_baseline"] = {"value": v, "unit": "image-caption pairs/s", "cores": cores, "kind": "port",
                                      "sample": sample}

@@ -47,6 +47,20 @@ def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+def allreduce_gradients(grad: torch.Tensor, loss: Optional[torch.Tensor] = None, group=None) -> None:
+    """The exchange step of data-parallel training: ONE all-reduce (sum) of the flat gradient buffer -- every rank has
+    already scaled its loss by 1 / (grad_accum_steps * world), so the sum IS the mean gradient over the global batch --
+    and one 4-byte all-reduce of the scaled loss, which then reads as the mean loss over the ranks.  NCCL on the GPUs
+    (NVLink; 4 MB for ViT-B/32 with r = 8), gloo in the CPU tests.  No-op without an initialised process group."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+    if loss is not None:
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+
+
 class _Group:
     """One fused GEMM's adapters over all layers of a tower."""
 
@@ -68,7 +82,8 @@ class LoraTrainer:
 
     def __init__(self, model: B200ClipModel, lr: float = 1e-4, weight_decay: float = 0.01,
                  max_grad_norm: float = 1.0, temperature: float = 0.07, betas: Tuple[float, float] = (0.9, 0.999),
-                 eps: float = 1e-8, grad_accum_steps: int = 1, use_graph: bool = True, deterministic: bool = False):
+                 eps: float = 1e-8, grad_accum_steps: int = 1, use_graph: bool = True, deterministic: bool = False,
+                 distributed: bool = False):
         if model.lora is None:
             raise ValueError("LoraTrainer needs a model with a LoRA adapter (attach_lora_to_clip first)")
         self.model = model
@@ -79,6 +94,17 @@ class LoraTrainer:
         self.temperature, self.betas, self.eps = float(temperature), betas, float(eps)
         self.grad_accum_steps = int(grad_accum_steps)
         self.use_graph = use_graph
+        # data-parallel training (an extension: the reference's script is one process): every rank runs the step on
+        # its own micro-batch and the flat gradient buffer is all-reduced once before the optimizer; the loss is the
+        # mean over ranks of the local InfoNCE losses (negatives are NOT shared across ranks), i.e. exactly what
+        # gradient_accumulation_steps = world would compute in one process
+        self.world = 1
+        if distributed:
+            import torch.distributed as dist
+
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("distributed=True needs an initialised torch.distributed process group")
+            self.world = dist.get_world_size()
         # False: the weight-gradient GEMMs may split K (partial products added through the L2 in arrival order:
         # reproducible to fp32 rounding); True: one work unit per tile, every step reproducible bit for bit
         self.deterministic = deterministic
@@ -441,7 +467,7 @@ class LoraTrainer:
     def _loss(self, batch: int, with_grad: bool) -> None:
         v, x = self._towers["vision"], self._towers["text"]
         check(self.lib.clm_clip_loss(ptr(v.feat), ptr(x.feat), batch, self.arch.proj_dim, self.temperature,
-                                     1.0 / self.grad_accum_steps if with_grad else 1.0, ptr(self.loss_dev),
+                                     1.0 / (self.grad_accum_steps * self.world) if with_grad else 1.0, ptr(self.loss_dev),
                                      ptr(v.dfeat) if with_grad else None, ptr(x.dfeat) if with_grad else None,
                                      ptr(v.dfeat_bf) if with_grad else None, ptr(x.dfeat_bf) if with_grad else None,
                                      ptr(self.loss_ws), self.loss_ws.numel(), cur_stream()), "clm_clip_loss")
@@ -498,6 +524,8 @@ class LoraTrainer:
     def optimizer_step(self, lr: Optional[float] = None) -> None:
         """clip_grad_norm_ + AdamW + zero_grad (train_lora.py:190-193) and the refresh of the bf16 operands."""
         self._set_hyper(self.lr if lr is None else float(lr))
+        if self.world > 1:
+            allreduce_gradients(self.grad)
         self._optimizer()
         self.opt_step += 1
         self._micro = 0
@@ -510,24 +538,35 @@ class LoraTrainer:
             raise ValueError("step() is the fused path for grad_accum_steps == 1; use forward_backward / optimizer_step")
         b = self._load_inputs(pixel_values, input_ids, attention_mask)
         self._set_hyper(self.lr if lr is None else float(lr))
+        def exchange():
+            if self.world > 1:
+                allreduce_gradients(self.grad, self.loss_dev)
+
         if not self.use_graph or self.lib.clm_prof_is_enabled():
             self._forward_backward(b)
+            exchange()
             self._optimizer()
         elif self._graph_state == 0:
             self._forward_backward(b)  # eager once: one-time cudaFuncSetAttribute calls must not fall into a capture
+            exchange()
             self._optimizer()
             self._graph_state = 1
         else:
             if self._graph_state == 1:
+                # two graphs -- forward + backward, then clip + AdamW + operand refresh -- with the gradient all-reduce
+                # (data-parallel training) between them on the same stream
                 n0 = self.lib.clm_launch_count()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_fb, capture_error_mode="thread_local"):
                     self._forward_backward(b)
+                with torch.cuda.graph(g_opt, capture_error_mode="thread_local"):
                     self._optimizer()
                 self._graph_launches = self.lib.clm_launch_count() - n0
                 self.lib.clm_launch_count_add(-self._graph_launches)
-                self._graph, self._graph_state = graph, 2
+                self._graph, self._graph_opt, self._graph_state = g_fb, g_opt, 2
             self._graph.replay()
+            exchange()
+            self._graph_opt.replay()
             self.lib.clm_launch_count_add(self._graph_launches)
         self.opt_step += 1
         return self.loss_dev

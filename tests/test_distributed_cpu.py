@@ -101,3 +101,57 @@ def test_query_rows_are_split_over_ranks_and_gathered_back():
     ret = mgr.dict()
     mp.spawn(_gather_worker, args=(2, port, 7, 16, ret), nprocs=2, join=True)
     assert all(ret.get(r) for r in range(2)), dict(ret)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# data-parallel LoRA training: the one exchange step (models/lora_trainer.allreduce_gradients)
+# ------------------------------------------------------------------------------------------------------------
+def _train_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from clip_lora_match_b200.models.lora_trainer import allreduce_gradients
+        from oracle import train_oracle as T
+
+        torch.set_num_threads(2)
+        targets = ("q_proj", "v_proj")
+
+        def flat(oracle):
+            return torch.cat([torch.cat([a.flatten(), b.flatten()]) for a, b in oracle.gradients().values()])
+
+        # every rank: its own micro-batch, loss scaled by 1 / world (the oracle stands in for the CUDA step here)
+        model = O.build_model("tiny-test", seed=0)
+        O.synthetic_lora(model, 8, 16, targets, seed=1)
+        oracle = T.TrainOracle(model, grad_accum_steps=world)
+        pv = O.synth_images(3, seed=20 + rank)
+        ids, mask = O.synth_captions(3, seed=30 + rank)
+        loss = torch.tensor([oracle.forward_backward(pv, ids, mask)])
+        grad = flat(oracle)
+        allreduce_gradients(grad, loss)  # ONE all-reduce of the flat gradient (+ 4 bytes of loss)
+        # checker: one process accumulating the same micro-batches (train_lora.py:186-190)
+        model2 = O.build_model("tiny-test", seed=0)
+        O.synthetic_lora(model2, 8, 16, targets, seed=1)
+        acc = T.TrainOracle(model2, grad_accum_steps=world)
+        total = 0.0
+        for r in range(world):
+            total += acc.forward_backward(O.synth_images(3, seed=20 + r), *O.synth_captions(3, seed=30 + r))
+        ref = flat(acc)
+        ret[rank] = bool(torch.allclose(grad, ref, rtol=1e-4, atol=1e-7) and abs(loss.item() - total) < 1e-5)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_training_exchange_equals_gradient_accumulation():
+    world, port = 2, _free_port()
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_train_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_allreduce_gradients_is_a_noop_without_a_process_group():
+    from clip_lora_match_b200.models.lora_trainer import allreduce_gradients
+
+    g = torch.arange(8, dtype=torch.float32)
+    allreduce_gradients(g, torch.ones(1))
+    assert torch.equal(g, torch.arange(8, dtype=torch.float32))

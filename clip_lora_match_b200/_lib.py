@@ -66,6 +66,10 @@ SIGNATURES = {
     "clm_version": (_I, []),
     "clm_device_check": (_I, []),
     "clm_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
+    "clm_layernorm_ex": (_I, [_P, _I, _P, _P, _P, _I, _I, _F, _P]),
+    "clm_embed_text_ex": (_I, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "clm_vision_embed_ln_ex": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "clm_pool_ln_ex": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "clm_fuse_normalize": (_I, [_P, _F, _P, _F, _P, _P, _I, _I, _P]),
     "clm_preprocess_workspace_bytes": (C.c_size_t, [_P, _I, _I]),
     "clm_preprocess_images": (_I, [_P, _I, _I, _P, _P, _P, _P, C.c_size_t, _P]),
@@ -94,6 +98,8 @@ SIGNATURES = {
                               C.POINTER(LayerWeights), C.POINTER(_P)]),
     "clm_tower_destroy": (None, [_P]),
     "clm_tower_workspace_bytes": (C.c_size_t, [_P, _I]),
+    "clm_tower_set_residual_dtype": (_I, [_P, _I]),
+    "clm_tower_residual_dtype": (_I, [_P]),
     "clm_encode_image": (_I, [_P, _P, _I, _P, _I, _P, C.c_size_t, _P]),
     "clm_encode_text": (_I, [_P, _P, _I, _P, _I, _P, C.c_size_t, _P]),
     "clm_encode_text_len": (_I, [_P, _P, _I, _I, _P, _I, _P, C.c_size_t, _P]),

@@ -19,6 +19,16 @@ struct Row {
 #pragma unroll
     for (int j = 0; j < NV; ++j) v[j] = p4[j * 32 + lane_id()];
   }
+  // the bf16 residual stream: 4 bf16 (8 bytes) per lane and vector, same column ownership as the fp32 form
+  __device__ __forceinline__ void load_bf16(const __nv_bfloat16* p) {
+    const uint2* p2 = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const uint2 u = p2[j * 32 + lane_id()];
+      v[j].x = __uint_as_float(u.x << 16); v[j].y = __uint_as_float(u.x & 0xffff0000u);
+      v[j].z = __uint_as_float(u.y << 16); v[j].w = __uint_as_float(u.y & 0xffff0000u);
+    }
+  }
   __device__ __forceinline__ void add(const float* p) {
     const float4* p4 = reinterpret_cast<const float4*>(p);
 #pragma unroll
@@ -70,22 +80,24 @@ struct Row {
   }
 };
 
-template <int NV>
+// kH16: the residual stream (x / h below) is bf16 instead of fp32
+template <int NV, bool kH16 = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows, float eps) {
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
   constexpr int D = NV * 128;
   Row<NV> r;
-  r.load(x + static_cast<size_t>(row) * D);
+  if (kH16) r.load_bf16(static_cast<const __nv_bfloat16*>(x) + static_cast<size_t>(row) * D);
+  else r.load(static_cast<const float*>(x) + static_cast<size_t>(row) * D);
   r.layernorm(gamma, beta, eps);
   r.store_bf16(y + static_cast<size_t>(row) * D);
 }
 
-template <int NV>
+template <int NV, bool kH16 = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-pool_ln_kernel(const float* __restrict__ h, const int32_t* __restrict__ row_idx,
+pool_ln_kernel(const void* __restrict__ h, const int32_t* __restrict__ row_idx,
                const float* __restrict__ gamma, const float* __restrict__ beta,
                __nv_bfloat16* __restrict__ y, int batch, int tokens, float eps) {
   const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -93,16 +105,18 @@ pool_ln_kernel(const float* __restrict__ h, const int32_t* __restrict__ row_idx,
   constexpr int D = NV * 128;
   const int t = row_idx ? row_idx[b] : 0;
   Row<NV> r;
-  r.load(h + (static_cast<size_t>(b) * tokens + t) * D);
+  const size_t off = (static_cast<size_t>(b) * tokens + t) * D;
+  if (kH16) r.load_bf16(static_cast<const __nv_bfloat16*>(h) + off);
+  else r.load(static_cast<const float*>(h) + off);
   r.layernorm(gamma, beta, eps);
   r.store_bf16(y + static_cast<size_t>(b) * D);
 }
 
-template <int NV>
+template <int NV, bool kH16 = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 vision_embed_ln_kernel(const float* __restrict__ patch_out, const float* __restrict__ class_emb,
                        const float* __restrict__ pos_emb, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, float* __restrict__ h, int batch, int np,
+                       const float* __restrict__ beta, void* __restrict__ h, int batch, int np,
                        float eps) {
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int tokens = np + 1;
@@ -115,13 +129,14 @@ vision_embed_ln_kernel(const float* __restrict__ patch_out, const float* __restr
   else r.load(patch_out + (static_cast<size_t>(b) * np + (t - 1)) * D);
   r.add(pos_emb + static_cast<size_t>(t) * D);
   r.layernorm(gamma, beta, eps);
-  r.store_f32(h + static_cast<size_t>(row) * D);
+  if (kH16) r.store_bf16(static_cast<__nv_bfloat16*>(h) + static_cast<size_t>(row) * D);
+  else r.store_f32(static_cast<float*>(h) + static_cast<size_t>(row) * D);
 }
 
-template <int NV>
+template <int NV, bool kH16 = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 embed_text_kernel(const int32_t* __restrict__ ids, const float* __restrict__ tok_emb,
-                  const float* __restrict__ pos_emb, float* __restrict__ h, int rows, int tokens,
+                  const float* __restrict__ pos_emb, void* __restrict__ h, int rows, int tokens,
                   int vocab) {
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -132,7 +147,8 @@ embed_text_kernel(const int32_t* __restrict__ ids, const float* __restrict__ tok
   Row<NV> r;
   r.load(tok_emb + static_cast<size_t>(id) * D);
   r.add(pos_emb + static_cast<size_t>(t) * D);
-  r.store_f32(h + static_cast<size_t>(row) * D);
+  if (kH16) r.store_bf16(static_cast<__nv_bfloat16*>(h) + static_cast<size_t>(row) * D);
+  else r.store_f32(static_cast<float*>(h) + static_cast<size_t>(row) * D);
 }
 
 // eos_pos[b] = first t with ids[b,t] == eos_id, else 0 (argmax of an all-zero mask)
@@ -288,16 +304,28 @@ inline int blocks_for(int rows) { return (rows + kWarpsPerBlock - 1) / kWarpsPer
 
 }  // namespace
 
-extern "C" int clm_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16,
-                             int rows, int dim, float eps, void* stream) {
+extern "C" int clm_layernorm_ex(const void* x, int x_dtype, const float* gamma, const float* beta, void* y_bf16,
+                                int rows, int dim, float eps, void* stream) {
   CLM_REQUIRE(x && gamma && beta && y_bf16 && rows >= 0, "clm_layernorm: bad argument");
+  CLM_REQUIRE(x_dtype == CLM_OUT_F32 || x_dtype == CLM_OUT_BF16, "clm_layernorm: x_dtype must be CLM_OUT_F32 / CLM_OUT_BF16");
   if (rows == 0) return CLM_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 6.0 * rows * dim, s);
-  CLM_DISPATCH_DIM(dim, (layernorm_kernel<NV><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
-                            x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), rows, eps)));
+  const bool h16 = x_dtype == CLM_OUT_BF16;
+  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, (h16 ? 4.0 : 6.0) * rows * dim, s);
+  if (h16) {
+    CLM_DISPATCH_DIM(dim, (layernorm_kernel<NV, true><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
+                              x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), rows, eps)));
+  } else {
+    CLM_DISPATCH_DIM(dim, (layernorm_kernel<NV, false><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
+                              x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), rows, eps)));
+  }
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
+}
+
+extern "C" int clm_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                             int rows, int dim, float eps, void* stream) {
+  return clm_layernorm_ex(x, CLM_OUT_F32, gamma, beta, y_bf16, rows, dim, eps, stream);
 }
 
 extern "C" int clm_l2norm(const float* x, float* y, void* y_bf16_or_null, int rows, int dim,
@@ -325,13 +353,26 @@ extern "C" int clm_fuse_normalize(const float* a, float wa, const float* b_or_nu
 extern "C" int clm_embed_text(const int32_t* ids, const float* tok_emb, const float* pos_emb,
                               float* h, int32_t* eos_pos, int batch, int tokens, int dim, int vocab,
                               int eos_id, void* stream) {
+  return clm_embed_text_ex(ids, tok_emb, pos_emb, h, CLM_OUT_F32, eos_pos, batch, tokens, dim, vocab, eos_id, stream);
+}
+
+extern "C" int clm_embed_text_ex(const int32_t* ids, const float* tok_emb, const float* pos_emb,
+                                 void* h, int h_dtype, int32_t* eos_pos, int batch, int tokens, int dim, int vocab,
+                                 int eos_id, void* stream) {
   CLM_REQUIRE(ids && tok_emb && pos_emb && h && batch >= 0 && tokens > 0, "clm_embed_text: bad argument");
+  CLM_REQUIRE(h_dtype == CLM_OUT_F32 || h_dtype == CLM_OUT_BF16, "clm_embed_text: h_dtype must be CLM_OUT_F32 / CLM_OUT_BF16");
   if (batch == 0) return CLM_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int rows = batch * tokens;
-  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 8.0 * rows * dim, s);
-  CLM_DISPATCH_DIM(dim, (embed_text_kernel<NV><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
-                            ids, tok_emb, pos_emb, h, rows, tokens, vocab)));
+  const bool h16 = h_dtype == CLM_OUT_BF16;
+  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, (h16 ? 6.0 : 8.0) * rows * dim, s);
+  if (h16) {
+    CLM_DISPATCH_DIM(dim, (embed_text_kernel<NV, true><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
+                              ids, tok_emb, pos_emb, h, rows, tokens, vocab)));
+  } else {
+    CLM_DISPATCH_DIM(dim, (embed_text_kernel<NV, false><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
+                              ids, tok_emb, pos_emb, h, rows, tokens, vocab)));
+  }
   if (eos_pos)
     eos_pos_kernel<<<blocks_for(batch), kWarpsPerBlock * 32, 0, s>>>(ids, eos_pos, batch, tokens,
                                                                      eos_id);
@@ -359,14 +400,29 @@ extern "C" int clm_patch_im2col(const float* pixel_values, void* patches_bf16, i
 extern "C" int clm_vision_embed_ln(const float* patch_out, const float* class_emb,
                                    const float* pos_emb, const float* gamma, const float* beta,
                                    float* h, int batch, int np, int dim, float eps, void* stream) {
+  return clm_vision_embed_ln_ex(patch_out, class_emb, pos_emb, gamma, beta, h, CLM_OUT_F32, batch, np, dim, eps,
+                                stream);
+}
+
+extern "C" int clm_vision_embed_ln_ex(const float* patch_out, const float* class_emb,
+                                      const float* pos_emb, const float* gamma, const float* beta,
+                                      void* h, int h_dtype, int batch, int np, int dim, float eps, void* stream) {
   CLM_REQUIRE(patch_out && class_emb && pos_emb && gamma && beta && h && batch >= 0 && np > 0,
               "clm_vision_embed_ln: bad argument");
+  CLM_REQUIRE(h_dtype == CLM_OUT_F32 || h_dtype == CLM_OUT_BF16,
+              "clm_vision_embed_ln: h_dtype must be CLM_OUT_F32 / CLM_OUT_BF16");
   if (batch == 0) return CLM_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int rows = batch * (np + 1);
-  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 8.0 * rows * dim, s);
-  CLM_DISPATCH_DIM(dim, (vision_embed_ln_kernel<NV><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
-                            patch_out, class_emb, pos_emb, gamma, beta, h, batch, np, eps)));
+  const bool h16 = h_dtype == CLM_OUT_BF16;
+  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, (h16 ? 6.0 : 8.0) * rows * dim, s);
+  if (h16) {
+    CLM_DISPATCH_DIM(dim, (vision_embed_ln_kernel<NV, true><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
+                              patch_out, class_emb, pos_emb, gamma, beta, h, batch, np, eps)));
+  } else {
+    CLM_DISPATCH_DIM(dim, (vision_embed_ln_kernel<NV, false><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
+                              patch_out, class_emb, pos_emb, gamma, beta, h, batch, np, eps)));
+  }
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
 }
@@ -374,13 +430,27 @@ extern "C" int clm_vision_embed_ln(const float* patch_out, const float* class_em
 extern "C" int clm_pool_ln(const float* h, const int32_t* row_idx_or_null, const float* gamma,
                            const float* beta, void* y_bf16, int batch, int tokens, int dim, float eps,
                            void* stream) {
+  return clm_pool_ln_ex(h, CLM_OUT_F32, row_idx_or_null, gamma, beta, y_bf16, batch, tokens, dim, eps, stream);
+}
+
+extern "C" int clm_pool_ln_ex(const void* h, int h_dtype, const int32_t* row_idx_or_null, const float* gamma,
+                              const float* beta, void* y_bf16, int batch, int tokens, int dim, float eps,
+                              void* stream) {
   CLM_REQUIRE(h && gamma && beta && y_bf16 && batch >= 0 && tokens > 0, "clm_pool_ln: bad argument");
+  CLM_REQUIRE(h_dtype == CLM_OUT_F32 || h_dtype == CLM_OUT_BF16, "clm_pool_ln: h_dtype must be CLM_OUT_F32 / CLM_OUT_BF16");
   if (batch == 0) return CLM_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 6.0 * batch * dim, s);
-  CLM_DISPATCH_DIM(dim, (pool_ln_kernel<NV><<<blocks_for(batch), kWarpsPerBlock * 32, 0, s>>>(
-                            h, row_idx_or_null, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16),
-                            batch, tokens, eps)));
+  const bool h16 = h_dtype == CLM_OUT_BF16;
+  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, (h16 ? 4.0 : 6.0) * batch * dim, s);
+  if (h16) {
+    CLM_DISPATCH_DIM(dim, (pool_ln_kernel<NV, true><<<blocks_for(batch), kWarpsPerBlock * 32, 0, s>>>(
+                              h, row_idx_or_null, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16),
+                              batch, tokens, eps)));
+  } else {
+    CLM_DISPATCH_DIM(dim, (pool_ln_kernel<NV, false><<<blocks_for(batch), kWarpsPerBlock * 32, 0, s>>>(
+                              h, row_idx_or_null, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16),
+                              batch, tokens, eps)));
+  }
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
 }

@@ -70,6 +70,8 @@ constexpr int kEpiLegacy = 0;     // per-thread global loads/stores; residual !=
 constexpr int kEpiStoreBf16 = 1;  // TMA store of bf16 tiles
 constexpr int kEpiStoreF32 = 2;   // TMA store of fp32 tiles
 constexpr int kEpiReduceF32 = 3;  // TMA reduce-add of fp32 tiles: out (== residual) += acc + bias
+constexpr int kEpiReduceBf16 = 4; // TMA reduce-add of bf16 tiles into a bf16 residual stream (out == residual, bf16):
+                                  // the L2 adds bf16(acc + bias) to the stored bf16 value, one rounding per update
 
 struct EpiParams {
   void* out;
@@ -289,7 +291,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // p ^ (r & 7) -- the SWIZZLE_128B pattern of the output tensor map, and conflict-free for the
     // eight lanes of every shared-memory wavefront.  One elected lane then hands the 32-row slab to
     // the TMA unit; the buffer is reused once the unit has READ it (wait_group.read).
-    constexpr bool kF32 = (kEpi != kEpiStoreBf16);
+    constexpr bool kF32 = (kEpi == kEpiStoreF32 || kEpi == kEpiReduceF32);
     constexpr int kSlabCols = kF32 ? 32 : 64;
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains
@@ -393,7 +395,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (kEpi == kEpiReduceF32) tma_reduce_add_2d(&map_out, stg, col0, m0);
+            if (kEpi == kEpiReduceF32 || kEpi == kEpiReduceBf16) tma_reduce_add_2d(&map_out, stg, col0, m0);
             else tma_store_2d(&map_out, stg, col0, m0);
             bulk_commit();
           }
@@ -625,10 +627,12 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
   }
   int epi = ep.out_f32 ? kEpiStoreF32 : kEpiStoreBf16;
   if (residual) {
-    const bool in_place = ep.out_f32 && residual == static_cast<const float*>(out) && ldr == ldo;
-    epi = in_place ? kEpiReduceF32 : kEpiLegacy;
+    // residual == out (same address, same pitch) is the in-place update of the residual stream, in the stream's own
+    // type: fp32, or bf16 when out_dtype says so (the pointer is then a bf16 buffer despite its declared type)
+    const bool in_place = residual == static_cast<const float*>(out) && ldr == ldo;
+    epi = in_place ? (ep.out_f32 ? kEpiReduceF32 : kEpiReduceBf16) : kEpiLegacy;
   }
-  if (force_legacy) epi = kEpiLegacy;
+  if (force_legacy && epi != kEpiReduceBf16) epi = kEpiLegacy;  // (the legacy path reads an fp32 residual)
   CUtensorMap mo = ma;
   if (epi != kEpiLegacy) {
     if ((rc = clm_make_tmap_2d(&mo, out, M, N, ldo, ep.out_f32 ? 4 : 2, ep.out_f32 ? 32 : 64, 32))) return rc;
@@ -641,7 +645,7 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
   // cut K so that every SM has a work unit, but keep at least 8 k-blocks per unit.
   ep.ksplit = 1;
   ep.kb_per = kb_main + kb_ext;
-  if (epi == kEpiReduceF32 && (epilogue & CLM_EPI_SPLIT_K)) {
+  if ((epi == kEpiReduceF32) && (epilogue & CLM_EPI_SPLIT_K)) {
     const long long sms = clm_num_sms();
     const long long tiles = pair ? static_cast<long long>((M + 255) / 256) * (N / 256)
                                  : static_cast<long long>((M + BM - 1) / BM) * ((N + BN - 1) / BN);
@@ -659,7 +663,7 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
   const double flops = 2.0 * M * N * (static_cast<double>(K) + (has_ext ? K2 : 0));
   const double bytes = 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) +
                        static_cast<double>(M) * N * (ep.out_f32 ? 4 : 2) +
-                       (residual ? 4.0 * M * N : 0.0);
+                       (residual ? (epi == kEpiReduceBf16 ? 2.0 : 4.0) * M * N : 0.0);
   ProfScope prof(CLM_K_GEMM, flops, bytes, stream);
   switch (epi) {
     case kEpiStoreBf16:
@@ -668,6 +672,8 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
       return launch_gemm_bn<kEpiStoreF32>(pair, BN, ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
     case kEpiReduceF32:
       return launch_gemm_bn<kEpiReduceF32>(pair, BN, ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
+    case kEpiReduceBf16:
+      return launch_gemm_bn<kEpiReduceBf16>(pair, BN, ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
     default:
       return launch_gemm_bn<kEpiLegacy>(pair, BN, ma, mb, ma2, mb2, mo, M, N, kb_main, kb_ext, ep, stream);
   }

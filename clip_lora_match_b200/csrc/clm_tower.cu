@@ -4,12 +4,13 @@
 // peft LoRA wrappers: a fixed sequence of stream-ordered launches, no allocation, no host
 // synchronisation (CUDA-graph capturable by the caller).
 //
-// Residual stream: fp32 [rows, D] ("h").  GEMM operands: bf16.  Per layer:
+// Residual stream: fp32 [rows, D] ("h"), or bf16 after clm_tower_set_residual_dtype(CLM_OUT_BF16).  GEMM operands:
+// bf16.  Per layer:
 //   x   = LN1(h)                                   (bf16)
 //   t   = x A_qkv^T                                (bf16 [rows,64], LoRA down-projection)
 //   qkv = x W_qkv^T + t (sB)_qkv^T + b             (bf16 [rows,3D])   <- LoRA fused as K-extension
 //   ao  = attention(qkv)                           (bf16 [rows,D])
-//   h  += ao W_o^T (+ LoRA) + b_o                  (fp32, in place)
+//   h  += ao W_o^T (+ LoRA) + b_o                  (in place, in the stream's type: TMA reduce-add)
 //   x   = LN2(h)
 //   g   = quickgelu(x W_1^T + b_1)                 (bf16 [rows,mlp])
 //   h  += g W_2^T + b_2
@@ -31,6 +32,7 @@ struct clm_tower {
   std::vector<clm_layer_weights> layers;
   int kpad;  // padded im2col width (vision)
   int np;    // patches per image (vision)
+  int h_dtype = CLM_OUT_F32;  // residual stream: fp32 (reference) or bf16 (clm_tower_set_residual_dtype)
 };
 
 namespace {
@@ -48,7 +50,7 @@ inline int max_lora_cols(const clm_tower_config& c) {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-  float* h;
+  void* h;  // residual stream, fp32 or bf16 (clm_tower::h_dtype)
   __nv_bfloat16* x;
   __nv_bfloat16* ao;
   __nv_bfloat16* qkv;
@@ -71,7 +73,7 @@ Workspace carve(const clm_tower* tw, int batch, uint8_t* base, int tokens = 0) {
     return p;
   };
   Workspace ws;
-  ws.h = reinterpret_cast<float*>(take(rows * c.width * 4));
+  ws.h = take(rows * c.width * (tw->h_dtype == CLM_OUT_BF16 ? 2 : 4));
   ws.x = reinterpret_cast<__nv_bfloat16*>(take(rows * c.width * 2));
   ws.ao = reinterpret_cast<__nv_bfloat16*>(take(rows * c.width * 2));
   size_t qkv_bytes = rows * 3 * c.width * 2;
@@ -118,9 +120,11 @@ int run_layers(clm_tower* tw, const Workspace& ws, int batch, const int32_t* poo
   const int rows = batch * tokens;
   const int D = c.width;
   void* sv = static_cast<void*>(s);
+  const int hd = tw->h_dtype;
+  const float* hres = static_cast<const float*>(ws.h);  // in-place residual: same pointer as `out`, type per hd
   for (int l = 0; l < c.layers; ++l) {
     const clm_layer_weights& L = tw->layers[l];
-    CLM_TRY(clm_layernorm(ws.h, L.ln1_g, L.ln1_b, ws.x, rows, D, c.ln_eps, sv));
+    CLM_TRY(clm_layernorm_ex(ws.h, hd, L.ln1_g, L.ln1_b, ws.x, rows, D, c.ln_eps, sv));
     // LoRA (unmerged): t = x A_cat^T is a skinny GEMM, then (t, (s B)_cat) ride along as extra K blocks
     const int cq = (c.lora_cols_qkv > 0 && L.lora_a_qkv && L.lora_b_qkv) ? c.lora_cols_qkv : 0;
     if (cq)
@@ -136,8 +140,8 @@ int run_layers(clm_tower* tw, const Workspace& ws, int batch, const int32_t* poo
                               ws.t, co, CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s));
     CLM_TRY(clm_gemm_launch(ws.ao, D, L.w_o, D, rows, D, D, co ? ws.t : nullptr, co,
                             co ? L.lora_b_o : nullptr, co, co, ws.h, D,
-                            CLM_OUT_F32, L.b_o, ws.h, D, CLM_EPI_NONE, s));
-    CLM_TRY(clm_layernorm(ws.h, L.ln2_g, L.ln2_b, ws.x, rows, D, c.ln_eps, sv));
+                            hd, L.b_o, hres, D, CLM_EPI_NONE, s));
+    CLM_TRY(clm_layernorm_ex(ws.h, hd, L.ln2_g, L.ln2_b, ws.x, rows, D, c.ln_eps, sv));
     const int c1 = (c.lora_cols_fc1 > 0 && L.lora_a_fc1 && L.lora_b_fc1) ? c.lora_cols_fc1 : 0;
     if (c1)
       CLM_TRY(clm_gemm_launch(ws.x, D, L.lora_a_fc1, D, rows, c1, D, nullptr, 0, nullptr, 0, 0,
@@ -150,11 +154,11 @@ int run_layers(clm_tower* tw, const Workspace& ws, int batch, const int32_t* poo
       CLM_TRY(clm_gemm_launch(ws.g, c.mlp, L.lora_a_fc2, c.mlp, rows, c2, c.mlp, nullptr, 0, nullptr, 0, 0,
                               ws.t, c2, CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s));
     CLM_TRY(clm_gemm_launch(ws.g, c.mlp, L.w_fc2, c.mlp, rows, D, c.mlp, c2 ? ws.t : nullptr, c2,
-                            c2 ? L.lora_b_fc2 : nullptr, c2, c2, ws.h, D, CLM_OUT_F32, L.b_fc2, ws.h, D,
+                            c2 ? L.lora_b_fc2 : nullptr, c2, c2, ws.h, D, hd, L.b_fc2, hres, D,
                             CLM_EPI_NONE, s));
   }
-  CLM_TRY(clm_pool_ln(ws.h, pool_idx, tw->w.final_ln_g, tw->w.final_ln_b, ws.pooled, batch, tokens,
-                      D, c.ln_eps, sv));
+  CLM_TRY(clm_pool_ln_ex(ws.h, hd, pool_idx, tw->w.final_ln_g, tw->w.final_ln_b, ws.pooled, batch, tokens,
+                         D, c.ln_eps, sv));
   float* proj_out = normalize ? ws.emb : out_emb;
   CLM_TRY(clm_gemm_launch(ws.pooled, D, tw->w.proj_w, D, batch, c.proj_dim, D, nullptr, 0, nullptr,
                           0, 0, proj_out, c.proj_dim, CLM_OUT_F32, nullptr, nullptr, 0, CLM_EPI_NONE, s));
@@ -208,6 +212,17 @@ extern "C" int clm_tower_create(const clm_tower_config* cfg, const clm_tower_wei
 
 extern "C" void clm_tower_destroy(clm_tower* t) { delete t; }
 
+extern "C" int clm_tower_set_residual_dtype(clm_tower* t, int dtype) {
+  CLM_REQUIRE(t != nullptr, "clm_tower_set_residual_dtype: null tower");
+  CLM_REQUIRE(dtype == CLM_OUT_F32 || dtype == CLM_OUT_BF16,
+              "clm_tower_set_residual_dtype: dtype must be CLM_OUT_F32 (%d) or CLM_OUT_BF16 (%d)", CLM_OUT_F32,
+              CLM_OUT_BF16);
+  t->h_dtype = dtype;
+  return CLM_OK;
+}
+
+extern "C" int clm_tower_residual_dtype(const clm_tower* t) { return t ? t->h_dtype : -1; }
+
 extern "C" size_t clm_tower_workspace_bytes(const clm_tower* t, int batch) {
   if (!t || batch <= 0) return 0;
   return carve(t, batch, nullptr).total;
@@ -234,8 +249,8 @@ extern "C" int clm_encode_image(clm_tower* t, const float* pixel_values, int bat
     CLM_TRY(clm_gemm_launch(patches, t->kpad, t->w.patch_w, t->kpad, nb * t->np, c.width, t->kpad,
                             nullptr, 0, nullptr, 0, 0, patch_out, c.width, CLM_OUT_F32, nullptr,
                             nullptr, 0, CLM_EPI_NONE, s));
-    CLM_TRY(clm_vision_embed_ln(patch_out, t->w.class_emb, t->w.pos_emb, t->w.pre_ln_g, t->w.pre_ln_b,
-                                ws.h, nb, t->np, c.width, c.ln_eps, s));
+    CLM_TRY(clm_vision_embed_ln_ex(patch_out, t->w.class_emb, t->w.pos_emb, t->w.pre_ln_g, t->w.pre_ln_b,
+                                   ws.h, t->h_dtype, nb, t->np, c.width, c.ln_eps, s));
     CLM_TRY(run_layers(t, ws, nb, nullptr, out_emb + static_cast<size_t>(b0) * c.proj_dim, normalize, s));
   }
   return CLM_OK;
@@ -257,8 +272,8 @@ extern "C" int clm_encode_text_len(clm_tower* t, const int32_t* ids, int batch, 
   for (int b0 = 0; b0 < batch; b0 += mb) {
     const int nb = (batch - b0) < mb ? (batch - b0) : mb;
     Workspace ws = carve(t, nb, static_cast<uint8_t*>(workspace), tokens);
-    CLM_TRY(clm_embed_text(ids + static_cast<size_t>(b0) * tokens, t->w.tok_emb, t->w.pos_emb, ws.h,
-                           ws.eos, nb, tokens, c.width, c.vocab, c.eos_id, s));
+    CLM_TRY(clm_embed_text_ex(ids + static_cast<size_t>(b0) * tokens, t->w.tok_emb, t->w.pos_emb, ws.h, t->h_dtype,
+                              ws.eos, nb, tokens, c.width, c.vocab, c.eos_id, s));
     CLM_TRY(run_layers(t, ws, nb, ws.eos, out_emb + static_cast<size_t>(b0) * c.proj_dim, normalize, s, tokens));
   }
   return CLM_OK;

@@ -25,10 +25,14 @@ def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
-    _req(x, torch.float32, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    """LayerNorm of an fp32 or bf16 residual stream x [rows, dim] -> bf16."""
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"x must be float32 or bfloat16, got {x.dtype}")
+    _req(x, x.dtype, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
     rows, dim = x.shape
     y = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device)
-    check(_lib.load().clm_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(y), rows, dim, eps, cur_stream()),
+    xd = OUT_F32 if x.dtype == torch.float32 else OUT_BF16
+    check(_lib.load().clm_layernorm_ex(ptr(x), xd, ptr(gamma), ptr(beta), ptr(y), rows, dim, eps, cur_stream()),
           "clm_layernorm")
     return y
 
@@ -94,7 +98,8 @@ def gemm_epi(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = No
              residual: Optional[torch.Tensor] = None, act: int = EPI_NONE,
              out_dtype: torch.dtype = torch.bfloat16, a2: Optional[torch.Tensor] = None,
              w2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = act(a @ w.T (+ a2 @ w2.T) + bias) (+ residual);  a [M,K], w [N,K] bf16."""
+    """out = act(a @ w.T (+ a2 @ w2.T) + bias) (+ residual);  a [M,K], w [N,K] bf16.  residual is fp32, or -- only
+    as the in-place update of a bf16 residual stream -- the bf16 tensor that is also `out`."""
     _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w")
     M, K = a.shape
     N, K2w = w.shape
@@ -103,7 +108,13 @@ def gemm_epi(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = No
     if bias is not None:
         _req(bias, torch.float32, "bias")
     if residual is not None:
-        _req(residual, torch.float32, "residual")
+        if residual.dtype == torch.bfloat16:
+            if out is None or out.data_ptr() != residual.data_ptr() or out.dtype != torch.bfloat16 \
+                    or out.stride(0) != residual.stride(0):
+                raise ValueError("a bfloat16 residual is only supported in place (out is residual)")
+            _req(residual, torch.bfloat16, "residual")
+        else:
+            _req(residual, torch.float32, "residual")
     k2 = 0
     if a2 is not None:
         _req(a2, torch.bfloat16, "a2"); _req(w2, torch.bfloat16, "w2")

@@ -58,6 +58,20 @@ int clm_device_check(void);
 int clm_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16,
                   int rows, int dim, float eps, void* stream);
 
+/* The same kernels over a residual stream held in bf16 (x_dtype / h_dtype = CLM_OUT_BF16) instead of fp32
+ * (CLM_OUT_F32: exactly the functions without the suffix).  A bf16 stream is what clm_tower_set_residual_dtype
+ * selects: every residual update then rounds once to bf16 (see there).  No reference counterpart: the reference's
+ * stream is whatever dtype the checkpoint was loaded in (models/clip_model.py:62-66, fp32). */
+int clm_layernorm_ex(const void* x, int x_dtype, const float* gamma, const float* beta, void* y_bf16,
+                     int rows, int dim, float eps, void* stream);
+int clm_embed_text_ex(const int32_t* ids, const float* tok_emb, const float* pos_emb, void* h, int h_dtype,
+                      int32_t* eos_pos, int batch, int tokens, int dim, int vocab, int eos_id, void* stream);
+int clm_vision_embed_ln_ex(const float* patch_out, const float* class_emb, const float* pos_emb,
+                           const float* gamma, const float* beta, void* h, int h_dtype, int batch, int np,
+                           int dim, float eps, void* stream);
+int clm_pool_ln_ex(const void* h, int h_dtype, const int32_t* row_idx_or_null, const float* gamma,
+                   const float* beta, void* y_bf16, int batch, int tokens, int dim, float eps, void* stream);
+
 /* Row L2 normalisation, no epsilon: x / ||x||  (models/clip_model.py:116,148;
  * src/embedding/search.py:68,93).  fp32 in, fp32 out (may alias), optional bf16 copy. */
 int clm_l2norm(const float* x, float* y, void* y_bf16_or_null, int rows, int dim, void* stream);
@@ -124,7 +138,10 @@ int clm_preprocess_images(const clm_image_desc* descs_host, int batch, int out_s
  * update y += (x A^T) (s B)^T  (models/lora_adapter.py:35-42; Appendix B of SURVEY.md)
  * folded in as a K-extension of the same accumulator.
  * bias fp32 [N] or NULL; residual fp32 [M, ldr] or NULL (added after the activation);
- * out is bf16 or fp32 per out_dtype; out may alias residual. */
+ * out is bf16 or fp32 per out_dtype; out may alias residual.
+ * In-place residual update (residual == out, ldr == ldo): the stream is updated in its own type through a TMA
+ * reduce-add inside the L2 -- fp32 with out_dtype = CLM_OUT_F32, and with out_dtype = CLM_OUT_BF16 the buffer is
+ * a bf16 residual stream (pass the same pointer for both): out = bf16(out + bf16(acc + bias)). */
 int clm_gemm_epi(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                  const void* A2, int lda2, const void* W2, int ldw2, int K2,
                  void* out, int ldo, int out_dtype, const float* bias,
@@ -132,7 +149,8 @@ int clm_gemm_epi(const void* A, int lda, const void* W, int ldw, int M, int N, i
 
 /* Debug / test hook: the kernel instantiation the calling thread's last clm_gemm_epi selected, encoded as
  * BN*100 + ctas*10 + epilogue (ctas: 1 = single CTA, 2 = cta_group::2 pair; epilogue: 0 = per-thread,
- * 1 = TMA store bf16, 2 = TMA store fp32, 3 = TMA reduce-add fp32).  25621 = gemm_kernel<256,2,1>.
+ * 1 = TMA store bf16, 2 = TMA store fp32, 3 = TMA reduce-add fp32, 4 = TMA reduce-add bf16).  25621 =
+ * gemm_kernel<256,2,1>.
  * 0 before the first call.  No reference counterpart (the reference calls ATen's matmul). */
 int clm_last_gemm_variant(void);
 
@@ -207,6 +225,14 @@ int clm_tower_create(const clm_tower_config* cfg, const clm_tower_weights* w,
 void clm_tower_destroy(clm_tower* t);
 /* bytes of caller-provided device workspace needed for a micro-batch of `batch` items */
 size_t clm_tower_workspace_bytes(const clm_tower* t, int batch);
+/* Type of the residual stream h between the layers: CLM_OUT_F32 (the default after clm_tower_create: the
+ * reference's fp32 stream, every update an fp32 add) or CLM_OUT_BF16 (h stored in bf16: LayerNorm reads 2 instead
+ * of 4 bytes per element and the out-projection / fc2 epilogues add bf16 tiles inside the L2; each of the 2 x layers
+ * updates rounds once to bf16 -- embeddings stay within north_star's cosine >= 0.999 of the fp32 path, measured
+ * >= 0.9999, tests/test_residual_bf16_gpu.py).  Applies to the following encode calls; the workspace need shrinks.
+ * clm_tower_residual_dtype returns the current setting. */
+int clm_tower_set_residual_dtype(clm_tower* t, int dtype);
+int clm_tower_residual_dtype(const clm_tower* t);
 
 /* models/clip_model.py:89-118 without the PIL step: pixel_values fp32 [batch,3,H,W]
  * -> embeddings fp32 [batch, P]; normalize != 0 applies x/||x|| (clip_model.py:116),

@@ -52,6 +52,16 @@ class LayerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _LAYER_FIELDS]
 
 
+_FOLD_FIELDS = [
+    "w_qkv_g", "s_qkv", "b_qkv_f", "lora_a_qkv_g", "s_a_qkv",
+    "w_fc1_g", "s_fc1", "b_fc1_f", "lora_a_fc1_g", "s_a_fc1",
+]
+
+
+class LayerLnFold(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _FOLD_FIELDS]
+
+
 class TowerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _TOWER_FIELDS]
 
@@ -70,6 +80,8 @@ SIGNATURES = {
     "clm_embed_text_ex": (_I, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "clm_vision_embed_ln_ex": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "clm_pool_ln_ex": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "clm_row_stats": (_I, [_P, _P, _I, _I, _F, _P]),
+    "clm_gemm_ln_epi": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _P, _P, _P, _I, _I, _P]),
     "clm_fuse_normalize": (_I, [_P, _F, _P, _F, _P, _P, _I, _I, _P]),
     "clm_preprocess_workspace_bytes": (C.c_size_t, [_P, _I, _I]),
     "clm_preprocess_images": (_I, [_P, _I, _I, _P, _P, _P, _P, C.c_size_t, _P]),
@@ -100,6 +112,7 @@ SIGNATURES = {
     "clm_tower_workspace_bytes": (C.c_size_t, [_P, _I]),
     "clm_tower_set_residual_dtype": (_I, [_P, _I]),
     "clm_tower_residual_dtype": (_I, [_P]),
+    "clm_tower_set_ln_fold": (_I, [_P, C.POINTER(LayerLnFold)]),
     "clm_encode_image": (_I, [_P, _P, _I, _P, _I, _P, C.c_size_t, _P]),
     "clm_encode_text": (_I, [_P, _P, _I, _P, _I, _P, C.c_size_t, _P]),
     "clm_encode_text_len": (_I, [_P, _P, _I, _I, _P, _I, _P, C.c_size_t, _P]),

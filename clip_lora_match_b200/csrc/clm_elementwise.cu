@@ -95,6 +95,31 @@ layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
   r.store_bf16(y + static_cast<size_t>(row) * D);
 }
 
+// (mean, rstd) of every row of a bf16 residual stream: what a GEMM with the LayerNorm folded in (clm_gemm_ln_epi)
+// needs of the row -- half the traffic of the LayerNorm pass it replaces (no normalised copy is written)
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+row_stats_kernel(const __nv_bfloat16* __restrict__ h, float2* __restrict__ stats, int rows, float eps) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  constexpr int D = NV * 128;
+  constexpr float inv_n = 1.0f / D;
+  Row<NV> r;
+  r.load_bf16(h + static_cast<size_t>(row) * D);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) s += (r.v[j].x + r.v[j].y) + (r.v[j].z + r.v[j].w);
+  const float mean = warp_sum(s) * inv_n;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float a = r.v[j].x - mean, b = r.v[j].y - mean, c = r.v[j].z - mean, d = r.v[j].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+  if (lane_id() == 0) stats[row] = make_float2(mean, rstd);
+}
+
 template <int NV, bool kH16 = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pool_ln_kernel(const void* __restrict__ h, const int32_t* __restrict__ row_idx,
@@ -319,6 +344,18 @@ extern "C" int clm_layernorm_ex(const void* x, int x_dtype, const float* gamma, 
     CLM_DISPATCH_DIM(dim, (layernorm_kernel<NV, false><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
                               x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), rows, eps)));
   }
+  CLM_CUDA_CHECK(cudaGetLastError());
+  return CLM_OK;
+}
+
+extern "C" int clm_row_stats(const void* h_bf16, float* stats, int rows, int dim, float eps, void* stream) {
+  CLM_REQUIRE(h_bf16 && stats && rows >= 0, "clm_row_stats: bad argument");
+  CLM_REQUIRE((reinterpret_cast<uintptr_t>(stats) & 7) == 0, "clm_row_stats: stats must be 8-byte aligned");
+  if (rows == 0) return CLM_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 2.0 * rows * dim + 8.0 * rows, s);
+  CLM_DISPATCH_DIM(dim, (row_stats_kernel<NV><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
+                            static_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<float2*>(stats), rows, eps)));
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
 }

@@ -85,7 +85,17 @@ struct EpiParams {
   // work unit of its own that adds its partial product into out; range 0 also adds the bias.  1 = off.
   int ksplit;
   int kb_per;
+  // LayerNorm folded into the GEMM (clm_gemm_ln_epi): A is the raw bf16 residual stream, W carries gamma, and the
+  // epilogue applies the per-row statistics.  ln_mode 1: out = rstd (acc - mean * col_s) + bias;
+  // ln_mode 2 (LoRA down-projection, to be scaled by rstd later): out = (acc - mean * col_s) + bias.  row_stats = NULL: off.
+  const float2* row_stats;
+  const float* col_s;
+  int ln_mode;
 };
+
+__device__ __forceinline__ float ln_fix(float v, float b, float s, float neg_mu, float alpha) {
+  return fmaf(alpha, fmaf(neg_mu, s, v), b);
+}
 
 // ---- cta_group::2 helpers ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -310,11 +320,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const float* bias = (unit - tile * ksplit == 0) ? ep.bias : nullptr;  // the first k range of a tile adds the bias
       const int m0 = (tile / n_tiles) * TM + static_cast<int>(rank) * BM + q * 32;
       const int n0 = (tile % n_tiles) * BN + (kSplit ? half * (BN / 2) : 0);
+      const bool rows_live = active && m0 < M;
+      const bool ln = ep.row_stats != nullptr;  // warp-uniform
+      float ln_mu = 0.f, ln_alpha = 1.f;  // ln_mu holds -mean; loaded while the tile's MMAs are still running
+      if (ln && rows_live && m0 + lane < M) {  // tcgen05.ld: lane = accumulator row
+        const float2 st = __ldg(ep.row_stats + m0 + lane);
+        ln_mu = -st.x;
+        if (ep.ln_mode == 1) ln_alpha = st.y;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(acc * BN + (kSplit ? half * (BN / 2) : 0));
-      const bool rows_live = active && m0 < M;
 #pragma unroll
       for (int sl = 0; sl < kSlabs; ++sl) {
         const int col0 = n0 + sl * kSlabCols;
@@ -339,8 +356,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             for (int p = 0; p < 8; ++p) {
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
               if (bias && col0 + 4 * p < N) b = __ldg(reinterpret_cast<const float4*>(bias + col0 + 4 * p));
-              float x0 = __uint_as_float(v[4 * p + 0]) + b.x, x1 = __uint_as_float(v[4 * p + 1]) + b.y;
-              float x2 = __uint_as_float(v[4 * p + 2]) + b.z, x3 = __uint_as_float(v[4 * p + 3]) + b.w;
+              float x0, x1, x2, x3;
+              if (ln) {
+                float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col0 + 4 * p < N) cs = __ldg(reinterpret_cast<const float4*>(ep.col_s + col0 + 4 * p));
+                x0 = ln_fix(__uint_as_float(v[4 * p + 0]), b.x, cs.x, ln_mu, ln_alpha);
+                x1 = ln_fix(__uint_as_float(v[4 * p + 1]), b.y, cs.y, ln_mu, ln_alpha);
+                x2 = ln_fix(__uint_as_float(v[4 * p + 2]), b.z, cs.z, ln_mu, ln_alpha);
+                x3 = ln_fix(__uint_as_float(v[4 * p + 3]), b.w, cs.w, ln_mu, ln_alpha);
+              } else {
+                x0 = __uint_as_float(v[4 * p + 0]) + b.x; x1 = __uint_as_float(v[4 * p + 1]) + b.y;
+                x2 = __uint_as_float(v[4 * p + 2]) + b.z; x3 = __uint_as_float(v[4 * p + 3]) + b.w;
+              }
               if (ep.act == CLM_EPI_QUICKGELU) {
                 x0 = quick_gelu(x0); x1 = quick_gelu(x1); x2 = quick_gelu(x2); x3 = quick_gelu(x3);
               }
@@ -372,10 +399,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * p + 4));
               }
               const uint32_t* src = (p < 4) ? &v0[8 * p] : &v1[8 * (p - 4)];
-              float x0 = __uint_as_float(src[0]) + b0.x, x1 = __uint_as_float(src[1]) + b0.y;
-              float x2 = __uint_as_float(src[2]) + b0.z, x3 = __uint_as_float(src[3]) + b0.w;
-              float x4 = __uint_as_float(src[4]) + b1.x, x5 = __uint_as_float(src[5]) + b1.y;
-              float x6 = __uint_as_float(src[6]) + b1.z, x7 = __uint_as_float(src[7]) + b1.w;
+              float x0, x1, x2, x3, x4, x5, x6, x7;
+              if (ln) {
+                float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+                if (col0 + 8 * p < N) {
+                  c0 = __ldg(reinterpret_cast<const float4*>(ep.col_s + col0 + 8 * p));
+                  c1 = __ldg(reinterpret_cast<const float4*>(ep.col_s + col0 + 8 * p + 4));
+                }
+                x0 = ln_fix(__uint_as_float(src[0]), b0.x, c0.x, ln_mu, ln_alpha);
+                x1 = ln_fix(__uint_as_float(src[1]), b0.y, c0.y, ln_mu, ln_alpha);
+                x2 = ln_fix(__uint_as_float(src[2]), b0.z, c0.z, ln_mu, ln_alpha);
+                x3 = ln_fix(__uint_as_float(src[3]), b0.w, c0.w, ln_mu, ln_alpha);
+                x4 = ln_fix(__uint_as_float(src[4]), b1.x, c1.x, ln_mu, ln_alpha);
+                x5 = ln_fix(__uint_as_float(src[5]), b1.y, c1.y, ln_mu, ln_alpha);
+                x6 = ln_fix(__uint_as_float(src[6]), b1.z, c1.z, ln_mu, ln_alpha);
+                x7 = ln_fix(__uint_as_float(src[7]), b1.w, c1.w, ln_mu, ln_alpha);
+              } else {
+                x0 = __uint_as_float(src[0]) + b0.x; x1 = __uint_as_float(src[1]) + b0.y;
+                x2 = __uint_as_float(src[2]) + b0.z; x3 = __uint_as_float(src[3]) + b0.w;
+                x4 = __uint_as_float(src[4]) + b1.x; x5 = __uint_as_float(src[5]) + b1.y;
+                x6 = __uint_as_float(src[6]) + b1.z; x7 = __uint_as_float(src[7]) + b1.w;
+              }
               if (ep.act == CLM_EPI_QUICKGELU) {
                 x0 = quick_gelu(x0); x1 = quick_gelu(x1); x2 = quick_gelu(x2); x3 = quick_gelu(x3);
                 x4 = quick_gelu(x4); x5 = quick_gelu(x5); x6 = quick_gelu(x6); x7 = quick_gelu(x7);
@@ -555,8 +599,14 @@ int launch_gemm_bn(bool pair, int BN, const CUtensorMap& ma, const CUtensorMap& 
 int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                     const void* A2, int lda2, const void* W2, int ldw2, int K2, void* out, int ldo,
                     int out_dtype, const float* bias, const float* residual, int ldr, int epilogue,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const float* row_stats, const float* col_sums, int ln_mode) {
   CLM_REQUIRE(A && W && out, "clm_gemm_epi: null operand");
+  if (row_stats) {
+    CLM_REQUIRE(col_sums && (ln_mode == 1 || ln_mode == 2), "clm_gemm_ln_epi: col_sums and ln_mode 1 / 2 are required");
+    CLM_REQUIRE(!residual, "clm_gemm_ln_epi: no residual with the folded LayerNorm epilogue");
+    CLM_REQUIRE((reinterpret_cast<uintptr_t>(row_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(col_sums) & 15) == 0,
+                "clm_gemm_ln_epi: row_stats must be 8-byte and col_sums 16-byte aligned");
+  }
   CLM_REQUIRE(M > 0 && N > 0 && K > 0, "clm_gemm_epi: bad shape M=%d N=%d K=%d", M, N, K);
   CLM_REQUIRE(N % 8 == 0, "clm_gemm_epi: N=%d must be a multiple of 8", N);
   CLM_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0,
@@ -618,6 +668,9 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
   ep.ldr = ldr;
   ep.out_f32 = (out_dtype == CLM_OUT_F32);
   ep.act = epilogue & CLM_EPI_QUICKGELU;
+  ep.row_stats = reinterpret_cast<const float2*>(row_stats);
+  ep.col_s = col_sums;
+  ep.ln_mode = ln_mode;
   // epilogue variant: TMA tile stores, or a TMA reduce-add for the in-place residual update; the
   // per-thread legacy path only for residual != out / bf16 out + residual (CLM_GEMM_EPI=legacy forces it)
   static int force_legacy = -1;
@@ -632,7 +685,7 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
     const bool in_place = residual == static_cast<const float*>(out) && ldr == ldo;
     epi = in_place ? (ep.out_f32 ? kEpiReduceF32 : kEpiReduceBf16) : kEpiLegacy;
   }
-  if (force_legacy && epi != kEpiReduceBf16) epi = kEpiLegacy;  // (the legacy path reads an fp32 residual)
+  if (force_legacy && epi != kEpiReduceBf16 && !row_stats) epi = kEpiLegacy;  // (the legacy path reads an fp32 residual)
   CUtensorMap mo = ma;
   if (epi != kEpiLegacy) {
     if ((rc = clm_make_tmap_2d(&mo, out, M, N, ldo, ep.out_f32 ? 4 : 2, ep.out_f32 ? 32 : 64, 32))) return rc;
@@ -686,5 +739,14 @@ extern "C" int clm_gemm_epi(const void* A, int lda, const void* W, int ldw, int 
                             int ldo, int out_dtype, const float* bias, const float* residual,
                             int ldr, int epilogue, void* stream) {
   return clm_gemm_launch(A, lda, W, ldw, M, N, K, A2, lda2, W2, ldw2, K2, out, ldo, out_dtype, bias,
-                         residual, ldr, epilogue, static_cast<cudaStream_t>(stream));
+                         residual, ldr, epilogue, static_cast<cudaStream_t>(stream), nullptr, nullptr, 0);
+}
+
+extern "C" int clm_gemm_ln_epi(const void* H, int ldh, const void* Wg, int ldw, int M, int N, int K,
+                               const void* A2, int lda2, const void* W2, int ldw2, int K2, void* out,
+                               int ldo, int out_dtype, const float* bias, const float* row_stats,
+                               const float* col_sums, int ln_mode, int epilogue, void* stream) {
+  CLM_REQUIRE(row_stats && col_sums, "clm_gemm_ln_epi: row_stats / col_sums are required");
+  return clm_gemm_launch(H, ldh, Wg, ldw, M, N, K, A2, lda2, W2, ldw2, K2, out, ldo, out_dtype, bias,
+                         nullptr, 0, epilogue, static_cast<cudaStream_t>(stream), row_stats, col_sums, ln_mode);
 }

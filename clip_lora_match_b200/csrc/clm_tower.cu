@@ -22,7 +22,8 @@
 int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                     const void* A2, int lda2, const void* W2, int ldw2, int K2, void* out, int ldo,
                     int out_dtype, const float* bias, const float* residual, int ldr, int epilogue,
-                    cudaStream_t stream);
+                    cudaStream_t stream, const float* row_stats = nullptr, const float* col_sums = nullptr,
+                    int ln_mode = 0);
 int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int heads, int causal,
                          cudaStream_t stream);
 
@@ -33,6 +34,7 @@ struct clm_tower {
   int kpad;  // padded im2col width (vision)
   int np;    // patches per image (vision)
   int h_dtype = CLM_OUT_F32;  // residual stream: fp32 (reference) or bf16 (clm_tower_set_residual_dtype)
+  std::vector<clm_layer_ln_fold> folds;  // LayerNorm folded into QKV / fc1 (bf16 stream only); empty = off
 };
 
 namespace {
@@ -59,6 +61,7 @@ struct Workspace {
   __nv_bfloat16* pooled;
   float* emb;
   int32_t* eos;
+  float* stats;  // (mean, rstd) per row, folded-LayerNorm mode
   size_t total;
 };
 
@@ -91,6 +94,7 @@ Workspace carve(const clm_tower* tw, int batch, uint8_t* base, int tokens = 0) {
   ws.pooled = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(batch) * c.width * 2));
   ws.emb = reinterpret_cast<float*>(take(static_cast<size_t>(batch) * c.proj_dim * 4));
   ws.eos = reinterpret_cast<int32_t*>(take(static_cast<size_t>(batch) * 4));
+  ws.stats = reinterpret_cast<float*>(take(rows * 8));
   ws.total = off;
   return ws;
 }
@@ -122,17 +126,30 @@ int run_layers(clm_tower* tw, const Workspace& ws, int batch, const int32_t* poo
   void* sv = static_cast<void*>(s);
   const int hd = tw->h_dtype;
   const float* hres = static_cast<const float*>(ws.h);  // in-place residual: same pointer as `out`, type per hd
+  const bool fold = hd == CLM_OUT_BF16 && !tw->folds.empty();
   for (int l = 0; l < c.layers; ++l) {
     const clm_layer_weights& L = tw->layers[l];
-    CLM_TRY(clm_layernorm_ex(ws.h, hd, L.ln1_g, L.ln1_b, ws.x, rows, D, c.ln_eps, sv));
     // LoRA (unmerged): t = x A_cat^T is a skinny GEMM, then (t, (s B)_cat) ride along as extra K blocks
     const int cq = (c.lora_cols_qkv > 0 && L.lora_a_qkv && L.lora_b_qkv) ? c.lora_cols_qkv : 0;
-    if (cq)
-      CLM_TRY(clm_gemm_launch(ws.x, D, L.lora_a_qkv, D, rows, cq, D, nullptr, 0, nullptr, 0, 0,
-                              ws.t, cq, CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s));
-    CLM_TRY(clm_gemm_launch(ws.x, D, L.w_qkv, D, rows, 3 * D, D, cq ? ws.t : nullptr, cq,
-                            cq ? L.lora_b_qkv : nullptr, cq, cq, ws.qkv, 3 * D,
-                            CLM_OUT_BF16, L.b_qkv, nullptr, 0, CLM_EPI_NONE, s));
+    const clm_layer_ln_fold* F = fold ? &tw->folds[l] : nullptr;
+    if (F) {
+      // LayerNorm folded into the GEMMs: the operand is the raw bf16 stream, the epilogue normalises (clm_gemm_ln_epi)
+      CLM_TRY(clm_row_stats(ws.h, ws.stats, rows, D, c.ln_eps, sv));
+      if (cq)
+        CLM_TRY(clm_gemm_launch(ws.h, D, F->lora_a_qkv_g, D, rows, cq, D, nullptr, 0, nullptr, 0, 0, ws.t, cq,
+                                CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s, ws.stats, F->s_a_qkv, 2));
+      CLM_TRY(clm_gemm_launch(ws.h, D, F->w_qkv_g, D, rows, 3 * D, D, cq ? ws.t : nullptr, cq,
+                              cq ? L.lora_b_qkv : nullptr, cq, cq, ws.qkv, 3 * D, CLM_OUT_BF16, F->b_qkv_f, nullptr,
+                              0, CLM_EPI_NONE, s, ws.stats, F->s_qkv, 1));
+    } else {
+      CLM_TRY(clm_layernorm_ex(ws.h, hd, L.ln1_g, L.ln1_b, ws.x, rows, D, c.ln_eps, sv));
+      if (cq)
+        CLM_TRY(clm_gemm_launch(ws.x, D, L.lora_a_qkv, D, rows, cq, D, nullptr, 0, nullptr, 0, 0,
+                                ws.t, cq, CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s));
+      CLM_TRY(clm_gemm_launch(ws.x, D, L.w_qkv, D, rows, 3 * D, D, cq ? ws.t : nullptr, cq,
+                              cq ? L.lora_b_qkv : nullptr, cq, cq, ws.qkv, 3 * D,
+                              CLM_OUT_BF16, L.b_qkv, nullptr, 0, CLM_EPI_NONE, s));
+    }
     CLM_TRY(clm_attention_launch(ws.qkv, ws.ao, batch, tokens, c.heads, c.kind == 1, s));
     const int co = (c.lora_cols_out > 0 && L.lora_a_o && L.lora_b_o) ? c.lora_cols_out : 0;
     if (co)
@@ -141,14 +158,24 @@ int run_layers(clm_tower* tw, const Workspace& ws, int batch, const int32_t* poo
     CLM_TRY(clm_gemm_launch(ws.ao, D, L.w_o, D, rows, D, D, co ? ws.t : nullptr, co,
                             co ? L.lora_b_o : nullptr, co, co, ws.h, D,
                             hd, L.b_o, hres, D, CLM_EPI_NONE, s));
-    CLM_TRY(clm_layernorm_ex(ws.h, hd, L.ln2_g, L.ln2_b, ws.x, rows, D, c.ln_eps, sv));
     const int c1 = (c.lora_cols_fc1 > 0 && L.lora_a_fc1 && L.lora_b_fc1) ? c.lora_cols_fc1 : 0;
-    if (c1)
-      CLM_TRY(clm_gemm_launch(ws.x, D, L.lora_a_fc1, D, rows, c1, D, nullptr, 0, nullptr, 0, 0,
-                              ws.t, c1, CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s));
-    CLM_TRY(clm_gemm_launch(ws.x, D, L.w_fc1, D, rows, c.mlp, D, c1 ? ws.t : nullptr, c1,
-                            c1 ? L.lora_b_fc1 : nullptr, c1, c1, ws.g,
-                            c.mlp, CLM_OUT_BF16, L.b_fc1, nullptr, 0, CLM_EPI_QUICKGELU, s));
+    if (F) {
+      CLM_TRY(clm_row_stats(ws.h, ws.stats, rows, D, c.ln_eps, sv));
+      if (c1)
+        CLM_TRY(clm_gemm_launch(ws.h, D, F->lora_a_fc1_g, D, rows, c1, D, nullptr, 0, nullptr, 0, 0, ws.t, c1,
+                                CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s, ws.stats, F->s_a_fc1, 2));
+      CLM_TRY(clm_gemm_launch(ws.h, D, F->w_fc1_g, D, rows, c.mlp, D, c1 ? ws.t : nullptr, c1,
+                              c1 ? L.lora_b_fc1 : nullptr, c1, c1, ws.g, c.mlp, CLM_OUT_BF16, F->b_fc1_f, nullptr, 0,
+                              CLM_EPI_QUICKGELU, s, ws.stats, F->s_fc1, 1));
+    } else {
+      CLM_TRY(clm_layernorm_ex(ws.h, hd, L.ln2_g, L.ln2_b, ws.x, rows, D, c.ln_eps, sv));
+      if (c1)
+        CLM_TRY(clm_gemm_launch(ws.x, D, L.lora_a_fc1, D, rows, c1, D, nullptr, 0, nullptr, 0, 0,
+                                ws.t, c1, CLM_OUT_BF16, nullptr, nullptr, 0, CLM_EPI_NONE, s));
+      CLM_TRY(clm_gemm_launch(ws.x, D, L.w_fc1, D, rows, c.mlp, D, c1 ? ws.t : nullptr, c1,
+                              c1 ? L.lora_b_fc1 : nullptr, c1, c1, ws.g,
+                              c.mlp, CLM_OUT_BF16, L.b_fc1, nullptr, 0, CLM_EPI_QUICKGELU, s));
+    }
     const int c2 = (c.lora_cols_fc2 > 0 && L.lora_a_fc2 && L.lora_b_fc2) ? c.lora_cols_fc2 : 0;
     if (c2)
       CLM_TRY(clm_gemm_launch(ws.g, c.mlp, L.lora_a_fc2, c.mlp, rows, c2, c.mlp, nullptr, 0, nullptr, 0, 0,
@@ -222,6 +249,29 @@ extern "C" int clm_tower_set_residual_dtype(clm_tower* t, int dtype) {
 }
 
 extern "C" int clm_tower_residual_dtype(const clm_tower* t) { return t ? t->h_dtype : -1; }
+
+extern "C" int clm_tower_set_ln_fold(clm_tower* t, const clm_layer_ln_fold* folds) {
+  CLM_REQUIRE(t != nullptr, "clm_tower_set_ln_fold: null tower");
+  if (!folds) {
+    t->folds.clear();
+    return CLM_OK;
+  }
+  const clm_tower_config& c = t->cfg;
+  for (int l = 0; l < c.layers; ++l) {
+    const clm_layer_ln_fold& f = folds[l];
+    const clm_layer_weights& L = t->layers[l];
+    CLM_REQUIRE(f.w_qkv_g && f.s_qkv && f.b_qkv_f && f.w_fc1_g && f.s_fc1 && f.b_fc1_f,
+                "clm_tower_set_ln_fold: layer %d: folded QKV / fc1 weights, column sums and biases are required", l);
+    const bool need_q = c.lora_cols_qkv > 0 && L.lora_a_qkv && L.lora_b_qkv;
+    const bool need_1 = c.lora_cols_fc1 > 0 && L.lora_a_fc1 && L.lora_b_fc1;
+    CLM_REQUIRE(!need_q || (f.lora_a_qkv_g && f.s_a_qkv),
+                "clm_tower_set_ln_fold: layer %d has a QKV adapter but no folded down-projection", l);
+    CLM_REQUIRE(!need_1 || (f.lora_a_fc1_g && f.s_a_fc1),
+                "clm_tower_set_ln_fold: layer %d has an fc1 adapter but no folded down-projection", l);
+  }
+  t->folds.assign(folds, folds + c.layers);
+  return CLM_OK;
+}
 
 extern "C" size_t clm_tower_workspace_bytes(const clm_tower* t, int batch) {
   if (!t || batch <= 0) return 0;

@@ -130,6 +130,55 @@ def gemm_epi(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = No
     return out
 
 
+def row_stats(h: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """(mean, rstd) per row of a bf16 residual stream h [rows, dim] -> fp32 [rows, 2]."""
+    _req(h, torch.bfloat16, "h")
+    rows, dim = h.shape
+    st = torch.empty((rows, 2), dtype=torch.float32, device=h.device)
+    check(_lib.load().clm_row_stats(ptr(h), ptr(st), rows, dim, eps, cur_stream()), "clm_row_stats")
+    return st
+
+
+def fold_layernorm(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor] = None):
+    """Host-side preparation for gemm_ln_epi from fp32 tensors: (Wg bf16 = W diag(gamma), col_sums fp32 of the bf16
+    values, bias' = bias + W beta)."""
+    w = w.float()
+    wg = (w * gamma.float()[None, :]).bfloat16()
+    col_sums = wg.float().sum(dim=1)
+    b = w @ beta.float()
+    if bias is not None:
+        b = b + bias.float()
+    return wg, col_sums.contiguous(), b.contiguous()
+
+
+def gemm_ln_epi(h: torch.Tensor, wg: torch.Tensor, stats: torch.Tensor, col_sums: torch.Tensor,
+                bias: Optional[torch.Tensor], ln_mode: int = 1, act: int = EPI_NONE, out_dtype: torch.dtype = torch.bfloat16,
+                a2: Optional[torch.Tensor] = None, w2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm folded into the GEMM (clm_gemm_ln_epi): h is the raw bf16 stream, (wg, col_sums, bias) come from
+    fold_layernorm, stats from row_stats.  ln_mode 1: act(LN(h) W^T + b (+ rstd a2 w2^T));
+    ln_mode 2: (LN(h) W^T - W beta) / rstd + bias (the LoRA down-projection: pass bias = None)."""
+    _req(h, torch.bfloat16, "h"); _req(wg, torch.bfloat16, "wg")
+    _req(stats, torch.float32, "stats"); _req(col_sums, torch.float32, "col_sums")
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+    M, K = h.shape
+    N = wg.shape[0]
+    if wg.shape[1] != K or tuple(stats.shape) != (M, 2) or col_sums.numel() != N or (bias is not None and bias.numel() != N):
+        raise ValueError("gemm_ln_epi: shape mismatch")
+    k2 = 0
+    if a2 is not None:
+        _req(a2, torch.bfloat16, "a2"); _req(w2, torch.bfloat16, "w2")
+        k2 = a2.shape[1]
+    out = torch.empty((M, N), dtype=out_dtype, device=h.device)
+    od = OUT_F32 if out_dtype == torch.float32 else OUT_BF16
+    check(_lib.load().clm_gemm_ln_epi(
+        ptr(h), h.stride(0), ptr(wg), wg.stride(0), M, N, K,
+        ptr(a2), a2.stride(0) if a2 is not None else 0, ptr(w2), w2.stride(0) if w2 is not None else 0, k2,
+        ptr(out), out.stride(0), od, ptr(bias), ptr(stats), ptr(col_sums), ln_mode, act, cur_stream()),
+        "clm_gemm_ln_epi")
+    return out
+
+
 def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, causal: bool) -> torch.Tensor:
     _req(qkv, torch.bfloat16, "qkv")
     dim = heads * 64

@@ -26,6 +26,7 @@ import torch
 import yaml
 
 from .. import _lib
+from .. import kernels as K
 from .lora_adapter import LoraAdapter, linear_module_paths, load_lora_adapter
 
 LORA_COLS = 64  # LoRA ranks are padded to multiples of this: one extra K block of the fused GEMMs each
@@ -159,10 +160,14 @@ class B200ClipModel:
 
     def __init__(self, arch: ClipArch, state_dict: Dict[str, torch.Tensor],
                  lora: Optional[LoraAdapter] = None, device: Union[str, torch.device] = "cuda",
-                 max_workspace_bytes: int = 24 << 30, residual_dtype: Optional[str] = None):
+                 max_workspace_bytes: int = 24 << 30, residual_dtype: Optional[str] = None,
+                 ln_fold: Optional[bool] = None):
         """residual_dtype: "float32" (the reference's fp32 residual stream) or "bfloat16" (the stream between the
         layers is stored in bf16: clm_tower_set_residual_dtype in include/clm_b200.h); None takes
-        DEFAULT_RESIDUAL_DTYPE (overridable with CLM_RESIDUAL_DTYPE)."""
+        DEFAULT_RESIDUAL_DTYPE (overridable with CLM_RESIDUAL_DTYPE).
+        ln_fold: with a bf16 stream, fold layer_norm1 / layer_norm2 into the QKV / fc1 GEMMs (gamma into the weights,
+        mean / rstd applied in the epilogue: clm_gemm_ln_epi) instead of running LayerNorm passes; None = on unless
+        CLM_LN_FOLD=0."""
         self.arch = arch
         self.name = arch.name
         self.device = torch.device(device)
@@ -175,6 +180,9 @@ class B200ClipModel:
         self.max_workspace_bytes = max_workspace_bytes
         self._towers: Dict[str, int] = {}
         self._keep: Dict[str, list] = {}
+        self._folds: Dict[str, object] = {}
+        # LayerNorm folded into the QKV / fc1 GEMMs (used by the towers only while the residual stream is bf16)
+        self.ln_fold = os.environ.get("CLM_LN_FOLD", "1") != "0" if ln_fold is None else bool(ln_fold)
         self._workspace: Optional[torch.Tensor] = None
         self._dummy = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._stage = None  # host->device staging (encode_images of host tensors)
@@ -220,10 +228,18 @@ class B200ClipModel:
         """Switch the residual stream of both towers between "float32" and "bfloat16" (weights untouched)."""
         self.residual_dtype = _residual_dtype_name(residual_dtype)
         self._graphs.clear()  # captured passes carry the stream's type
-        self._workspace = None
         for kind, h in self._towers.items():
             _lib.check(self._lib.clm_tower_set_residual_dtype(h, _RESIDUAL_CODES[self.residual_dtype]),
                        f"clm_tower_set_residual_dtype({kind})")
+
+    def set_ln_fold(self, on: bool) -> None:
+        """Use (or stop using) the folded-LayerNorm GEMMs; needs the folded weights built at construction."""
+        self._graphs.clear()
+        for kind, h in self._towers.items():
+            folds = self._folds.get(kind) if on else None
+            if on and folds is None:
+                raise ValueError("the model was built with ln_fold=False: no folded weights exist")
+            _lib.check(self._lib.clm_tower_set_ln_fold(h, folds), f"clm_tower_set_ln_fold({kind})")
 
     def _dev(self, t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
         return t.to(device=self.device, dtype=dtype).contiguous()
@@ -252,6 +268,7 @@ class B200ClipModel:
             row0 = sum(outs[:i])
             a_cat[slot * r:(slot + 1) * r] = a
             b_cat[row0:row0 + outs[i], slot * r:(slot + 1) * r] = b * s
+        self._last_a_cat_f32 = a_cat  # fp32 host copy: the LayerNorm fold scales it by gamma before rounding
         return self._dev(a_cat, torch.bfloat16), self._dev(b_cat, torch.bfloat16), cols
 
     def _build_tower(self, kind: str) -> None:
@@ -272,7 +289,20 @@ class B200ClipModel:
             return t.data_ptr()
 
         layers = (_lib.LayerWeights * ta.layers)()
+        folds = (_lib.LayerLnFold * ta.layers)()
         cols = {"qkv": 0, "out": 0, "fc1": 0, "fc2": 0}  # every layer of a tower carries the same adapter shape
+        a_f32: Dict[str, torch.Tensor] = {}   # fp32 host A_cat of this layer's adapters, per fused GEMM
+        b_bf16: Dict[str, torch.Tensor] = {}  # the (s B)_cat the device multiplies with
+
+        def fold(Fl, name, w, gamma, beta, bias, names):
+            """LayerNorm folded into the Linear that consumes it (include/clm_b200.h: clm_gemm_ln_epi)."""
+            wg, cs, bf = K.fold_layernorm(w, gamma, beta, bias)
+            for field, t, dt in zip(names, (wg, cs, bf), (torch.bfloat16, torch.float32, torch.float32)):
+                if field is None:
+                    continue
+                t = self._dev(t, dt)
+                keep.append(t)
+                setattr(Fl, field, t.data_ptr())
 
         def lora(L, name, prefix, in_dim, group):
             a_cat, b_cat, c = self._lora_operands(prefix, in_dim, group)
@@ -282,6 +312,8 @@ class B200ClipModel:
                 raise ValueError(f"LoRA targets differ between layers of the {kind} tower ({name}: {cols[name]} vs {c})")
             cols[name] = c
             keep.extend([a_cat, b_cat])
+            a_f32[name] = self._last_a_cat_f32
+            b_bf16[name] = b_cat
             setattr(L, f"lora_a_{name if name != 'out' else 'o'}", a_cat.data_ptr())
             setattr(L, f"lora_b_{name if name != 'out' else 'o'}", b_cat.data_ptr())
 
@@ -304,6 +336,26 @@ class B200ClipModel:
             L.w_fc2, L.b_fc2 = bf16(sd[f"{lp}.mlp.fc2.weight"]), f32(f"{lp}.mlp.fc2.bias")
             lora(L, "fc1", f"{lp}.mlp", ta.width, [("fc1", ta.mlp)])
             lora(L, "fc2", f"{lp}.mlp", ta.mlp, [("fc2", ta.width)])
+            if self.ln_fold:
+                Fl = folds[i]
+                g1, b1 = sd[f"{lp}.layer_norm1.weight"], sd[f"{lp}.layer_norm1.bias"]
+                g2, b2 = sd[f"{lp}.layer_norm2.weight"], sd[f"{lp}.layer_norm2.bias"]
+                # the adapter's share of the folded bias: LN(h) A^T = rstd u + A beta, so every row gets (A beta)(sB)^T
+                extra_q = extra_1 = None
+                if "qkv" in a_f32:
+                    extra_q = b_bf16["qkv"].float().cpu() @ (a_f32["qkv"] @ b1.float())
+                    fold(Fl, "a_qkv", a_f32["qkv"], g1, b1, None, ("lora_a_qkv_g", "s_a_qkv", None))
+                if "fc1" in a_f32:
+                    extra_1 = b_bf16["fc1"].float().cpu() @ (a_f32["fc1"] @ b2.float())
+                    fold(Fl, "a_fc1", a_f32["fc1"], g2, b2, None, ("lora_a_fc1_g", "s_a_fc1", None))
+                fold(Fl, "qkv", torch.cat([sd[f"{ap}.q_proj.weight"], sd[f"{ap}.k_proj.weight"],
+                                           sd[f"{ap}.v_proj.weight"]], dim=0), g1, b1,
+                     bq.cpu() if extra_q is None else bq.cpu() + extra_q, ("w_qkv_g", "s_qkv", "b_qkv_f"))
+                fold(Fl, "fc1", sd[f"{lp}.mlp.fc1.weight"], g2, b2,
+                     sd[f"{lp}.mlp.fc1.bias"] if extra_1 is None else sd[f"{lp}.mlp.fc1.bias"] + extra_1,
+                     ("w_fc1_g", "s_fc1", "b_fc1_f"))
+            a_f32.clear()
+            b_bf16.clear()
 
         w = _lib.TowerWeights()
         cfg = _lib.TowerConfig()
@@ -333,6 +385,9 @@ class B200ClipModel:
                    f"clm_tower_create({kind})")
         self._towers[kind] = handle.value
         self._keep[kind] = keep
+        self._folds[kind] = folds if self.ln_fold else None
+        if self.ln_fold:
+            _lib.check(self._lib.clm_tower_set_ln_fold(handle.value, folds), f"clm_tower_set_ln_fold({kind})")
         _lib.check(self._lib.clm_tower_set_residual_dtype(handle.value, _RESIDUAL_CODES[self.residual_dtype]),
                    f"clm_tower_set_residual_dtype({kind})")
 
@@ -342,6 +397,7 @@ class B200ClipModel:
             self._lib.clm_tower_destroy(h)
         self._towers.clear()
         self._keep.clear()
+        self._folds.clear()
 
     def __del__(self):
         try:

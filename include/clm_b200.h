@@ -72,6 +72,11 @@ int clm_vision_embed_ln_ex(const float* patch_out, const float* class_emb, const
 int clm_pool_ln_ex(const void* h, int h_dtype, const int32_t* row_idx_or_null, const float* gamma,
                    const float* beta, void* y_bf16, int batch, int tokens, int dim, float eps, void* stream);
 
+/* stats[row] = (mean, 1/sqrt(var + eps)) of every row of a bf16 residual stream h [rows, dim]; stats fp32
+ * [rows, 2].  The row statistics of nn.LayerNorm (modeling_clip.py:359,361) for a GEMM that has the LayerNorm
+ * folded in (clm_gemm_ln_epi). */
+int clm_row_stats(const void* h_bf16, float* stats, int rows, int dim, float eps, void* stream);
+
 /* Row L2 normalisation, no epsilon: x / ||x||  (models/clip_model.py:116,148;
  * src/embedding/search.py:68,93).  fp32 in, fp32 out (may alias), optional bf16 copy. */
 int clm_l2norm(const float* x, float* y, void* y_bf16_or_null, int rows, int dim, void* stream);
@@ -146,6 +151,22 @@ int clm_gemm_epi(const void* A, int lda, const void* W, int ldw, int M, int N, i
                  const void* A2, int lda2, const void* W2, int ldw2, int K2,
                  void* out, int ldo, int out_dtype, const float* bias,
                  const float* residual, int ldr, int epilogue, void* stream);
+
+/* nn.LayerNorm folded into the nn.Linear that consumes it (layer_norm1 -> q/k/v, layer_norm2 -> fc1;
+ * modeling_clip.py:359-362,368-369), for a bf16 residual stream:
+ *   LN(h) W^T + b  =  rstd (h Wg^T - mean * col_sums) + bias',   Wg = W diag(gamma) (bf16), col_sums[n] = sum_k Wg[n,k]
+ *   (of the bf16 values, in fp32), bias' = b + W beta.
+ * H is the raw bf16 stream [M, K] (no normalised copy exists), row_stats = clm_row_stats(H).
+ * ln_mode 1: out = act( rstd (acc - mean col_sums) + bias ).  The optional (A2, W2) K-extension is inside acc, so A2
+ *   must be the LoRA down-projection DIVIDED by rstd, which is what ln_mode 2 produces:
+ * ln_mode 2: out = (acc - mean col_sums) + bias.  With Wg = A diag(gamma) and bias = NULL this is
+ *   u = (LN(h) A^T - A beta) / rstd; the constant (A beta) (sB)^T the adapter adds to every row belongs into the bias'
+ *   of the ln_mode 1 GEMM (kernels.py fold_layernorm / models/clip_model.py do this on the host).
+ * No residual; out bf16 or fp32; everything else as clm_gemm_epi. */
+int clm_gemm_ln_epi(const void* H, int ldh, const void* Wg, int ldw, int M, int N, int K,
+                    const void* A2, int lda2, const void* W2, int ldw2, int K2,
+                    void* out, int ldo, int out_dtype, const float* bias, const float* row_stats,
+                    const float* col_sums, int ln_mode, int epilogue, void* stream);
 
 /* Debug / test hook: the kernel instantiation the calling thread's last clm_gemm_epi selected, encoded as
  * BN*100 + ctas*10 + epilogue (ctas: 1 = single CTA, 2 = cta_group::2 pair; epilogue: 0 = per-thread,
@@ -233,6 +254,19 @@ size_t clm_tower_workspace_bytes(const clm_tower* t, int batch);
  * clm_tower_residual_dtype returns the current setting. */
 int clm_tower_set_residual_dtype(clm_tower* t, int dtype);
 int clm_tower_residual_dtype(const clm_tower* t);
+
+/* LayerNorm folding for the bf16 residual stream: per layer, the weights of the two GEMMs that consume a
+ * LayerNorm (fused QKV, fc1) and of their LoRA down-projections with gamma folded in, see clm_gemm_ln_epi.  With
+ * these set (and the stream in bf16) the per-layer LayerNorm passes are replaced by clm_row_stats (half the bytes)
+ * and the normalisation happens in the GEMM epilogues.  Device pointers; the caller keeps them alive.
+ * folds = NULL switches folding off again. */
+typedef struct {
+  const void* w_qkv_g; const float* s_qkv; const float* b_qkv_f; /* [3D, D] bf16, [3D], [3D] (incl. the adapter's constant) */
+  const void* lora_a_qkv_g; const float* s_a_qkv;                /* [cols_qkv, D] bf16, [cols_qkv], or NULL */
+  const void* w_fc1_g; const float* s_fc1; const float* b_fc1_f; /* [mlp, D] bf16, [mlp], [mlp] */
+  const void* lora_a_fc1_g; const float* s_a_fc1;                /* [cols_fc1, D] bf16, [cols_fc1], or NULL */
+} clm_layer_ln_fold;
+int clm_tower_set_ln_fold(clm_tower* t, const clm_layer_ln_fold* folds /* [layers] or NULL */);
 
 /* models/clip_model.py:89-118 without the PIL step: pixel_values fp32 [batch,3,H,W]
  * -> embeddings fp32 [batch, P]; normalize != 0 applies x/||x|| (clip_model.py:116),

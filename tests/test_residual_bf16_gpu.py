@@ -113,6 +113,86 @@ def test_layernorm_over_a_bf16_stream(cuda_device, dim, rows):
     assert torch.allclose(y.float().cpu(), ref, atol=2e-2, rtol=8e-3)
 
 
+def _ln_ref(h, g, b, eps=1e-5):
+    return torch.nn.functional.layer_norm(h.float(), (h.shape[1],), g, b, eps)
+
+
+@pytest.mark.parametrize("dim", [128, 512, 768, 1024])
+def test_row_stats(cuda_device, dim):
+    h = (_randn((1000, dim), 5, 3.0) + 0.7).bfloat16()
+    st = K.row_stats(h.to(cuda_device), 1e-5).cpu()
+    hf = h.float()
+    assert torch.allclose(st[:, 0], hf.mean(dim=1), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(st[:, 1], torch.rsqrt(hf.var(dim=1, unbiased=False) + 1e-5), atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("M,N,Kd,act,variant", [
+    (8192, 3072, 768, K.EPI_QUICKGELU, 25621),   # fc1 of ViT-B/16 on the CTA-pair kernel
+    (8192 - 77, 3072, 1024, K.EPI_NONE, 25621),  # QKV of ViT-L/14, ragged last pair tile
+    (394, 2304, 768, K.EPI_NONE, None),          # single-CTA tiles
+    (77, 2048, 512, K.EPI_QUICKGELU, None),
+])
+def test_gemm_with_folded_layernorm(cuda_device, M, N, Kd, act, variant):
+    """act(LN(h) W^T + b) with gamma folded into W and (mean, rstd) applied in the epilogue, against fp32 torch on the
+    same bf16 stream.  The stream has a per-row offset several times its spread: the rank-1 correction has to cancel it."""
+    d = cuda_device
+    h = (_randn((M, Kd), 80, 1.5) + _randn((M, 1), 81, 4.0)).bfloat16()
+    w = _randn((N, Kd), 82, Kd ** -0.5)
+    g = _randn((Kd,), 83) * 0.2 + 1.0
+    b = _randn((Kd,), 84) * 0.1
+    bias = _randn((N,), 85)
+    wg, cs, bf = K.fold_layernorm(w, g, b, bias)
+    hd = h.to(d)
+    st = K.row_stats(hd, 1e-5)
+    out = K.gemm_ln_epi(hd, wg.to(d), st, cs.to(d), bf.to(d), ln_mode=1, act=act)
+    if variant is not None:
+        assert _variant() == variant, _variant()
+    ref = _ln_ref(hd, g.to(d), b.to(d)) @ w.to(d).T + bias.to(d)
+    if act == K.EPI_QUICKGELU:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    err = (out.float() - ref).abs()
+    tol = 3e-2 + 1e-2 * ref.abs()   # bf16 output + bf16 rounding of W diag(gamma) over K terms
+    assert not (err > tol).any(), f"max err {float(err.max()):.4g}, {int((err > tol).sum())} off"
+    # fp32 output: the only error left is the rounding of the folded weight
+    out32 = K.gemm_ln_epi(hd, wg.to(d), st, cs.to(d), bf.to(d), ln_mode=1, act=act, out_dtype=torch.float32)
+    ref_w = _ln_ref(hd, torch.ones_like(g).to(d), torch.zeros_like(b).to(d)) @ wg.to(d).float().T + bf.to(d)
+    if act == K.EPI_QUICKGELU:
+        ref_w = ref_w * torch.sigmoid(1.702 * ref_w)
+    assert torch.allclose(out32, ref_w, atol=4e-3, rtol=2e-3), float((out32 - ref_w).abs().max())
+
+
+def test_gemm_with_folded_layernorm_and_lora_extension(cuda_device):
+    """The LoRA pair in folded form: u = (LN(h) A^T) / rstd from ln_mode 2, then u (sB)^T inside the accumulator of
+    the ln_mode 1 GEMM, whose epilogue multiplies by rstd."""
+    d = cuda_device
+    M, D, cols, r = 8192, 768, 64, 16
+    h = (_randn((M, D), 90, 1.5) + _randn((M, 1), 91, 3.0)).bfloat16().to(d)
+    w = _randn((3 * D, D), 92, D ** -0.5)
+    g = _randn((D,), 93) * 0.2 + 1.0
+    b = _randn((D,), 94) * 0.1
+    bias = _randn((3 * D,), 95)
+    a_cat = torch.zeros((cols, D)); a_cat[:2 * r] = _randn((2 * r, D), 96, D ** -0.5)
+    b_cat = torch.zeros((3 * D, cols)); b_cat[:D, :r] = _randn((D, r), 97, 0.1); b_cat[2 * D:, r:2 * r] = _randn((D, r), 98, 0.1)
+    b_cat_b = b_cat.bfloat16().to(d)
+    st = K.row_stats(h, 1e-5)
+    ag, s_a, c_a = K.fold_layernorm(a_cat, g, b)          # c_a = A beta
+    u = K.gemm_ln_epi(h, ag.to(d), st, s_a.to(d), None, ln_mode=2)
+    x = _ln_ref(h, g.to(d), b.to(d))
+    t_ref = x @ a_cat.to(d).T
+    t_got = u.float() * st[:, 1:2] + c_a.to(d)
+    assert torch.allclose(t_got, t_ref, atol=3e-2, rtol=2e-2), float((t_got - t_ref).abs().max())
+    # the adapter's constant (A beta)(sB)^T goes into the folded bias of the wide GEMM
+    wg, cs, bf = K.fold_layernorm(w, g, b, bias + b_cat_b.float().cpu() @ c_a)
+    out = K.gemm_ln_epi(h, wg.to(d), st, cs.to(d), bf.to(d), ln_mode=1, a2=u, w2=b_cat_b)
+    assert _variant() == 25621, _variant()
+    ref = x @ w.to(d).T + bias.to(d) + t_ref @ b_cat_b.float().T
+    err = (out.float() - ref).abs()
+    tol = 3e-2 + 1e-2 * ref.abs()
+    assert not (err > tol).any(), f"max err {float(err.max()):.4g}"
+    base = x @ w.to(d).T + bias.to(d)
+    assert float((ref[:, :D] - base[:, :D]).abs().max()) > 1e-2  # the adapter does something on q
+
+
 def _model(arch_name, device, residual_dtype, r=16, alpha=32, targets=("q_proj", "v_proj")):
     from clip_lora_match_b200.models import clip_model as CM
     from clip_lora_match_b200.models.lora_adapter import LoraAdapter, LoraConfig
@@ -145,6 +225,15 @@ def test_encoder_with_bf16_stream_vs_oracle_and_vs_fp32_stream(cuda_device, arch
     print(f"[bf16 stream vs oracle] {arch}: image {mi} text {mt}")
     assert mi["cos_min"] >= 0.999 and mt["cos_min"] >= 0.999, (mi, mt)        # north_star
     assert mi["rel_l2_max"] <= 0.04 and mt["rel_l2_max"] <= 0.04, (mi, mt)
+    # the same stream with standalone LayerNorm passes instead of the folded GEMMs
+    gpu.set_ln_fold(False)
+    img16n, txt16n = gpu.encode_images(pv).cpu(), gpu.encode_texts(ids).cpu()
+    ni, nt = O.parity_metrics(img16n, O.encode_images(model, pv)), O.parity_metrics(txt16n, O.encode_texts(model, ids, mask))
+    print(f"[bf16 stream, LayerNorm passes, vs oracle] {arch}: image {ni} text {nt}")
+    assert ni["cos_min"] >= 0.999 and nt["cos_min"] >= 0.999, (ni, nt)
+    assert not torch.equal(img16n, img16)
+    gpu.set_ln_fold(True)
+    assert torch.equal(gpu.encode_images(pv).cpu(), img16)
     gpu.set_residual_dtype("float32")
     for h in gpu._towers.values():
         assert _lib.load().clm_tower_residual_dtype(h) == _lib.OUT_F32

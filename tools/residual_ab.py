@@ -9,6 +9,7 @@ from clip_lora_match_b200 import _lib
 from clip_lora_match_b200.models import clip_model as CM
 from clip_lora_match_b200.models.lora_adapter import LoraConfig, init_lora_adapter
 
+ARMS = (("float32", False), ("bfloat16", False), ("bfloat16", True))
 ARCHS = {"l14": ("openai/clip-vit-large-patch14", 512), "b16": ("openai/clip-vit-base-patch16", 1024)}
 
 
@@ -37,8 +38,9 @@ def main():
         emb = {}
         for _ in range(3): model.encode_images(pv)
         for r in range(a.rounds):
-            for dt in ("float32", "bfloat16"):
-                model.set_residual_dtype(dt)
+            for dt, fold in ARMS:
+                model.set_residual_dtype(dt); model.set_ln_fold(fold)
+                dt = dt + ("+fold" if fold and dt == "bfloat16" else "")
                 for _ in range(3): emb[dt] = model.encode_images(pv)
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -50,8 +52,9 @@ def main():
                 e1.record(); torch.cuda.synchronize()
                 print(json.dumps({"arch": key, "round": r, "residual": dt, "ms_per_step": round(e0.elapsed_time(e1) / a.steps, 3),
                                   "sm_mhz": clk, "power_w": pw}), flush=True)
-        for dt in ("float32", "bfloat16"):
-            model.set_residual_dtype(dt)
+        for dt, fold in ARMS:
+            model.set_residual_dtype(dt); model.set_ln_fold(fold)
+            dt = dt + ("+fold" if fold and dt == "bfloat16" else "")
             for _ in range(2): model.encode_images(pv)
             lib.clm_prof_enable(1)
             for _ in range(2): model.encode_images(pv)
@@ -60,8 +63,9 @@ def main():
             recs = recs[-(len(recs) // 2):]
             kinds = {k: round(sum(x[3] for x in recs if x[0] == k), 3) for k in ("gemm", "attention", "elementwise")}
             print(json.dumps({"arch": key, "residual": dt, "kernel_ms_profiled_step": kinds, "launches": len(recs)}), flush=True)
-        cos = torch.nn.functional.cosine_similarity(emb["float32"], emb["bfloat16"], dim=-1)
-        print(json.dumps({"arch": key, "cos_bf16_vs_fp32_stream_min": float(cos.min()), "mean": float(cos.mean())}), flush=True)
+        for other in ("bfloat16", "bfloat16+fold"):
+            cos = torch.nn.functional.cosine_similarity(emb["float32"], emb[other], dim=-1)
+            print(json.dumps({"arch": key, "cos_vs_fp32_stream": other, "min": float(cos.min()), "mean": float(cos.mean())}), flush=True)
         del model, pv
         torch.cuda.empty_cache()
 

@@ -6,6 +6,8 @@
 #include <mutex>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "clm_common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -31,6 +33,15 @@ extern "C" int clm_device_check(void) {
     return CLM_ERR_UNSUPPORTED;
   }
   return CLM_OK;
+}
+
+int clm_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CLM_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on;
 }
 
 int clm_num_sms() {

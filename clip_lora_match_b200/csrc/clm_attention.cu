@@ -552,6 +552,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();  // the QKV GEMM's output is visible from here on (prologue overlapped its tail)
+  pdl_trigger();
 
   if (warp == kTmaWarpV1) {
     // ================= TMA producer =================
@@ -1199,6 +1201,8 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();  // the QKV GEMM's output is visible from here on (prologue overlapped its tail)
+  pdl_trigger();
 
   if (warp >= kSplitCtlWarp0) {
     setmaxnreg_dec<kRegsSplitCtl>();
@@ -1687,12 +1691,12 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   if (split) {
     if (split == 256) {
       CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel_split<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      attention_kernel_split<256><<<grid, kThreadsSplit, smem_bytes, stream>>>(map64, map16, map_out,
-                                                                              static_cast<__nv_bfloat16*>(out), p);
+      CLM_CUDA_CHECK(clm_launch_pdl(attention_kernel_split<256>, dim3(grid), dim3(kThreadsSplit), smem_bytes, stream,
+                                    map64, map16, map_out, static_cast<__nv_bfloat16*>(out), p));
     } else {
       CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel_split<208>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      attention_kernel_split<208><<<grid, kThreadsSplit, smem_bytes, stream>>>(map64, map16, map_out,
-                                                                              static_cast<__nv_bfloat16*>(out), p);
+      CLM_CUDA_CHECK(clm_launch_pdl(attention_kernel_split<208>, dim3(grid), dim3(kThreadsSplit), smem_bytes, stream,
+                                    map64, map16, map_out, static_cast<__nv_bfloat16*>(out), p));
     }
     CLM_CUDA_CHECK(cudaGetLastError());
     return CLM_OK;
@@ -1700,13 +1704,13 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
   if (causal) {
     CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attention_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(
-        map64, map16, map_out, static_cast<__nv_bfloat16*>(out), p);
+    CLM_CUDA_CHECK(clm_launch_pdl(attention_kernel<true>, dim3(grid), dim3(kThreads), smem_bytes, stream, map64, map16,
+                                  map_out, static_cast<__nv_bfloat16*>(out), p));
   } else {
     CLM_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attention_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(
-        map64, map16, map_out, static_cast<__nv_bfloat16*>(out), p);
+    CLM_CUDA_CHECK(clm_launch_pdl(attention_kernel<false>, dim3(grid), dim3(kThreads), smem_bytes, stream, map64, map16,
+                                  map_out, static_cast<__nv_bfloat16*>(out), p));
   }
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;

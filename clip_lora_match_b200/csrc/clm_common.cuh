@@ -52,6 +52,28 @@ int clm_make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint6
 
 int clm_num_sms();
 
+// Programmatic dependent launch (PDL).  A kernel launched through clm_launch_pdl may be scheduled while the kernel
+// before it in the stream is still draining; it runs its prologue (barrier init, TMEM allocation, descriptor
+// prefetch), then every thread calls pdl_wait() BEFORE its first access to global memory -- that returns once the
+// preceding grid has completed and its writes are visible -- and pdl_trigger() lets the kernel after it do the
+// same.  Both instructions are no-ops in a kernel launched without the attribute.  CLM_PDL=0 launches plainly.
+int clm_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t clm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = clm_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Launch accounting + optional per-launch CUDA-event timing (bench.py's roofline numbers).
 // Every kernel launch in the library goes through a ProfScope: it always counts the launch and,
 // when profiling is enabled, brackets it with two events on the launching stream.
@@ -198,6 +220,8 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
                : "l"(map), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the newest `N` groups of this thread have finished READING their shared-memory source
 template <int N>

@@ -85,6 +85,8 @@ template <int NV, bool kH16 = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows, float eps) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
   constexpr int D = NV * 128;
@@ -100,6 +102,8 @@ layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
 template <int NV>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 row_stats_kernel(const __nv_bfloat16* __restrict__ h, float2* __restrict__ stats, int rows, float eps) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
   constexpr int D = NV * 128;
@@ -338,11 +342,11 @@ extern "C" int clm_layernorm_ex(const void* x, int x_dtype, const float* gamma, 
   const bool h16 = x_dtype == CLM_OUT_BF16;
   ProfScope prof(CLM_K_ELEMENTWISE, 0.0, (h16 ? 4.0 : 6.0) * rows * dim, s);
   if (h16) {
-    CLM_DISPATCH_DIM(dim, (layernorm_kernel<NV, true><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
-                              x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), rows, eps)));
+    CLM_DISPATCH_DIM(dim, (clm_launch_pdl(layernorm_kernel<NV, true>, dim3(blocks_for(rows)), dim3(kWarpsPerBlock * 32),
+                                          0, s, x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), rows, eps)));
   } else {
-    CLM_DISPATCH_DIM(dim, (layernorm_kernel<NV, false><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
-                              x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), rows, eps)));
+    CLM_DISPATCH_DIM(dim, (clm_launch_pdl(layernorm_kernel<NV, false>, dim3(blocks_for(rows)), dim3(kWarpsPerBlock * 32),
+                                          0, s, x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), rows, eps)));
   }
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
@@ -354,8 +358,9 @@ extern "C" int clm_row_stats(const void* h_bf16, float* stats, int rows, int dim
   if (rows == 0) return CLM_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 2.0 * rows * dim + 8.0 * rows, s);
-  CLM_DISPATCH_DIM(dim, (row_stats_kernel<NV><<<blocks_for(rows), kWarpsPerBlock * 32, 0, s>>>(
-                            static_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<float2*>(stats), rows, eps)));
+  CLM_DISPATCH_DIM(dim, (clm_launch_pdl(row_stats_kernel<NV>, dim3(blocks_for(rows)), dim3(kWarpsPerBlock * 32), 0, s,
+                                        static_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<float2*>(stats),
+                                        rows, eps)));
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
 }

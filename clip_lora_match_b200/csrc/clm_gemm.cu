@@ -220,6 +220,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();     // everything above overlapped the tail of the previous kernel; its outputs are visible from here on
+  pdl_trigger();
 
   if (warp == kTmaWarp) {
     // ================= TMA producer (every CTA loads its own A rows and its share of B) ======
@@ -565,13 +567,15 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCtas;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = clm_pdl_enabled() ? 2 : 1;
   CLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, kCtas, kEpi>, ma, mb, ma2, mb2, mo, M, N, kb_main,
                                     kb_ext, ep));
   return CLM_OK;

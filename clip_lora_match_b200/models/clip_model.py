@@ -746,8 +746,8 @@ def _get_device(device_str: Optional[str] = None) -> torch.device:
 
 def _get_dtype(dtype_str: str, device: torch.device) -> torch.dtype:
     """The reference picks fp16 on CUDA else fp32 (:31-34).  Here the arithmetic type is fixed:
-    bf16 tensor-core operands, fp32 accumulation/residual/LN/softmax; the config key is
-    accepted for compatibility and reported."""
+    bf16 tensor-core operands, fp32 accumulation / LN statistics / softmax; the config key selects the type of
+    the residual stream (load_clip_model) and is otherwise reported."""
     return torch.bfloat16
 
 
@@ -830,7 +830,13 @@ def load_clip_model(
                 print(f"[clip_model] Loading LoRA weights from: {lora_path}")
                 lora = load_lora_adapter(lora_path)
 
-    model = B200ClipModel(arch, state_dict, lora=lora, device=device)
+    # model.dtype of the YAML: the reference runs the WHOLE model in fp16 for "float16" on CUDA and in fp32 otherwise
+    # (models/clip_model.py:31-34).  Here the GEMM operands are always bf16; the key selects the residual stream:
+    # "float32" keeps it in fp32 (the shipped config), a half type stores it in bf16 (CLM_RESIDUAL_DTYPE overrides).
+    stream = os.environ.get("CLM_RESIDUAL_DTYPE") or (
+        "float32" if str(model_cfg.get("dtype", "bfloat16")).lower() in ("float32", "fp32", "float") else "bfloat16")
+    model = B200ClipModel(arch, state_dict, lora=lora, device=device, residual_dtype=stream)
+    print(f"[clip_model] residual stream: {model.residual_dtype}")
     processor = ClmProcessor(model_name)
     model.eval()
     return model, processor, device

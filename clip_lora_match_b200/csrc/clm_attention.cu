@@ -88,6 +88,9 @@ struct AttnParams {
   // other softmax group, so the two groups take turns on the MUFU pipe instead of running in lockstep (both
   // exponentiating, then both waiting for their P V and output phases with the pipe idle)
   int serial;
+  // reverse != 0: walk the (image, head) items from the last to the first -- a scheduling hint for L2 reuse between
+  // consecutive kernels (the tower alternates the direction), no effect on the result
+  int reverse;
   // TMEM column of the S / P region and of the O accumulator used by tiles of parity 0 / 1;
   // o_alias: O lives inside the same parity's S region (dead by then), so S(t+2) waits for the drain
   int s_col0, s_col1, o_col0, o_col1, o_alias0, o_alias1;
@@ -565,7 +568,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       int tl = 0;
 #endif
       for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-        const int b = it / H, h = it % H;
+        const int iv = p.reverse ? p.num_items - 1 - it : it, b = iv / H, h = iv % H;
         const int row_base = b * T;
         TRACE(tl, 0);
         mbar_wait(&stage_empty[st], ph ^ 1);
@@ -791,7 +794,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       for (int it = blockIdx.x; it < p.num_items; it += gridDim.x)
       for (int mt = 0; mt < p.mtiles; ++mt, ++t) {
         if ((t & 1) != g) continue;
-        const int b = it / H, h = it - b * H;
+        const int iv = p.reverse ? p.num_items - 1 - it : it, b = iv / H, h = iv - b * H;
         const int qi = mt * 128 + r;
         const bool warp_live = mt * 128 + q * 32 < T;
         int valid = T;
@@ -889,7 +892,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, ++li)
     for (int mt = 0; mt < p.mtiles; ++mt, ++t) {
       if ((t & 1) != g) continue;
-      const int b = it / H, h = it - b * H;
+      const int iv = p.reverse ? p.num_items - 1 - it : it, b = iv / H, h = iv - b * H;
       const uint32_t par = static_cast<uint32_t>((t >> 1) & 1);
       const int qi = mt * 128 + r;                     // query position in the sequence
       const bool warp_live = mt * 128 + q * 32 < T;    // does this warp own any real row?
@@ -1075,7 +1078,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
     uint32_t ph = 0;
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, ++tl) {
       if ((tl & 1) == tw) {
-        const int b = it / H, h = it - b * H;
+        const int iv = p.reverse ? p.num_items - 1 - it : it, b = iv / H, h = iv - b * H;
         TRACE(tl, 0);
         mbar_wait(&stage_full[st], ph);
         TRACE(tl, 1);
@@ -1216,7 +1219,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
         int tl = 0;
 #endif
         for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-          const int b = it / H, h = it % H;
+          const int iv = p.reverse ? p.num_items - 1 - it : it, b = iv / H, h = iv % H;
           const int row_base = b * T;
           TRACE(tl, 0);
           mbar_wait(&stage_empty[st], ph ^ 1);
@@ -1360,7 +1363,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
     int pend_stage = -1;  // stage whose share this warp pair still has to release (stage_out == 2)
     bool pend_store = false;
     for (int n = 0; t < n_tiles; ++n, t += 2) {
-      const int b = it / H, h = it - b * H;
+      const int iv = p.reverse ? p.num_items - 1 - it : it, b = iv / H, h = iv - b * H;
       const uint32_t par = static_cast<uint32_t>(n & 1);
       const int buf = n & 1;
       const bool warp_live = mt * 128 + q * 32 < T;
@@ -1527,7 +1530,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
       int st = 0, tl = 0;
       uint32_t ph = 0;
       for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, ++tl) {
-        const int b = it / H, h = it - b * H;
+        const int iv = p.reverse ? p.num_items - 1 - it : it, b = iv / H, h = iv - b * H;
         TRACE(tl, 0);
         mbar_wait(&stage_full[st], ph);
         TRACE(tl, 1);
@@ -1549,7 +1552,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
 }  // namespace
 
 int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int heads, int causal,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, int reverse) {
   CLM_REQUIRE(qkv && out && batch >= 0 && tokens > 0 && heads > 0, "clm_attention: bad argument");
   CLM_REQUIRE(tokens <= 384, "clm_attention: tokens=%d > 384 unsupported (CLIP uses <= 257)", tokens);
   if (batch == 0) return CLM_OK;
@@ -1576,6 +1579,7 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
     serial = !e ? -1 : (e[0] == '1' ? 1 : 0);
   }
   p.serial = serial > 0 ? 1 : 0;
+  p.reverse = reverse ? 1 : 0;
   p.Tk = p.xt ? T - 1 : p.Tp;
   if (p.xt) p.mtiles = p.Tk / 128;
   const long long items = static_cast<long long>(batch) * heads;
@@ -1727,5 +1731,5 @@ extern "C" int clm_attention_set_trace(void* dev_buf) {
 extern "C" int clm_attention(const void* qkv_bf16, void* out_bf16, int batch, int tokens, int heads,
                              int causal, void* stream) {
   return clm_attention_launch(qkv_bf16, out_bf16, batch, tokens, heads, causal,
-                              static_cast<cudaStream_t>(stream));
+                              static_cast<cudaStream_t>(stream), 0);
 }

@@ -2,6 +2,8 @@
 // token/patch embedding, pooling.  One warp owns one row; rows are read and written with
 // 128-bit accesses that are contiguous across the warp; statistics are fp32 and use the
 // two-pass (mean, then centred variance) form so they track torch's nn.LayerNorm closely.
+#include <stdlib.h>
+
 #include "clm_common.cuh"
 
 namespace {
@@ -101,11 +103,14 @@ layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
 // needs of the row -- half the traffic of the LayerNorm pass it replaces (no normalised copy is written)
 template <int NV>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-row_stats_kernel(const __nv_bfloat16* __restrict__ h, float2* __restrict__ stats, int rows, float eps) {
+row_stats_kernel(const __nv_bfloat16* __restrict__ h, float2* __restrict__ stats, int rows, float eps, int reverse) {
   pdl_wait();
   pdl_trigger();
-  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  // reverse: the first blocks take the LAST rows, so the pass ends on rows 0.. and leaves those in the L2 -- the rows the
+  // GEMM that follows reads first (and it starts on the rows the reduce-add GEMM before it touched last)
+  int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (reverse) row = rows - 1 - row;
   constexpr int D = NV * 128;
   constexpr float inv_n = 1.0f / D;
   Row<NV> r;
@@ -352,7 +357,14 @@ extern "C" int clm_layernorm_ex(const void* x, int x_dtype, const float* gamma, 
   return CLM_OK;
 }
 
+int clm_row_stats_dir(const void* h_bf16, float* stats, int rows, int dim, float eps, void* stream, int reverse);
+
 extern "C" int clm_row_stats(const void* h_bf16, float* stats, int rows, int dim, float eps, void* stream) {
+  return clm_row_stats_dir(h_bf16, stats, rows, dim, eps, stream, 0);
+}
+
+// reverse: block order only (see row_stats_kernel); the tower alternates the direction of consecutive kernels
+int clm_row_stats_dir(const void* h_bf16, float* stats, int rows, int dim, float eps, void* stream, int reverse) {
   CLM_REQUIRE(h_bf16 && stats && rows >= 0, "clm_row_stats: bad argument");
   CLM_REQUIRE((reinterpret_cast<uintptr_t>(stats) & 7) == 0, "clm_row_stats: stats must be 8-byte aligned");
   if (rows == 0) return CLM_OK;
@@ -360,7 +372,7 @@ extern "C" int clm_row_stats(const void* h_bf16, float* stats, int rows, int dim
   ProfScope prof(CLM_K_ELEMENTWISE, 0.0, 2.0 * rows * dim + 8.0 * rows, s);
   CLM_DISPATCH_DIM(dim, (clm_launch_pdl(row_stats_kernel<NV>, dim3(blocks_for(rows)), dim3(kWarpsPerBlock * 32), 0, s,
                                         static_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<float2*>(stats),
-                                        rows, eps)));
+                                        rows, eps, reverse)));
   CLM_CUDA_CHECK(cudaGetLastError());
   return CLM_OK;
 }

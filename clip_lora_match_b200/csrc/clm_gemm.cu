@@ -91,6 +91,9 @@ struct EpiParams {
   const float2* row_stats;
   const float* col_s;
   int ln_mode;
+  // walk the tile list from its end (last rows first): a scheduling hint for L2 reuse between consecutive kernels
+  // (CLM_EPI_REVERSE), no effect on the result
+  int reverse;
 };
 
 __device__ __forceinline__ float ln_fix(float v, float b, float s, float neg_mu, float alpha) {
@@ -231,8 +234,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       for (int unit = worker; unit < num_tiles; unit += num_workers) {
         const int tile = unit / ksplit, ks = unit - tile * ksplit;
         const int kb_lo = ks * ep.kb_per, kb_hi = (ksplit == 1 || kb_lo + ep.kb_per > kb_total) ? kb_total : kb_lo + ep.kb_per;
-        const int m0 = (tile / n_tiles) * TM + static_cast<int>(rank) * BM;
-        const int n0 = (tile % n_tiles) * BN + static_cast<int>(rank) * (BN / kCtas);
+        const int tpos = ep.reverse ? (m_tiles * n_tiles - 1 - tile) : tile;  // reverse: last rows first
+        const int m0 = (tpos / n_tiles) * TM + static_cast<int>(rank) * BM;
+        const int n0 = (tpos % n_tiles) * BN + static_cast<int>(rank) * (BN / kCtas);
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
@@ -320,8 +324,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     for (int unit = worker; unit < num_tiles; unit += num_workers) {
       const int tile = unit / ksplit;
       const float* bias = (unit - tile * ksplit == 0) ? ep.bias : nullptr;  // the first k range of a tile adds the bias
-      const int m0 = (tile / n_tiles) * TM + static_cast<int>(rank) * BM + q * 32;
-      const int n0 = (tile % n_tiles) * BN + (kSplit ? half * (BN / 2) : 0);
+      const int tpos = ep.reverse ? (m_tiles * n_tiles - 1 - tile) : tile;
+      const int m0 = (tpos / n_tiles) * TM + static_cast<int>(rank) * BM + q * 32;
+      const int n0 = (tpos % n_tiles) * BN + (kSplit ? half * (BN / 2) : 0);
       const bool rows_live = active && m0 < M;
       const bool ln = ep.row_stats != nullptr;  // warp-uniform
       float ln_mu = 0.f, ln_alpha = 1.f;  // ln_mu holds -mean; loaded while the tile's MMAs are still running
@@ -467,8 +472,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
-      const int m0 = (tile / n_tiles) * TM + static_cast<int>(rank) * BM + q * 32;
-      const int n0 = (tile % n_tiles) * BN + half * (BN / 2);
+      const int tpos = ep.reverse ? (m_tiles * n_tiles - 1 - tile) : tile;
+      const int m0 = (tpos / n_tiles) * TM + static_cast<int>(rank) * BM + q * 32;
+      const int n0 = (tpos % n_tiles) * BN + half * (BN / 2);
       float4 rcur[8], rnxt[8];  // residual of the current / next chunk (coalesced layout)
       auto load_residual = [&](float4 (&dst)[8], int col0) {
         const int col = col0 + piece * 4;
@@ -675,6 +681,7 @@ int clm_gemm_launch(const void* A, int lda, const void* W, int ldw, int M, int N
   ep.row_stats = reinterpret_cast<const float2*>(row_stats);
   ep.col_s = col_sums;
   ep.ln_mode = ln_mode;
+  ep.reverse = (epilogue & CLM_EPI_REVERSE) ? 1 : 0;
   // epilogue variant: TMA tile stores, or a TMA reduce-add for the in-place residual update; the
   // per-thread legacy path only for residual != out / bf16 out + residual (CLM_GEMM_EPI=legacy forces it)
   static int force_legacy = -1;

@@ -39,6 +39,10 @@ extern "C" {
  * bit for bit.  Used by the training step's LoRA weight gradients (out [features, 64] += dy^T t over all token
  * rows).  No effect on any other call. */
 #define CLM_EPI_SPLIT_K 2
+/* Scheduling hint: walk the tile list from its end (the LAST rows of the output first).  A kernel that starts on the
+ * rows its predecessor touched last finds them in the L2; the tower alternates the direction from kernel to kernel.
+ * No effect on the result. */
+#define CLM_EPI_REVERSE 4
 #define CLM_OUT_BF16 0
 #define CLM_OUT_F32 1
 

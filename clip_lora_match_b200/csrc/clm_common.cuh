@@ -220,6 +220,18 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
                : "l"(map), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+// one lane of the (fully converged) warp: elect.sync, which ptxas treats as a uniform predicate source
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -180,7 +180,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint64_t* tmem_empty = tmem_full + kAccStages;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform, so the role dispatch below is a uniform branch and ptxas
+  // keeps the single-thread issue loops on the uniform datapath (see the MMA issuer)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = (kCtas == 2) ? cluster_ctarank() : 0u;  // position inside the CTA pair
   const int worker = (kCtas == 2) ? (blockIdx.x >> 1) : blockIdx.x;
@@ -222,7 +224,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   tc_fence_before();
   if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_slot, 0);  // (uniform for the same reason)
   pdl_wait();     // everything above overlapped the tail of the previous kernel; its outputs are visible from here on
   pdl_trigger();
 
@@ -262,6 +264,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // ================= MMA issuer (leader CTA only) =================
     if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(TM, BN, 0, 0);
+      // K-major SWIZZLE_128B operand descriptor (umma_desc_sw128 with SBO = 1024): the high word is constant, the low
+      // word is (1 << 16) | (shared-memory address >> 4)
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -275,23 +281,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(smem + stage * C::kStageBytes);
-            const uint32_t b_addr = a_addr + C::kABytes;
+          // Every lane computes the (warp-uniform) operands; one elected lane issues.  With the operands provably
+          // uniform the four tcgen05.mma of a k-block are four UTCHMMA on uniform registers; under `if (lane == 0)`
+          // ptxas wrapped EACH of them (and each commit) in an ELECT / 5 x R2UR / branch loop -- ~150 instructions per
+          // k-block on the one warp whose issue rate paces the whole GEMM (the issuer was never seen waiting for
+          // operands or for TMEM, profiles/r2_ncu_l14_layer_gemms_bf16stream.md).
+          const uint32_t a_lo = (1u << 16) | (((smem_base + static_cast<uint32_t>(stage) * C::kStageBytes) & 0x3FFFFu) >> 4);
+          const uint32_t b_lo = a_lo + (C::kABytes >> 4);
+          const bool last_kb = (kb == kb_hi - 1);
+          if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              // advancing 16 bf16 (32 B) along K inside the 128-B swizzle atom
-              const uint64_t da = umma_desc_sw128(a_addr + k * 32, 1024);
-              const uint64_t db = umma_desc_sw128(b_addr + k * 32, 1024);
+              // advancing 16 bf16 (32 B = 2 descriptor units) along K inside the 128-B swizzle atom
+              const uint64_t da = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2u * k);
+              const uint64_t db = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2u * k);
               if (kCtas == 2) umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb != kb_lo || k != 0) ? 1u : 0u);
               else umma_bf16_ss(tmem_d, da, db, idesc, (kb != kb_lo || k != 0) ? 1u : 0u);
             }
             if (kCtas == 2) {
-              umma_commit_2sm(&empty[stage]);                           // frees the slot in both CTAs
-              if (kb == kb_hi - 1) umma_commit_2sm(&tmem_full[acc]);  // accumulators ready (both)
+              umma_commit_2sm(&empty[stage]);                 // frees the slot in both CTAs
+              if (last_kb) umma_commit_2sm(&tmem_full[acc]);  // accumulators ready (both)
             } else {
               umma_commit(&empty[stage]);
-              if (kb == kb_hi - 1) umma_commit(&tmem_full[acc]);
+              if (last_kb) umma_commit(&tmem_full[acc]);
             }
           }
           __syncwarp();

@@ -522,7 +522,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
   uint8_t* vxs = reinterpret_cast<uint8_t*>(xdot + 2 * 2 * 128);
   float* prow = reinterpret_cast<float*>(vxs + 16 * 64);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int T = p.T, H = p.H, Tp = p.Tp, Tk = p.Tk, D = p.H * kHeadDim;
   const int kv_bytes = Tp * 128;  // one of Q / K / V in a stage (Tp rows are loaded; the MMAs see Tk keys)
@@ -554,7 +554,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   pdl_wait();  // the QKV GEMM's output is visible from here on (prologue overlapped its tail)
   pdl_trigger();
 
@@ -614,7 +614,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       }
     };
     auto do_s = [&](const Cursor& c) {
-      if (lane == 0) {
+      if (elect_one_sync()) {  // uniform operands, one issuing lane: UTCHMMA straight from uniform registers
         const uint32_t q_addr = smem_u32(smem + c.st * p.stage_bytes);
         const uint32_t k_addr = q_addr + kv_bytes;
         const uint32_t sbase = tmem + static_cast<uint32_t>(p.s_col(c.t & 1));
@@ -639,7 +639,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       const int b = c.t & 1;
       const bool last = (++pv_cnt[c.st] == p.mtiles);
       if (last) pv_cnt[c.st] = 0;
-      if (lane == 0) {
+      if (elect_one_sync()) {  // uniform operands, one issuing lane: UTCHMMA straight from uniform registers
         const uint32_t v_addr = smem_u32(smem + c.st * p.stage_bytes) + 2 * kv_bytes;
         const uint32_t pbase = tmem + static_cast<uint32_t>(p.s_col(b));
         const uint32_t obase = tmem + static_cast<uint32_t>(p.o_col(b));
@@ -657,7 +657,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
       //   S0 -> [softmax blk 0] -> PV0 (O = P0 V0), S1 -> [softmax blk 1 + rescale of O] -> PV1 (O += P1 V1)
       // Every barrier of a stream completes twice per tile, so block 0 always waits parity 0, block 1 parity 1.
       auto mma_s = [&](const Cursor& c, int key0, int nk) {
-        if (lane == 0) {
+        if (elect_one_sync()) {  // uniform operands, one issuing lane: UTCHMMA straight from uniform registers
           const uint32_t q_addr = smem_u32(smem + c.st * p.stage_bytes);
           const uint32_t k_addr = q_addr + kv_bytes + static_cast<uint32_t>(key0) * 128u;
           const uint32_t sbase = tmem + static_cast<uint32_t>(p.s_col(c.t & 1));
@@ -671,7 +671,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constan
         __syncwarp();
       };
       auto mma_pv = [&](const Cursor& c, int key0, int nk, bool first, bool release) {
-        if (lane == 0) {
+        if (elect_one_sync()) {  // uniform operands, one issuing lane: UTCHMMA straight from uniform registers
           const int b = c.t & 1;
           const uint32_t v_addr = smem_u32(smem + c.st * p.stage_bytes) + 2 * kv_bytes + static_cast<uint32_t>(key0) * 128u;
           const uint32_t pbase = tmem + static_cast<uint32_t>(p.s_col(b));
@@ -1169,7 +1169,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
   uint8_t* vxs = reinterpret_cast<uint8_t*>(xdot + 2 * 2 * 2 * 128);  // [buf][16 warps][64 B]
   float* prow = reinterpret_cast<float*>(vxs + 2 * 16 * 64);          // [4 tail warps][288]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int T = p.T, H = p.H, Tp = p.Tp, Tk = p.Tk;
   const int D = p.H * kHeadDim;
@@ -1203,7 +1203,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   pdl_wait();  // the QKV GEMM's output is visible from here on (prologue overlapped its tail)
   pdl_trigger();
 
@@ -1266,7 +1266,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
         mbar_wait(&stage_full[st], ph);
         tc_fence_after();
         TRACE(t, 0);
-        if (lane == 0) {
+        if (elect_one_sync()) {  // uniform operands, one issuing lane: UTCHMMA straight from uniform registers
 #pragma unroll
           for (int k = 0; k < kHeadDim / 16; ++k)
             umma_bf16_ss(sbase, umma_desc_sw128(q_addr + mt * 16384 + k * 32, 1024),
@@ -1276,7 +1276,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
         __syncwarp();
         MBAR_WAIT_HOT(&p_half[b], par);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one_sync()) {  // uniform operands, one issuing lane: UTCHMMA straight from uniform registers
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             umma_bf16_ts(obase, sbase + ks * 8, umma_desc_sw128_mn(v_addr + ks * 2048), idesc_pv, ks != 0 ? 1u : 0u);
@@ -1285,7 +1285,7 @@ attention_kernel_split(const __grid_constant__ CUtensorMap map64, const __grid_c
         MBAR_WAIT_HOT(&p_full[b], par);
         tc_fence_after();
         TRACE(t, 1);
-        if (lane == 0) {
+        if (elect_one_sync()) {  // uniform operands, one issuing lane: UTCHMMA straight from uniform registers
 #pragma unroll
           for (int ks = 8; ks < kSplit / 16; ++ks) {
             const int kk = ks * 16 - 128;

@@ -79,7 +79,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   float* delta_s = lse_s + 128;                                     // [128] per query: rowsum(P dP)
   uint64_t* bars = reinterpret_cast<uint64_t*>(delta_s + 128);      // full, mma1, mma2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = lane_id();
   const int D = p.heads * 64;
   const size_t ld = 3 * static_cast<size_t>(D);
 
@@ -98,7 +98,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const int T = p.T, Tp = p.Tp;
   const int nch = Tp / 32;  // 32-column chunks of a score row
@@ -110,7 +110,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const int b = it / p.heads, h = it - b * p.heads;
     const int row0 = b * T;
     if (warp == 8) {
-      if (lane == 0) {
+      if (elect_one_sync()) {  // uniform operands: UTCHMMA straight from uniform registers
         mbar_arrive_expect_tx(&bars[0], 4 * kTileBytes);
         tma_load_2d(q_s, &map_qkv, &bars[0], h * 64, row0);
         tma_load_2d(k_s, &map_qkv, &bars[0], D + h * 64, row0);
@@ -219,7 +219,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     tc_fence_before();
     __syncthreads();  // every packed operand is in TMEM, every score column is dead
     if (warp == 8) {
-      if (lane == 0) {
+      if (elect_one_sync()) {  // uniform operands: UTCHMMA straight from uniform registers
         tc_fence_after();
         const uint32_t qa = smem_u32(q_s), ka = smem_u32(k_s), oa = smem_u32(o_s);
         const int nks = Tp / 16;

@@ -229,7 +229,7 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   uint64_t* tmem_empty = tmem_full + kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform (see clm_gemm.cu)
   const int lane = threadIdx.x & 31;
   const int num_units = p.q_tiles * p.splits;
 
@@ -258,7 +258,7 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   tc_fence_before();
   if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == kTmaWarp) {
     // ================= TMA producer =================
@@ -308,7 +308,7 @@ search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one_sync()) {  // uniform operands, one issuing lane: four UTCHMMA straight from uniform registers
             const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
             const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll

@@ -50,6 +50,11 @@ constexpr int kAccStages = 2;
 #ifndef CLM_GEMM_CTL_HI
 #define CLM_GEMM_CTL_HI 1
 #endif
+// bf16 epilogues: branch-free, one-piece-ahead loads of the per-column constants (0 = the piece-by-piece form)
+#ifndef CLM_GEMM_EPI_PREFETCH
+#define CLM_GEMM_EPI_PREFETCH 1
+#endif
+__device__ float g_zero_f32[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 constexpr int kTmaWarp = CLM_GEMM_CTL_HI ? 8 : 0;
 constexpr int kMmaWarp = CLM_GEMM_CTL_HI ? 9 : 1;
 constexpr int kEpiWarp0 = CLM_GEMM_CTL_HI ? 0 : 2;
@@ -409,6 +414,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               else mbar_arrive(&tmem_empty[acc]);
             }
           }
+#if CLM_GEMM_EPI_PREFETCH
+          if (live) {
+            // Per-column constants (bias, col_sums) without a branch and one piece AHEAD of the arithmetic: clamped
+            // column index (N % 8 == 0), a zero vector stands in for an absent array, and ln_fix with mean = 0,
+            // alpha = 1, s = 0 is exactly acc + bias.  The loads of piece p + 1 are in flight while piece p is computed
+            // (piece by piece under `if (bias && col < N)` every piece stalled on its own broadcast loads: a third of the
+            // epilogue warps' busy time in the stall samples).
+            const float* bsrc = bias ? bias : g_zero_f32;
+            const float* csrc = ln ? ep.col_s : g_zero_f32;
+            const int bstep = bias ? 1 : 0, cstep = ln ? 1 : 0;
+            auto col_of = [&](int p) { const int c = col0 + 8 * p; return c < N ? c : N - 8; };
+            float4 nb0, nb1, nc0, nc1;
+            {
+              const int c = col_of(0);
+              nb0 = __ldg(reinterpret_cast<const float4*>(bsrc + bstep * c)); nb1 = __ldg(reinterpret_cast<const float4*>(bsrc + bstep * c + 4));
+              nc0 = __ldg(reinterpret_cast<const float4*>(csrc + cstep * c)); nc1 = __ldg(reinterpret_cast<const float4*>(csrc + cstep * c + 4));
+            }
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {  // piece p = columns col0 + 8p .. + 7
+              const float4 b0 = nb0, b1 = nb1, c0 = nc0, c1 = nc1;
+              if (p + 1 < 8) {
+                const int c = col_of(p + 1);
+                nb0 = __ldg(reinterpret_cast<const float4*>(bsrc + bstep * c)); nb1 = __ldg(reinterpret_cast<const float4*>(bsrc + bstep * c + 4));
+                nc0 = __ldg(reinterpret_cast<const float4*>(csrc + cstep * c)); nc1 = __ldg(reinterpret_cast<const float4*>(csrc + cstep * c + 4));
+              }
+              const uint32_t* src = (p < 4) ? &v0[8 * p] : &v1[8 * (p - 4)];
+              float x0 = ln_fix(__uint_as_float(src[0]), b0.x, c0.x, ln_mu, ln_alpha);
+              float x1 = ln_fix(__uint_as_float(src[1]), b0.y, c0.y, ln_mu, ln_alpha);
+              float x2 = ln_fix(__uint_as_float(src[2]), b0.z, c0.z, ln_mu, ln_alpha);
+              float x3 = ln_fix(__uint_as_float(src[3]), b0.w, c0.w, ln_mu, ln_alpha);
+              float x4 = ln_fix(__uint_as_float(src[4]), b1.x, c1.x, ln_mu, ln_alpha);
+              float x5 = ln_fix(__uint_as_float(src[5]), b1.y, c1.y, ln_mu, ln_alpha);
+              float x6 = ln_fix(__uint_as_float(src[6]), b1.z, c1.z, ln_mu, ln_alpha);
+              float x7 = ln_fix(__uint_as_float(src[7]), b1.w, c1.w, ln_mu, ln_alpha);
+              if (ep.act == CLM_EPI_QUICKGELU) {
+                x0 = quick_gelu(x0); x1 = quick_gelu(x1); x2 = quick_gelu(x2); x3 = quick_gelu(x3);
+                x4 = quick_gelu(x4); x5 = quick_gelu(x5); x6 = quick_gelu(x6); x7 = quick_gelu(x7);
+              }
+              pk[4 * p + 0] = pack_bf16x2(x0, x1); pk[4 * p + 1] = pack_bf16x2(x2, x3);
+              pk[4 * p + 2] = pack_bf16x2(x4, x5); pk[4 * p + 3] = pack_bf16x2(x6, x7);
+            }
+          }
+#else
           if (live) {
 #pragma unroll
             for (int p = 0; p < 8; ++p) {  // piece p = columns col0 + 8p .. + 7
@@ -447,6 +495,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               pk[4 * p + 2] = pack_bf16x2(x4, x5); pk[4 * p + 3] = pack_bf16x2(x6, x7);
             }
           }
+#endif
         }
         if (live) {
           if (lane == 0) bulk_wait_read<0>();  // the previous slab has left the staging buffer

@@ -1655,17 +1655,19 @@ int clm_attention_launch(const void* qkv, void* out, int batch, int tokens, int 
     }
   }
   if (p.blocks == 2) p.stage_out = 0;  // the two-block path (T > 224) keeps per-thread stores
-  // Split kernel (attention_kernel_split<Tk>): ViT-B/16 (T = 197 -> 208 keys) and the extra-token plan of
-  // ViT-L/14 (256 keys).  An aliased O accumulator moves to columns [64, 128) of its S region.  CLM_ATTN_SPLIT=0
+  // Split kernel (attention_kernel_split<Tk>), the default for both: ViT-B/16 (T = 197 -> 208 keys) and the extra-token
+  // plan of ViT-L/14 (256 keys).  An aliased O accumulator moves to columns [64, 128) of its S region.  CLM_ATTN_SPLIT=0
   // keeps the alternate-chunk kernel for A/B runs.
   // (read on every call so that one test process can exercise both kernels)
   const char* split_env = getenv("CLM_ATTN_SPLIT");
   const int split_on = !split_env ? 1 : (split_env[0] == '0' ? 0 : (split_env[0] == '2' ? 2 : 1));
   int split = 0;
-  // (measured, tools/attn_bench.py at batch 1024: ViT-L/14 0.723 ms against 0.783 ms; ViT-B/16's 208-key shape
-  // is 2.5 % SLOWER with it — 0.397 against 0.387 ms — so that shape takes it only on request, CLM_ATTN_SPLIT=2)
+  // (measured, tools/attn_bench.py at batch 1024: ViT-L/14 0.723 ms against 0.783 ms.  ViT-B/16's 208-key shape was
+  // 2.5 % slower with it -- 0.397 against 0.387 ms -- while the MMA issue sat in ELECT / R2UR loops; with the issuers
+  // on the uniform datapath it is 3.3 % faster, 0.348 against 0.359 ms, and takes it by default too.  1 and 2 mean
+  // the same now.)
   if (split_on && !causal && p.blocks == 1 && p.nslots == 2 && p.mtiles == 2 &&
-      (p.Tk == 256 || (p.Tk == 208 && split_on == 2)) &&
+      (p.Tk == 256 || p.Tk == 208) &&
       T > p.Tk - 16 && (p.stage_out == 1 || p.mtiles * 128 <= p.Tp)) {
     split = p.Tk;
     if (p.o_alias0) p.o_col0 = p.s_col0 + 64;

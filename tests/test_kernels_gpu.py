@@ -322,13 +322,13 @@ def test_attention(cuda_device, batch, tokens, heads, causal):
 @pytest.mark.parametrize("batch,tokens,heads", [
     (2, 257, 16),   # ViT-L/14: split kernel by default, alternate-chunk kernel with CLM_ATTN_SPLIT=0
     (40, 257, 8),   # several items per CTA: stage ring, TMEM region reuse, the four extra-token warps
-    (37, 197, 12),  # ViT-B/16 (208 keys): alternate-chunk kernel by default, split kernel with CLM_ATTN_SPLIT=2
+    (37, 197, 12),  # ViT-B/16 (208 keys): split kernel by default as well, alternate-chunk kernel with CLM_ATTN_SPLIT=0
     (3, 200, 2),    # 208 keys with 8 masked ones
     (5, 193, 3),    # the smallest T of the 208-key plan
 ])
 def test_attention_split_and_alternate_kernels(cuda_device, monkeypatch, mode, batch, tokens, heads):
     """Both softmax kernels for the ViT shapes (attention_kernel_split<Tk> and attention_kernel) against fp32:
-    CLM_ATTN_SPLIT is read on every call (0 = never split, 2 = split for 208 and 256 keys)."""
+    CLM_ATTN_SPLIT is read on every call (0 = never split, 1 / 2 / unset = split for 208 and 256 keys)."""
     monkeypatch.setenv("CLM_ATTN_SPLIT", mode)
     D = heads * 64
     qkv = _randn((batch * tokens, 3 * D), 41, 1.5).bfloat16()

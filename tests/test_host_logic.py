@@ -339,3 +339,56 @@ def test_train_lora_mirror_host_logic(tmp_path):
     # the shipped YAML carries the reference's training section
     cfg = TL.load_lora_training_config(os.path.join(ROOT, "clip_lora_match_b200", "config", "lora_config.yaml"))
     assert cfg["training"]["temperature"] == 0.07 and cfg["training"]["batch_size"] == 8
+
+
+def test_layernorm_fold_algebra_on_the_host():
+    """kernels.fold_layernorm prepares what clm_gemm_ln_epi consumes (include/clm_b200.h): with Wg = W diag(gamma)
+    rounded to bf16, col_sums of the ROUNDED values and bias' = b + W beta, the epilogue formula
+    rstd (h Wg^T - mean col_sums) + bias' is LayerNorm(h) W^T + b up to the rounding of Wg -- and exactly the
+    LayerNorm without affine part applied to Wg.  Same for the LoRA down-projection in its 1 / rstd form, whose constant
+    (A beta)(sB)^T moves into the wide GEMM's bias."""
+    from clip_lora_match_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(0)
+    D, N, r = 256, 96, 16
+    h = (torch.randn((40, D), generator=g) * 1.5 + torch.randn((40, 1), generator=g) * 3.0).bfloat16().float()
+    w = torch.randn((N, D), generator=g) * D ** -0.5
+    gamma = torch.rand((D,), generator=g) + 0.5
+    beta = torch.randn((D,), generator=g) * 0.1
+    bias = torch.randn((N,), generator=g)
+    wg, cs, bf = K.fold_layernorm(w, gamma, beta, bias)
+    assert wg.dtype == torch.bfloat16 and cs.dtype == torch.float32 and bf.dtype == torch.float32
+    assert torch.equal(cs, wg.float().sum(dim=1))
+    mu = h.mean(dim=1, keepdim=True)
+    rstd = torch.rsqrt(h.var(dim=1, unbiased=False, keepdim=True) + 1e-5)
+    folded = rstd * (h @ wg.float().T - mu * cs) + bf
+    plain_ln = torch.nn.functional.layer_norm(h, (D,), None, None, 1e-5)
+    assert torch.allclose(folded, plain_ln @ wg.float().T + bf, atol=2e-4, rtol=1e-4)          # exact in Wg
+    ref = torch.nn.functional.layer_norm(h, (D,), gamma, beta, 1e-5) @ w.T + bias
+    assert torch.allclose(folded, ref, atol=3e-2, rtol=1e-2)                                    # bf16 rounding of Wg
+    # LoRA: u = (LN(h) A^T - A beta) / rstd from ln_mode 2 (no bias); t = rstd u + A beta
+    a = torch.randn((r, D), generator=g) * D ** -0.5
+    sb = torch.randn((N, r), generator=g) * 0.1
+    ag, s_a, c_a = K.fold_layernorm(a, gamma, beta)
+    u = h @ ag.float().T - mu * s_a
+    t_ref = torch.nn.functional.layer_norm(h, (D,), gamma, beta, 1e-5) @ a.T
+    assert torch.allclose(rstd * u + c_a, t_ref, atol=3e-2, rtol=1e-2)
+    # the wide GEMM: acc = h Wg^T + u (sB)^T, epilogue rstd (acc - mean col_sums) + (bias' + (sB)(A beta))
+    out = rstd * (h @ wg.float().T + u @ sb.T - mu * cs) + (bf + sb @ c_a)
+    assert torch.allclose(out, ref + t_ref @ sb.T, atol=4e-2, rtol=1e-2)
+
+
+def test_residual_stream_option_names():
+    from clip_lora_match_b200.models import clip_model as CM
+
+    assert CM.DEFAULT_RESIDUAL_DTYPE == "bfloat16"
+    assert CM._residual_dtype_name("bf16") == "bfloat16" and CM._residual_dtype_name("fp32") == "float32"
+    assert CM._residual_dtype_name(torch.bfloat16) == "bfloat16" and CM._residual_dtype_name(torch.float32) == "float32"
+    with pytest.raises(ValueError):
+        CM._residual_dtype_name("float16")
+    os.environ["CLM_RESIDUAL_DTYPE"] = "float32"
+    try:
+        assert CM._residual_dtype_name(None) == "float32"
+    finally:
+        del os.environ["CLM_RESIDUAL_DTYPE"]
+    assert CM._residual_dtype_name(None) == CM.DEFAULT_RESIDUAL_DTYPE

@@ -269,6 +269,40 @@ def test_built_library_contains_tcgen05_and_tma_sass():
     assert not re.search(r"\bHMMA\.", sass) and "WGMMA" not in sass
 
 
+def test_mma_issue_loops_stay_on_the_uniform_datapath():
+    """a tcgen05.mma issued under `if (lane == 0)` compiles into an ELECT / R2UR.BROADCAST / branch loop
+    per instruction (~20 SASS instructions between two UTCHMMA), and that paced every GEMM of the encoder.  With
+    warp-uniform operands and one elect.sync per k-block the four MMAs are back to back.  Guard it in the SASS of the
+    built library: in every GEMM / search / attention kernel the typical distance between consecutive UTCHMMA is a few
+    instructions, and no R2UR.BROADCAST sits between two of them inside a k-block."""
+    import shutil
+    import subprocess
+
+    from clip_lora_match_b200 import _lib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    _lib.load()
+    sass = subprocess.run([cuobjdump, "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    checked = 0
+    for fn in re.split(r"\n\s*Function : ", sass)[1:]:
+        name = fn.split("\n", 1)[0]
+        ins = [l for l in fn.split("\n") if re.search(r"/\*[0-9a-f]{4,6}\*/", l)]
+        idx = [i for i, l in enumerate(ins) if "UTCHMMA" in l]
+        if len(idx) < 4:
+            continue
+        gaps = sorted(b - a for a, b in zip(idx, idx[1:]))
+        median = gaps[len(gaps) // 2]
+        assert median <= 6, f"{name}: {median} instructions between consecutive UTCHMMA (waterfall issue loop?)"
+        if "gemm_kernel" in name or "search_kernel" in name:
+            # the four MMAs of a k-block: nothing but uniform-datapath work in between
+            between = "\n".join(ins[idx[0]:idx[3] + 1])
+            assert "R2UR.BROADCAST" not in between and "ELECT" not in between, name
+        checked += 1
+    assert checked >= 10, f"only {checked} kernels with tcgen05.mma found"
+
+
 def test_extra_token_attention_decomposition_is_exact_softmax_attention():
     """The ViT-L/14 attention plan (csrc/clm_attention.cu, T = 128k + 1) restated in torch: tensor cores take the
     256 x 256 block (P rounded to bf16), the class token's key enters each row through one dot product (row max,
